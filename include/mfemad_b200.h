@@ -1,0 +1,148 @@
+/* mfemad_b200.h -- C ABI of the B200-native AD assembly hot path.
+ *
+ * Drop-in boundary for the element-level AD assembly path of dohyun-cse/mfem-ad
+ * (reference file:line cited per entry point).  The reference sits behind MFEM's
+ * per-element virtuals
+ *     GetElementEnergy / AssembleElementVector / AssembleElementGrad
+ * (src/_ad_intg.hpp:108-135 single space, :245-276 block), called once per
+ * element by NonlinearForm / BlockNonlinearForm.  Per-element virtual calls
+ * cannot feed a GPU, so this ABI is the whole-mesh batched equivalent: the
+ * element loop, gather (GetElementVDofs/GetSubVector), the integrator body and
+ * the scatter (AddElementVector / AddSubMatrix) are one call.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every vector/array argument may be a HOST or
+ *    a DEVICE pointer (detected with cudaPointerGetAttributes).  Host pointers
+ *    are staged through device buffers owned by the integrator (H2D/D2H copies
+ *    inside the call); device pointers are used in place on the context stream.
+ *  - the caller owns every array it passes; handles own their workspaces and
+ *    are destroyed explicitly.
+ *  - error convention: every function returns 0 on success, non-zero on error;
+ *    madb_last_error() gives the message.  (The reference aborts through
+ *    MFEM_VERIFY / MFEM_ABORT, src/ad_native.hpp:167, src/ad_native.cpp:111-117;
+ *    an MFEM adapter turns non-zero into MFEM_ABORT -- see INTEGRATION.md.)
+ *  - not re-entrant per context, like the reference's integrators (mutable
+ *    scratch, src/_ad_intg.hpp:80-93): one host thread + one CUDA stream per
+ *    context / GPU.  Functional parameters are re-read at every call
+ *    (ex2.cpp:98 mutates eps, ex4.cpp:187 alpha between solves).
+ *  - all element-local orderings are LEXICOGRAPHIC (x fastest); an MFEM adapter
+ *    applies TensorBasisElement::GetDofMap() as MFEM's ElementRestriction does.
+ */
+#ifndef MFEMAD_B200_H
+#define MFEMAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct madb_ctx madb_ctx;
+typedef struct madb_mesh madb_mesh;
+typedef struct madb_space madb_space;
+typedef struct madb_functional madb_functional;
+typedef struct madb_integrator madb_integrator;
+
+/* ADEval flags: src/_ad_intg.hpp:24-36 (same bit values) */
+enum
+{
+   MADB_QVALUE = 1 << 0,
+   MADB_VALUE = 1 << 1,
+   MADB_GRAD = 1 << 2,
+   MADB_DIV = 1 << 3,
+   MADB_CURL = 1 << 4,
+   MADB_HESSIAN = 1 << 5,
+   MADB_VECTOR = 1 << 6,
+   MADB_VECFE = 1 << 7
+};
+enum { MADB_BASIS_H1 = 0 /* H1_FECollection: closed Gauss-Lobatto */, MADB_BASIS_L2 = 1 /* L2_FECollection: open Gauss-Legendre */ };
+enum { MADB_BYNODES = 0, MADB_BYVDIM = 1 }; /* mfem::Ordering */
+enum { MADB_ROLE_INPUT = 0, MADB_ROLE_PARAM = 1 };
+
+int madb_version(void);
+const char *madb_last_error(void);
+
+/* One context per GPU / rank (replaces nothing in the reference: it has no device). */
+int madb_ctx_create(int device, madb_ctx **out);
+int madb_ctx_destroy(madb_ctx *ctx);
+int madb_ctx_sync(madb_ctx *ctx);
+/* cudaStream_t of the context, so callers can bracket calls with CUDA events. */
+void *madb_ctx_stream(madb_ctx *ctx);
+
+/* Geometry: replaces ElementTransformation::SetIntPoint / Weight / InverseJacobian
+ * as used at src/ad_intg.hpp:236-237 (Tr.Weight()) and inside CalcPhysDShape
+ * (:137).  Tensor-product elements (quads dim=2, hexes dim=3) with the order-1
+ * isoparametric map through the element vertices.
+ *   e2n    [ne * 2^dim]  vertex ids, lexicographic per element
+ *   coords [nnodes*dim]  xyzxyz... */
+int madb_mesh_create(madb_ctx *ctx, int dim, int ne, const int32_t *e2n, int nnodes, const double *coords,
+                     madb_mesh **out);
+int madb_mesh_destroy(madb_mesh *m);
+
+/* FiniteElementSpace view: element -> scalar dof map, basis and vdim.
+ * Replaces fes->GetElementVDofs + FiniteElement::CalcShape/CalcDShape tables
+ * (src/ad_intg.hpp:132-137).  e2l [ne * (order+1)^dim], lexicographic. */
+int madb_space_create(madb_ctx *ctx, madb_mesh *mesh, int basis, int order, int vdim, int ordering, int ndofs,
+                      const int32_t *e2l, madb_space **out);
+int madb_space_destroy(madb_space *s);
+
+/* ADFunction objects (src/ad_native.hpp:137-190, :413-691; src/pg.hpp; src/mmto.hpp).
+ * kind: "mass" "diffusion" "elasticity" "minsurf" "obstacle" "gradobstacle"
+ *       "diff" "pg" "lambdapg" "shannon" "fermidirac" "hellinger" "simplex"
+ *       "simp" "paramcompliance" "empty" "ex0", or any kind registered by a plugin.
+ * params: the functional's own run-time constants (e.g. minsurf: eps; elasticity:
+ *         lambda, mu; fermidirac: lower, upper; pg: alpha; simp: E[0..n-1], p).
+ * iparams: structural integers that select the compiled variant (pg: primal_idx). */
+int madb_functional_create(madb_ctx *ctx, const char *kind, int nparams, const double *params, int niparams,
+                           const int *iparams, int nchildren, madb_functional *const *children,
+                           madb_functional **out);
+int madb_functional_set_params(madb_functional *f, int nparams, const double *params);
+int madb_functional_destroy(madb_functional *f);
+
+/* AD layer on the device at n points (ADFunction::operator(), Gradient, Hessian:
+ * src/ad_native.cpp:181-230).  x [npts*n_input]; qprm [npts*n_qprm] or NULL;
+ * outputs may be NULL: value [npts], grad [npts*n], hess [npts*n*n] (symmetric). */
+int madb_functional_eval(madb_ctx *ctx, madb_functional *f, int n_input, int npts, const double *x,
+                         const double *qprm, double *value, double *grad, double *hess);
+
+/* AD(Block)NonlinearFormIntegrator<modes...>(f, ir) attached to its form
+ * (src/_ad_intg.hpp:71-155, :157-327).  fields: spaces[i] with ADEval modes[i];
+ * roles[i] = MADB_ROLE_INPUT for a differentiated unknown (a block of x), or
+ * MADB_ROLE_PARAM for a GridFunction parameter of the functional's Evaluator
+ * (src/ad_native.cpp:166-171), e.g. psi_k of ADPGFunctional (src/pg.hpp:110).
+ * quad_order < 0 selects the default 2*max_order+2 (src/_ad_intg.hpp:99-105, :298-313). */
+int madb_integrator_create(madb_ctx *ctx, int nfields, madb_space *const *spaces, const int *modes,
+                           const int *roles, madb_functional *f, int quad_order, madb_integrator **out);
+int madb_integrator_destroy(madb_integrator *I);
+
+/* sizes: total dofs of the concatenated input blocks, quadrature points per element */
+int madb_integrator_sizes(madb_integrator *I, int64_t *ntotal, int *nq_el, int *ncolors);
+
+/* Evaluator sources that vary in space (src/ad_native.hpp:56-61):
+ * GridFunction parameter of field `field` (dof vector of that space), and
+ * QuadratureFunction parameters  qf[(e*nq + q)*nqf + k]  (GetValues(ElementNo, ip.index)). */
+int madb_integrator_set_param_field(madb_integrator *I, int field, const double *dofs);
+int madb_integrator_set_param_qf(madb_integrator *I, int nqf, const double *qf);
+
+/* NonlinearForm::SetEssentialTrueDofs: Mult zeroes y there; GetGradient
+ * eliminates rows+columns with unit diagonal [MFEM-upstream, SURVEY a32]. */
+int madb_integrator_set_essential(madb_integrator *I, int n, const int32_t *dofs);
+
+/* NonlinearForm::GetEnergy -> sum_e GetElementEnergy (src/ad_intg.hpp:157-199, :469-530) */
+int madb_integrator_energy(madb_integrator *I, const double *x, double *energy);
+/* NonlinearForm::Mult -> AssembleElementVector (src/ad_intg.hpp:202-257, :533-619) */
+int madb_integrator_mult(madb_integrator *I, const double *x, double *y);
+/* Sparsity of GetGradient: full element connectivity, sorted columns.
+ * Call with rowptr = colidx = NULL for the sizes. */
+int madb_integrator_pattern(madb_integrator *I, int64_t *nrows, int64_t *nnz, int32_t *rowptr, int32_t *colidx);
+/* NonlinearForm::GetGradient -> AssembleElementGrad (src/ad_intg.hpp:260-334, :622-729) */
+int madb_integrator_grad_assemble(madb_integrator *I, const double *x, double *vals);
+/* residual + Jacobian at the same state in one pass (one Newton iteration's assembly) */
+int madb_integrator_assemble(madb_integrator *I, const double *x, double *y, double *vals);
+/* matrix-free Jacobian action y = J(x) v (no reference equivalent; config 3) */
+int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,303 @@
+"""mfem-ad element-level AD assembly hot path, B200-native.
+
+Python face of the C ABI in include/mfemad_b200.h (ctypes; no torch types cross
+the boundary).  The classes mirror the reference's interface for this path:
+
+    Functional        <-> ADFunction and subclasses (src/ad_native.hpp, src/pg.hpp, src/mmto.hpp)
+    Integrator        <-> AD(Block)NonlinearFormIntegrator<modes...> attached to a
+                          (Block)NonlinearForm: Mult / GetGradient / GetEnergy
+    PGStepSizeRule    <-> src/pg.hpp:10-34, src/pg.cpp:4-54
+
+There is NO CPU fallback: without the compiled CUDA library or without a GPU
+every compute entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmadb.so")
+
+QVALUE, VALUE, GRAD, DIV, CURL, HESSIAN, VECTOR, VECFE = (1 << i for i in range(8))
+BASIS_H1, BASIS_L2 = 0, 1
+BYNODES, BYVDIM = 0, 1
+ROLE_INPUT, ROLE_PARAM = 0, 1
+
+_lib = None
+
+
+class MadbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads libmadb.so; fails loudly when the CUDA extension is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MadbError("CUDA extension %s is missing: run `python mfem-ad_b200/build.py` "
+                            "(there is no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, dp, ip = C.c_void_p, C.c_void_p, C.c_void_p
+        pp = C.POINTER(C.c_void_p)
+        L.madb_version.restype = C.c_int
+        L.madb_last_error.restype = C.c_char_p
+        L.madb_ctx_create.argtypes = [C.c_int, pp]
+        L.madb_ctx_destroy.argtypes = [vp]
+        L.madb_ctx_sync.argtypes = [vp]
+        L.madb_ctx_stream.restype = C.c_void_p
+        L.madb_ctx_stream.argtypes = [vp]
+        L.madb_mesh_create.argtypes = [vp, C.c_int, C.c_int, ip, C.c_int, dp, pp]
+        L.madb_mesh_destroy.argtypes = [vp]
+        L.madb_space_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, pp]
+        L.madb_space_destroy.argtypes = [vp]
+        L.madb_functional_create.argtypes = [vp, C.c_char_p, C.c_int, dp, C.c_int, ip, C.c_int, pp, pp]
+        L.madb_functional_set_params.argtypes = [vp, C.c_int, dp]
+        L.madb_functional_destroy.argtypes = [vp]
+        L.madb_functional_eval.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        L.madb_integrator_create.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, pp]
+        L.madb_integrator_destroy.argtypes = [vp]
+        L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.madb_integrator_set_param_field.argtypes = [vp, C.c_int, dp]
+        L.madb_integrator_set_param_qf.argtypes = [vp, C.c_int, dp]
+        L.madb_integrator_set_essential.argtypes = [vp, C.c_int, ip]
+        L.madb_integrator_energy.argtypes = [vp, dp, C.POINTER(C.c_double)]
+        L.madb_integrator_mult.argtypes = [vp, dp, dp]
+        L.madb_integrator_pattern.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), ip, ip]
+        L.madb_integrator_grad_assemble.argtypes = [vp, dp, dp]
+        L.madb_integrator_assemble.argtypes = [vp, dp, dp, dp]
+        L.madb_integrator_grad_mult.argtypes = [vp, dp, dp, dp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise MadbError(lib().madb_last_error().decode())
+
+
+def _ptr(a):
+    """numpy array -> host pointer; torch tensor -> its data pointer (host or device); int passes through."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    return int(a)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        _check(lib().madb_ctx_create(device, C.byref(h)))
+        self.h, self.device = h, device
+
+    def sync(self):
+        _check(lib().madb_ctx_sync(self.h))
+
+    @property
+    def stream(self):
+        return lib().madb_ctx_stream(self.h)
+
+    def __del__(self):
+        try:
+            lib().madb_ctx_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Mesh:
+    def __init__(self, ctx, mesh):
+        e2n, coords = _i32(mesh["e2n"]), _f64(mesh["coords"])
+        h = C.c_void_p()
+        _check(lib().madb_mesh_create(ctx.h, mesh["dim"], e2n.shape[0], e2n.ctypes.data, coords.shape[0],
+                                      coords.ctypes.data, C.byref(h)))
+        self.h, self.ctx, self.dim, self.ne = h, ctx, mesh["dim"], e2n.shape[0]
+
+    def __del__(self):
+        try:
+            lib().madb_mesh_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Space:
+    def __init__(self, ctx, mesh, space):
+        e2l = _i32(space["e2l"])
+        h = C.c_void_p()
+        _check(lib().madb_space_create(ctx.h, mesh.h, space["basis"], space["order"], space.get("vdim", 1),
+                                       space.get("ordering", BYNODES), space["ndofs"], e2l.ctypes.data, C.byref(h)))
+        self.h, self.mesh, self.desc = h, mesh, space
+        self.vsize = space["ndofs"] * space.get("vdim", 1)
+
+    def __del__(self):
+        try:
+            lib().madb_space_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Functional:
+    """ADFunction handle: kind + run-time constants + structural integers + children."""
+
+    def __init__(self, ctx, kind, params=(), iparams=(), children=()):
+        self.ctx, self.kind, self.children = ctx, kind, list(children)
+        p, ip_ = _f64(list(params)), _i32(list(iparams))
+        ch = (C.c_void_p * max(len(children), 1))(*[c.h for c in children])
+        h = C.c_void_p()
+        _check(lib().madb_functional_create(ctx.h, kind.encode(), p.size, p.ctypes.data, ip_.size, ip_.ctypes.data,
+                                            len(children), ch, C.byref(h)))
+        self.h = h
+
+    def set_params(self, params):
+        p = _f64(list(params))
+        _check(lib().madb_functional_set_params(self.h, p.size, p.ctypes.data))
+
+    def eval(self, x, qprm=None):
+        """value, gradient, Hessian at points x[npts, n] on the device (src/ad_native.cpp:181-230)."""
+        x = _f64(np.atleast_2d(x))
+        npts, n = x.shape
+        q = _f64(qprm) if qprm is not None else None
+        v, g, h = np.zeros(npts), np.zeros((npts, n)), np.zeros((npts, n, n))
+        _check(lib().madb_functional_eval(self.ctx.h, self.h, n, npts, x.ctypes.data, _ptr(q), v.ctypes.data,
+                                          g.ctypes.data, h.ctypes.data))
+        return v, g, h
+
+    def __del__(self):
+        try:
+            lib().madb_functional_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Integrator:
+    """A (Block)NonlinearForm holding one AD(Block)NonlinearFormIntegrator.
+
+    fields: list of (Space, mode[, role]); input fields are the blocks of x in order."""
+
+    def __init__(self, ctx, fields, functional, quad_order=-1):
+        self.ctx, self.fn = ctx, functional
+        self.fields = [(f[0], f[1], f[2] if len(f) > 2 else ROLE_INPUT) for f in fields]
+        n = len(self.fields)
+        sp = (C.c_void_p * n)(*[f[0].h for f in self.fields])
+        modes = _i32([f[1] for f in self.fields])
+        roles = _i32([f[2] for f in self.fields])
+        h = C.c_void_p()
+        _check(lib().madb_integrator_create(ctx.h, n, sp, modes.ctypes.data, roles.ctypes.data, functional.h,
+                                            quad_order, C.byref(h)))
+        self.h = h
+        nt, nq, nc = C.c_int64(), C.c_int(), C.c_int()
+        _check(lib().madb_integrator_sizes(h, C.byref(nt), C.byref(nq), C.byref(nc)))
+        self.ntotal, self.nq_el, self.ncolors = nt.value, nq.value, nc.value
+        self._pattern = None
+        self._keep = []
+
+    def set_param_field(self, field, dofs):
+        if isinstance(dofs, np.ndarray):
+            dofs = _f64(dofs)
+        self._keep.append(dofs)
+        _check(lib().madb_integrator_set_param_field(self.h, field, _ptr(dofs)))
+
+    def set_param_qf(self, qf):
+        qf = _f64(qf)
+        _check(lib().madb_integrator_set_param_qf(self.h, qf.shape[-1], qf.ctypes.data))
+
+    def set_essential(self, dofs):
+        d = _i32(dofs)
+        _check(lib().madb_integrator_set_essential(self.h, d.size, d.ctypes.data))
+
+    def energy(self, x):
+        x = _f64(x) if isinstance(x, np.ndarray) else x
+        e = C.c_double()
+        _check(lib().madb_integrator_energy(self.h, _ptr(x), C.byref(e)))
+        return e.value
+
+    def mult(self, x, y=None):
+        if isinstance(x, np.ndarray):
+            x = _f64(x)
+            y = np.empty(self.ntotal) if y is None else y
+        _check(lib().madb_integrator_mult(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def pattern(self):
+        if self._pattern is None:
+            nr, nnz = C.c_int64(), C.c_int64()
+            _check(lib().madb_integrator_pattern(self.h, C.byref(nr), C.byref(nnz), None, None))
+            rowptr, colidx = np.zeros(nr.value + 1, dtype=np.int32), np.zeros(nnz.value, dtype=np.int32)
+            _check(lib().madb_integrator_pattern(self.h, None, None, rowptr.ctypes.data, colidx.ctypes.data))
+            self._pattern = (rowptr, colidx)
+        return self._pattern
+
+    @property
+    def nnz(self):
+        return self.pattern()[1].size
+
+    def grad(self, x, vals=None):
+        if isinstance(x, np.ndarray):
+            x = _f64(x)
+            vals = np.empty(self.nnz) if vals is None else vals
+        _check(lib().madb_integrator_grad_assemble(self.h, _ptr(x), _ptr(vals)))
+        return vals
+
+    def assemble(self, x, y=None, vals=None):
+        """residual + Jacobian values at the same state (one Newton iteration's assembly)."""
+        if isinstance(x, np.ndarray):
+            x = _f64(x)
+            y = np.empty(self.ntotal) if y is None else y
+            vals = np.empty(self.nnz) if vals is None else vals
+        _check(lib().madb_integrator_assemble(self.h, _ptr(x), _ptr(y), _ptr(vals)))
+        return y, vals
+
+    def grad_mult(self, x, v, y=None):
+        if isinstance(x, np.ndarray):
+            x, v = _f64(x), _f64(v)
+            y = np.empty(self.ntotal) if y is None else y
+        _check(lib().madb_integrator_grad_mult(self.h, _ptr(x), _ptr(v), _ptr(y)))
+        return y
+
+    def __del__(self):
+        try:
+            lib().madb_integrator_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PGStepSizeRule:
+    """src/pg.hpp:10-34, src/pg.cpp:4-54 (host scalar; stays on the host)."""
+    CONSTANT, POLY, EXP, DOUBLE_EXP, INVALID = range(5)
+
+    def __init__(self, rule_type, alpha0=1.0, max_alpha=1e6, ratio=-1.0, ratio2=-1.0):
+        if not rule_type < self.INVALID:
+            raise MadbError("PGStepSizeRule: Invalid rule type")
+        if not alpha0 > 0:
+            raise MadbError("PGStepSizeRule: alpha0 must be positive")
+        if not max_alpha >= alpha0:
+            raise MadbError("PGStepSizeRule: max_alpha must be greater than or equal to alpha0")
+        if rule_type == self.POLY and not ratio > 0:
+            raise MadbError("PGStepSizeRule: ratio must be positive for POLY rule")
+        if rule_type == self.EXP and not ratio > 1:
+            raise MadbError("PGStepSizeRule: ratio must be greater than 1 for EXP rule")
+        if rule_type == self.DOUBLE_EXP and not (ratio > 1 and ratio2 > 1):
+            raise MadbError("PGStepSizeRule: ratio and ratio2 must be greater than 1 for DOUBLE_EXP rule")
+        self.rule_type, self.alpha0, self.max_alpha, self.ratio, self.ratio2 = rule_type, alpha0, max_alpha, ratio, ratio2
+
+    def get(self, it):
+        a = np.float64(self.alpha0)
+        with np.errstate(over="ignore"):  # std::pow overflows to inf, then min() caps it
+            if self.rule_type == self.POLY:
+                a = a * np.power(np.float64(it + 1), self.ratio)
+            elif self.rule_type == self.EXP:
+                a = a * np.power(np.float64(self.ratio), np.float64(it))
+            elif self.rule_type == self.DOUBLE_EXP:
+                a = a * np.power(np.float64(self.ratio), np.power(np.float64(self.ratio2), np.float64(it)))
+        return float(min(a, self.max_alpha))

@@ -1,0 +1,25 @@
+// Pointwise AD instances (ex0 known answers, entropy maps).
+#include "madb_eval.cuh"
+#include "madb_functionals.cuh"
+using namespace madb;
+
+using MinS2 = MinimalSurfaceEnergy<2>;
+using Simplex5 = SimplexEntropy<5>;
+using Simplex3 = SimplexEntropy<3>;
+using Hell2 = HellingerEntropy<2>;
+using SIMP5 = SIMPFunction<5>;
+using Elast2 = LinearElasticityEnergy<2>;
+using Elast3 = LinearElasticityEnergy<3>;
+using PGObsFD = PGFunctional<ObstacleEnergy<2>, FermiDiracEntropy, 0>;
+
+MADB_EVAL_INSTANCE("ex0", Ex0Function)
+MADB_EVAL_INSTANCE("minsurf", MinS2)
+MADB_EVAL_INSTANCE("shannon", ShannonEntropy)
+MADB_EVAL_INSTANCE("fermidirac", FermiDiracEntropy)
+MADB_EVAL_INSTANCE("hellinger", Hell2)
+MADB_EVAL_INSTANCE("simplex", Simplex5)
+MADB_EVAL_INSTANCE("simplex", Simplex3)
+MADB_EVAL_INSTANCE("simp", SIMP5)
+MADB_EVAL_INSTANCE("elasticity", Elast2)
+MADB_EVAL_INSTANCE("elasticity", Elast3)
+MADB_EVAL_INSTANCE("pg:0[obstacle,fermidirac]", PGObsFD)

@@ -1,0 +1,14 @@
+// Fused-kernel instances: 2-D scalar H1 space, ADEval::GRAD (ex1, ex2, config 2).
+#include "madb_functionals.cuh"
+#include "madb_registry.cuh"
+using namespace madb;
+
+using Q1 = Config<2, 3, Field<2, 1, EV_GRAD>>; // order 1, default rule 2p+2 -> 3x3 points
+using Q2 = Config<2, 4, Field<3, 1, EV_GRAD>>; // order 2 -> 4x4 points (config 2)
+using Diff2 = DiffusionEnergy<2, 0>;
+using MinS2 = MinimalSurfaceEnergy<2>;
+
+MADB_INSTANCE("diffusion:0", Diff2, Q1, true)
+MADB_INSTANCE("diffusion:0", Diff2, Q2, true)
+MADB_INSTANCE("minsurf", MinS2, Q1, true)
+MADB_INSTANCE("minsurf", MinS2, Q2, true)

@@ -1,0 +1,352 @@
+// madb_functionals.cuh -- device-side pointwise functionals (the AD_IMPL bodies).
+//
+// Each functional is a trivially-copyable struct
+//    static constexpr int N_INPUT   number of differentiated inputs
+//    static constexpr int N_PARAM   run-time constants, re-read at every call
+//                                   (the reference mutates them between calls:
+//                                   ex2.cpp:98 eps, ex4.cpp:187 alpha)
+//    static constexpr int N_QPRM    per-quadrature-point parameters
+//                                   (= Evaluator::val, src/ad_native.cpp:120-179)
+//    void load(const double *p)     consume N_PARAM constants (own first, then children)
+//    template <class T> T operator()(const T *x, const double *qp) const
+// evaluated with T = double (energy), AD<N,1> (residual), AD<N,2> (Jacobian).
+// Composition (ADPGFunctional, DiffEnergy, ...) is static (templates) instead
+// of the reference's virtual nested calls (src/pg.hpp:210, src/ad_native.hpp:523).
+#pragma once
+#include "madb_ad.cuh"
+
+namespace madb
+{
+
+// ex0.cpp:20  f = sin(x0) e^{x1} + x2^3
+struct Ex0Function
+{
+   static constexpr int N_INPUT = 3, N_PARAM = 0, N_QPRM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      return sin(x[0]) * exp(x[1]) + pow(x[2], 3.0);
+   }
+};
+
+// src/ad_native.hpp:413-420
+template <int N> struct MassEnergy
+{
+   static constexpr int N_INPUT = N, N_PARAM = 0, N_QPRM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      T s = x[0] * x[0];
+#pragma unroll
+      for (int i = 1; i < N; i++) { s += x[i] * x[i]; }
+      return 0.5 * s;
+   }
+};
+
+// src/ad_native.hpp:421-481.  KDIM selects the K kind at compile time
+// (0 none, 1 scalar, DIM diagonal, DIM*DIM full, column-major) instead of the
+// per-point size dispatch of the reference.  K is a constant here;
+// DiffusionEnergyQ reads it from the per-point parameters.
+template <int DIM, int KDIM, bool QP = false> struct DiffusionEnergy
+{
+   static constexpr int N_INPUT = DIM, N_PARAM = QP ? 0 : KDIM, N_QPRM = QP ? KDIM : 0;
+   double K[KDIM > 0 ? KDIM : 1];
+   MADB_HD void load(const double *p)
+   {
+      if constexpr (!QP) { for (int i = 0; i < KDIM; i++) { K[i] = p[i]; } }
+   }
+   template <class T> MADB_HD T operator()(const T *gradu, const double *qp) const
+   {
+      const double *Kp = QP ? qp : K;
+      if constexpr (KDIM == 0 || KDIM == 1)
+      {
+         T s = gradu[0] * gradu[0];
+#pragma unroll
+         for (int i = 1; i < DIM; i++) { s += gradu[i] * gradu[i]; }
+         if constexpr (KDIM == 0) { return 0.5 * s; }
+         else { return (0.5 * Kp[0]) * s; }
+      }
+      else if constexpr (KDIM == DIM)
+      {
+         T result = Kp[0] * gradu[0] * gradu[0];
+#pragma unroll
+         for (int i = 1; i < DIM; i++) { result += Kp[i] * gradu[i] * gradu[i]; }
+         return 0.5 * result;
+      }
+      else
+      {
+         T result = T();
+#pragma unroll
+         for (int j = 0; j < DIM; j++)
+         {
+#pragma unroll
+            for (int i = 0; i < DIM; i++) { result += Kp[i + DIM * j] * gradu[i] * gradu[j]; }
+         }
+         return 0.5 * result;
+      }
+   }
+};
+
+// src/ad_native.hpp:527-566 ; gradu[i*dim + j]
+template <int DIM> struct LinearElasticityEnergy
+{
+   static constexpr int N_INPUT = DIM * DIM, N_PARAM = 2, N_QPRM = 0;
+   double lambda, mu;
+   MADB_HD void load(const double *p) { lambda = p[0]; mu = p[1]; }
+   template <class T> MADB_HD static T body(const T *gradu, double lambda, double mu)
+   {
+      T divnorm = gradu[0];
+#pragma unroll
+      for (int i = 1; i < DIM; i++) { divnorm += gradu[i * DIM + i]; }
+      divnorm = divnorm * divnorm;
+      T h1_norm = T();
+#pragma unroll
+      for (int i = 0; i < DIM; i++)
+      {
+#pragma unroll
+         for (int j = 0; j < DIM; j++)
+         {
+            T symm = 0.5 * (gradu[i * DIM + j] + gradu[j * DIM + i]);
+            h1_norm += symm * symm;
+         }
+      }
+      return 0.5 * lambda * divnorm + mu * h1_norm;
+   }
+   template <class T> MADB_HD T operator()(const T *gradu, const double *) const { return body(gradu, lambda, mu); }
+};
+
+// ex2.cpp:12-24
+template <int DIM> struct MinimalSurfaceEnergy
+{
+   static constexpr int N_INPUT = DIM, N_PARAM = 1, N_QPRM = 0;
+   double eps;
+   MADB_HD void load(const double *p) { eps = p[0]; }
+   template <class T> MADB_HD T operator()(const T *gradu, const double *) const
+   {
+      T h1_norm = gradu[0] * gradu[0];
+#pragma unroll
+      for (int i = 1; i < DIM; i++) { h1_norm += gradu[i] * gradu[i]; }
+      return sqrt(h1_norm + 1.0) + eps * h1_norm;
+   }
+};
+
+// ex4.cpp:15-28 ; x = [u, grad u]
+template <int DIM> struct ObstacleEnergy
+{
+   static constexpr int N_INPUT = DIM + 1, N_PARAM = 0, N_QPRM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      T result = x[1] * x[1];
+#pragma unroll
+      for (int i = 2; i < DIM + 1; i++) { result += x[i] * x[i]; }
+      return result * 0.5;
+   }
+};
+
+// ex5.cpp:15-22
+template <int DIM> struct GradientObstacleEnergy
+{
+   static constexpr int N_INPUT = DIM, N_PARAM = 0, N_QPRM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      T s = x[0] * x[0];
+#pragma unroll
+      for (int i = 1; i < DIM; i++) { s += x[i] * x[i]; }
+      return s * 0.5;
+   }
+};
+
+// src/_dof_pg.hpp:9-15
+template <int N> struct EmptyEnergy
+{
+   static constexpr int N_INPUT = N, N_PARAM = 0, N_QPRM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *, const double *) const { return T(); }
+};
+
+// src/ad_native.hpp:483-525: energy(x - target); target is a per-point parameter
+template <class E> struct DiffEnergy
+{
+   static constexpr int N_INPUT = E::N_INPUT, N_PARAM = E::N_PARAM, N_QPRM = E::N_INPUT + E::N_QPRM;
+   E energy;
+   MADB_HD void load(const double *p) { energy.load(p); }
+   template <class T> MADB_HD T operator()(const T *x, const double *qp) const
+   {
+      T diff[N_INPUT];
+#pragma unroll
+      for (int i = 0; i < N_INPUT; i++) { diff[i] = x[i] - qp[i]; }
+      return energy(diff, qp + N_INPUT);
+   }
+};
+
+// ---------------------------------------------------------------------------
+// Dual entropies (src/pg.hpp:253-376): gradients are the latent->primal maps
+// ---------------------------------------------------------------------------
+// src/pg.hpp:259-278
+struct ShannonEntropy
+{
+   static constexpr int N_INPUT = 1, N_PARAM = 2, N_QPRM = 0;
+   double bound, sign;
+   MADB_HD void load(const double *p) { bound = p[0]; sign = p[1]; }
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      return sign * (exp(x[0] * sign)) + bound * x[0];
+   }
+};
+
+// src/pg.hpp:281-322.  Parameters are the constructor arguments (lower, upper);
+// the reference binds member upper_bound to evaluator slot 0 (= lower argument)
+// and lower_bound to slot 1 (:291-295), so effectively shift = upper argument,
+// scale = lower - upper.  Replicated here.
+struct FermiDiracEntropy
+{
+   static constexpr int N_INPUT = 1, N_PARAM = 2, N_QPRM = 0;
+   double shift, scale;
+   MADB_HD void load(const double *p)
+   {
+      const double upper_bound = p[0], lower_bound = p[1];
+      shift = lower_bound;         // :305
+      scale = upper_bound - shift; // :306
+   }
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      T z = x[0] * scale;
+      if (z > 0) { return z + log(1.0 + exp(-z)) + shift * x[0]; }
+      else { return log(1.0 + exp(z)) + shift * x[0]; }
+   }
+};
+
+// src/pg.hpp:324-342 ; QP: the bound is a spatial coefficient (ex5.cpp:114-117)
+template <int DIM, bool QP = false> struct HellingerEntropy
+{
+   static constexpr int N_INPUT = DIM, N_PARAM = QP ? 0 : 1, N_QPRM = QP ? 1 : 0;
+   double scale;
+   MADB_HD void load(const double *p) { if constexpr (!QP) { scale = p[0]; } }
+   template <class T> MADB_HD T operator()(const T *x, const double *qp) const
+   {
+      const double s = QP ? qp[0] : scale;
+      T xx = x[0] * x[0];
+#pragma unroll
+      for (int i = 1; i < DIM; i++) { xx += x[i] * x[i]; }
+      return sqrt(1 + xx * (s * s));
+   }
+};
+
+// src/pg.hpp:347-376 (log-sum-exp; max chain with tie averaging)
+template <int N> struct SimplexEntropy
+{
+   static constexpr int N_INPUT = N, N_PARAM = 1, N_QPRM = 0;
+   double scale;
+   MADB_HD void load(const double *p) { scale = p[0]; }
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      T maxval = x[0];
+#pragma unroll
+      for (int i = 1; i < N; i++) { maxval = max(maxval, x[i]); }
+      T sum_exp = exp(x[0] - maxval);
+#pragma unroll
+      for (int i = 1; i < N; i++) { sum_exp += exp(x[i] - maxval); }
+      return scale * (maxval + log(sum_exp));
+   }
+};
+
+// ---------------------------------------------------------------------------
+// Proximal-Galerkin functionals (src/pg.hpp:58-243)
+//   L(u,psi) = f(x) + (sum_j x[primal_idx+j]*(psi_j - psi_k,j) - E*(psi)) / alpha
+// x = [f inputs, psi]; psi_k is a per-point parameter (first N_E slots of qp).
+// ---------------------------------------------------------------------------
+template <class F, class E, int PRIMAL_IDX> struct PGFunctional
+{
+   static constexpr int NF = F::N_INPUT, NE = E::N_INPUT;
+   static constexpr int N_INPUT = NF + NE, N_PARAM = 1 + F::N_PARAM + E::N_PARAM;
+   static constexpr int N_QPRM = NE + F::N_QPRM + E::N_QPRM;
+   double alpha;
+   F f;
+   E entropy;
+   MADB_HD void load(const double *p)
+   {
+      alpha = p[0];
+      f.load(p + 1);
+      entropy.load(p + 1 + F::N_PARAM);
+   }
+   template <class T> MADB_HD T operator()(const T *x_psi, const double *qp) const
+   {
+      const T *psi = x_psi + NF;
+      const double *psi_k = qp;
+      T cross_entropy = x_psi[PRIMAL_IDX] * (psi[0] - psi_k[0]);
+#pragma unroll
+      for (int j = 1; j < NE; j++) { cross_entropy += x_psi[PRIMAL_IDX + j] * (psi[j] - psi_k[j]); }
+      T dual_entropy_sum = entropy(psi, qp + NE + F::N_QPRM);
+      return f(x_psi, qp + NE) + (cross_entropy - dual_entropy_sum) / alpha;
+   }
+};
+
+// src/pg.hpp:216-243: lambda-form  f(x) + x.lambda - E*(psi_k + alpha*lambda)/alpha
+template <class F, class E, int PRIMAL_IDX> struct LambdaPGFunctional
+{
+   static constexpr int NF = F::N_INPUT, NE = E::N_INPUT;
+   static constexpr int N_INPUT = NF + NE, N_PARAM = 1 + F::N_PARAM + E::N_PARAM;
+   static constexpr int N_QPRM = NE + F::N_QPRM + E::N_QPRM;
+   double alpha;
+   F f;
+   E entropy;
+   MADB_HD void load(const double *p)
+   {
+      alpha = p[0];
+      f.load(p + 1);
+      entropy.load(p + 1 + F::N_PARAM);
+   }
+   template <class T> MADB_HD T operator()(const T *x_lambda, const double *qp) const
+   {
+      const T *lambda = x_lambda + NF;
+      T psi[NE];
+      T cross_entropy = x_lambda[PRIMAL_IDX] * lambda[0];
+#pragma unroll
+      for (int j = 0; j < NE; j++)
+      {
+         psi[j] = qp[j] + alpha * lambda[j];
+         if (j > 0) { cross_entropy += x_lambda[PRIMAL_IDX + j] * lambda[j]; }
+      }
+      T dual_entropy_sum = entropy(psi, qp + NE + F::N_QPRM);
+      return f(x_lambda, qp + NE) + cross_entropy - dual_entropy_sum / alpha;
+   }
+};
+
+// ---------------------------------------------------------------------------
+// mmto pieces (src/mmto.hpp)
+// ---------------------------------------------------------------------------
+// src/mmto.hpp:9-28  sum_i E_i x_i^p
+template <int N> struct SIMPFunction
+{
+   static constexpr int N_INPUT = N, N_PARAM = N + 1, N_QPRM = 0;
+   double E[N];
+   double p;
+   MADB_HD void load(const double *q)
+   {
+      for (int i = 0; i < N; i++) { E[i] = q[i]; }
+      p = q[N];
+   }
+   template <class T> MADB_HD T operator()(const T *x, const double *) const
+   {
+      T result = E[0] * pow(x[0], p);
+#pragma unroll
+      for (int i = 1; i < N; i++) { result += E[i] * pow(x[i], p); }
+      return result;
+   }
+};
+
+// src/mmto.hpp:154-189: elastic energy whose lambda, mu are per-point parameters
+// (evaluator slots dim*dim, dim*dim+1 -- :169-170; here the first two qp slots)
+template <int DIM> struct ParametrizedCompliance
+{
+   static constexpr int N_INPUT = DIM * DIM, N_PARAM = 0, N_QPRM = 2;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *gradu, const double *qp) const
+   {
+      return LinearElasticityEnergy<DIM>::body(gradu, qp[0], qp[1]);
+   }
+};
+
+} // namespace madb

@@ -1,0 +1,160 @@
+// madb_host.hpp -- host-side objects behind the C ABI (include/mfemad_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace madb
+{
+
+enum { MODE_RES = 1, MODE_JAC = 2, MODE_ACT = 4, MODE_ENERGY = 8 };
+
+// ---- kernel registry -------------------------------------------------------------
+// Fused kernels are templates on <functional type, element configuration>.  Each
+// instantiation registers a launcher under a string key built from the same
+// run-time descriptors the C ABI receives, e.g.
+//    "minsurf|d2q4|3.1.4.0"          (kind | DIM,NQ1D | nd1d.vdim.mode.role per field)
+// A missing key is a loud error naming the MADB_INSTANCE line to add.
+struct LaunchCtx
+{
+   cudaStream_t stream;
+   int ne, stride, ncolors;
+   const int *color_off; // host, [ncolors+1] sorted-element offsets
+   const int *e2n, *vmap, *pmap, *e2csr;
+   const double *coords;
+   const double *pdata[8];
+   const double *qf;
+   const double *x, *v;
+   double *y, *vals, *energy;
+   int write_y, write_vals;
+   const double *fparams; // host
+   // host tables, laid out exactly as madb::Tables<Cfg>
+   const double *phi, *dphi, *gdphi, *w;
+};
+
+struct KernelOps
+{
+   int (*launch)(const LaunchCtx &, int mode);
+   int n_input, n_fparam, n_qprm, n_field_qprm, nvd, ndof_all, nq, ntab, dim;
+};
+
+std::map<std::string, KernelOps> &registry();
+struct Registrar
+{
+   Registrar(const std::string &key, const KernelOps &ops);
+};
+
+// ---- 1-D bases and rules ---------------------------------------------------------
+void gauss_legendre_01(int n, std::vector<double> &x, std::vector<double> &w);
+void gauss_lobatto_01(int n, std::vector<double> &x);
+void lagrange_tables(const std::vector<double> &nodes, const std::vector<double> &pts,
+                     std::vector<double> &B, std::vector<double> &G); // [npts][nnodes]
+inline int rule_npts_1d(int order) { return (order | 1) / 2 + 1; } // IntRules.Get(...): SURVEY a18
+
+// ---- objects ---------------------------------------------------------------------
+struct Ctx
+{
+   int device = 0;
+   cudaStream_t stream = nullptr;
+};
+
+struct Mesh
+{
+   Ctx *ctx;
+   int dim, ne, geom_order, nnodes;
+   std::vector<int> e2n;       // [ne][2^dim] lexicographic
+   std::vector<double> coords; // [nnodes][dim]
+   double *d_coords = nullptr;
+};
+
+enum { BASIS_H1 = 0, BASIS_L2 = 1 };
+enum { ORD_BYNODES = 0, ORD_BYVDIM = 1 };
+
+struct Space
+{
+   Ctx *ctx;
+   Mesh *mesh;
+   int basis, order, vdim, ordering;
+   int ndofs;            // scalar dofs
+   std::vector<int> e2l; // [ne][(order+1)^dim] lexicographic scalar dof ids
+   int nd_el() const
+   {
+      int n = 1;
+      for (int d = 0; d < mesh->dim; d++) { n *= (order + 1); }
+      return n;
+   }
+   int vsize() const { return ndofs * vdim; }
+};
+
+struct Functional
+{
+   std::string kind;           // e.g. "minsurf", "pg"
+   std::vector<double> params; // own constants
+   std::vector<int> iparams;   // structural integers (become part of the key)
+   std::vector<Functional *> children;
+   std::string key() const;
+   void flat_params(std::vector<double> &out) const;
+};
+
+struct FieldDesc
+{
+   Space *space;
+   unsigned mode;
+   int role; // ROLE_INPUT / ROLE_PARAM
+};
+
+struct Integrator
+{
+   Ctx *ctx = nullptr;
+   Mesh *mesh = nullptr;
+   std::vector<FieldDesc> fields;
+   Functional *fn = nullptr;
+   int quad_order = -1, nq1d = 0, nq = 0;
+   std::string key;
+   KernelOps ops;
+
+   // sizes
+   int nvd = 0, ndof_all = 0, npd = 0;
+   long ntotal = 0;        // size of the concatenated vector
+   std::vector<long> goff; // block offset of each input field
+   int ne = 0, stride = 0;
+
+   // colouring / ordering
+   std::vector<int> perm;      // sorted position -> element
+   std::vector<int> color_off; // [ncolors+1]
+
+   // pattern (host) -- built lazily
+   bool have_pattern = false;
+   std::vector<int> rowptr, colidx;
+
+   // device data
+   int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
+   int *d_rowptr = nullptr, *d_colidx = nullptr;
+   double *d_energy = nullptr, *d_esum = nullptr;
+   double *d_x = nullptr, *d_v = nullptr, *d_y = nullptr, *d_vals = nullptr; // staging for host callers
+   std::vector<double *> d_pstage;                                           // staging of parameter fields
+   double *d_qf = nullptr;
+   size_t qf_count = 0;
+   std::vector<const double *> pdata; // device pointers of the parameter fields (per field)
+   std::vector<double> phi, dphi, gdphi, w;
+
+   // essential dofs
+   int ness = 0;
+   int *d_ess = nullptr;
+
+   ~Integrator();
+};
+
+const char *last_error();
+void set_error(const std::string &s);
+
+// pattern / colouring helpers (madb_pattern.cpp)
+void build_vdofs(const Integrator &I, int e, std::vector<int> &vd);
+void color_elements(const Integrator &I, std::vector<int> &color, int &ncolors);
+void build_pattern(Integrator &I);
+void build_e2csr(const Integrator &I, const std::vector<int> &color, std::vector<int> &e2csr);
+
+} // namespace madb

@@ -1,0 +1,535 @@
+// madb_kernels.cuh -- whole-mesh batched element kernels (one thread per element).
+//
+// One launch per element colour replaces the reference's per-element virtual
+// calls from MFEM's element loop:
+//   gather  (GetElementVDofs + GetSubVector)               -> vmap loads
+//   geometry (Tr.SetIntPoint / Weight / InverseJacobian)   -> from 2^DIM vertices
+//   CalcInputShapes + x = allshapes^T elfun                -> src/ad_intg.hpp:118-154,:242
+//   f.Gradient / f.Hessian                                 -> one AD<N,1>/AD<N,2> pass
+//   elvect += allshapes*jac, elmat += B H B^T              -> src/ad_intg.hpp:245-255,:307-331,:698-727
+//   AddElementVector / AddSubMatrix                        -> direct scatter through vmap / e2csr
+// Physical shapes are never formed: the gradient and Hessian are pulled back to
+// reference coordinates (g^ = w T^T g, H^ = w T^T H T with T = blockdiag(1, J^-T)),
+// so the test/trial contraction uses the constant reference tables only.
+//
+// Determinism: elements of one colour share no dof, so the scatter uses plain
+// loads/stores; colours run in stream order, hence every y[i] / vals[p] is
+// summed in a fixed (colour) order.  Bit 31 of a map entry marks the first
+// contribution to that slot: it stores instead of accumulating, so neither y
+// nor vals needs a memset.
+#pragma once
+#include "madb_config.cuh"
+#include "madb_host.hpp"
+#include <cuda_runtime.h>
+
+namespace madb
+{
+
+
+template <class Func, class Cfg> struct AsmArgs
+{
+   static constexpr int NQF = Func::N_QPRM - Cfg::N_FIELD_QPRM;
+   static_assert(Func::N_INPUT == Cfg::N_INPUT, "functional n_input must match shapedim*vdim summed over the input spaces");
+   static_assert(NQF >= 0, "functional expects fewer per-point parameters than the parameter fields supply");
+   int begin, end; // sorted-element range of this launch (one colour)
+   int stride;     // padded element count = SoA stride of all maps
+   int write_y, write_vals;
+   const int *e2n;       // [NGN][stride] vertex ids, lexicographic
+   const double *coords; // [nnodes][DIM]
+   const int *vmap;      // [NVD][stride] index into x / y (bit 31: first touch)
+   const int *pmap;      // [NDOF_ALL-NVD][stride] indices into pdata
+   const double *pdata[Cfg::NF]; // parameter-field vectors (null for input fields)
+   const double *qf;     // [NQF][NQ][stride] per-point parameters given as quadrature functions
+   const int *e2csr;     // [NVD*NVD][stride] CSR positions (bit 31: first touch)
+   const double *x;
+   const double *v; // MODE_ACT: direction
+   double *y;
+   double *vals;
+   double *energy; // [stride] per-element energies (sorted order)
+   double fparams[Func::N_PARAM > 0 ? Func::N_PARAM : 1];
+   Tables<Cfg> tab;
+};
+
+template <int DIM> MADB_HD void invert(const double (&J)[DIM][DIM], double (&Ji)[DIM][DIM], double &det)
+{
+   if constexpr (DIM == 1)
+   {
+      det = J[0][0];
+      Ji[0][0] = 1.0 / det;
+   }
+   else if constexpr (DIM == 2)
+   {
+      det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      const double t = 1.0 / det;
+      Ji[0][0] = J[1][1] * t;
+      Ji[0][1] = -J[0][1] * t;
+      Ji[1][0] = -J[1][0] * t;
+      Ji[1][1] = J[0][0] * t;
+   }
+   else
+   {
+      const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+      const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+      const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+      det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+      const double t = 1.0 / det;
+      Ji[0][0] = c00 * t;
+      Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * t;
+      Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * t;
+      Ji[1][0] = c01 * t;
+      Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * t;
+      Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * t;
+      Ji[2][0] = c02 * t;
+      Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * t;
+      Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * t;
+   }
+}
+
+MADB_HD constexpr int symidx(int a, int b) { return a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b; }
+
+/// Everything the functional needs at one quadrature point, then the
+/// contribution of that point to the element vector / matrix.
+template <class Func, class Cfg, int MODE>
+__device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q, const int t,
+                                       const double (&X)[Cfg::NGN][Cfg::DIM],
+                                       const double (&u)[Cfg::NDOF_ALL],
+                                       const double (&vdir)[(MODE & MODE_ACT) ? Cfg::NVD : 1],
+                                       const Func &f,
+                                       double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
+                                       double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1],
+                                       double &energy)
+{
+   constexpr int DIM = Cfg::DIM, NF = Cfg::NF, N = Cfg::N_INPUT;
+   using Args = AsmArgs<Func, Cfg>;
+
+   // ---- geometry: J = sum_k X_k (x) dN_k/dxi ; Weight = det J ; J^-1 ------------
+   double J[DIM][DIM];
+#pragma unroll
+   for (int i = 0; i < DIM; i++)
+   {
+#pragma unroll
+      for (int j = 0; j < DIM; j++) { J[i][j] = 0.0; }
+   }
+#pragma unroll
+   for (int k = 0; k < Cfg::NGN; k++)
+   {
+#pragma unroll
+      for (int j = 0; j < DIM; j++)
+      {
+         const double g = a.tab.gdphi[q][k][j];
+#pragma unroll
+         for (int i = 0; i < DIM; i++) { J[i][j] = fma(X[k][i], g, J[i][j]); }
+      }
+   }
+   double Ji[DIM][DIM], detJ;
+   invert<DIM>(J, Ji, detJ);
+   const double w = a.tab.w[q] * detJ; // ip.weight * Tr.Weight()
+
+   // ---- inputs x (physical) and field parameters ---------------------------------
+   double xin[N];
+   double qp[Func::N_QPRM > 0 ? Func::N_QPRM : 1];
+   static_for<NF>([&](auto F)
+   {
+      constexpr int fi = decltype(F)::value;
+      using Fd = typename Cfg::template field<fi>;
+      constexpr int nd = Cfg::template nd<fi>(), sd = Cfg::template sd<fi>();
+      constexpr int toff = Cfg::template toff<fi>(), doff = Cfg::template doff<fi>();
+#pragma unroll
+      for (int c = 0; c < Fd::VDIM; c++)
+      {
+         double val = 0.0, rg[DIM];
+#pragma unroll
+         for (int k = 0; k < DIM; k++) { rg[k] = 0.0; }
+#pragma unroll
+         for (int i = 0; i < nd; i++)
+         {
+            const double ui = u[doff + c * nd + i];
+            if constexpr (Fd::HAS_VALUE) { val = fma(a.tab.phi[q][toff + i], ui, val); }
+            if constexpr (Fd::HAS_GRAD)
+            {
+#pragma unroll
+               for (int k = 0; k < DIM; k++) { rg[k] = fma(a.tab.dphi[q][toff + i][k], ui, rg[k]); }
+            }
+         }
+         double *dst = Cfg::template is_input<fi>() ? (xin + Cfg::template xoff<fi>()) : (qp + Cfg::template poff<fi>());
+         int slot = c * sd;
+         if constexpr (Fd::HAS_VALUE) { dst[slot++] = val; }
+         if constexpr (Fd::HAS_GRAD)
+         {
+            // physical gradient: gshape = dshape * J^-1  (CalcPhysDShape)
+#pragma unroll
+            for (int j = 0; j < DIM; j++)
+            {
+               double s = 0.0;
+#pragma unroll
+               for (int k = 0; k < DIM; k++) { s = fma(Ji[k][j], rg[k], s); }
+               dst[slot + j] = s;
+            }
+         }
+      }
+   });
+#pragma unroll
+   for (int k = 0; k < Args::NQF; k++) { qp[Cfg::N_FIELD_QPRM + k] = a.qf[((size_t)k * Cfg::NQ + q) * a.stride + t]; }
+
+   if constexpr (MODE == MODE_ENERGY)
+   {
+      energy += f(xin, qp) * w; // src/ad_intg.hpp:196
+      return;
+   }
+   else
+   {
+      constexpr int ORDER = (MODE & (MODE_JAC | MODE_ACT)) ? 2 : 1;
+      using T = AD<N, ORDER>;
+      T xs[N];
+#pragma unroll
+      for (int m = 0; m < N; m++) { xs[m] = ad_seed<N, ORDER>(xin[m], m); }
+      const T res = f(xs, qp);
+
+      // ---- pull back to reference coordinates: g^ = w T^T g ; H^ = w T^T H T ------
+      ZD gh[N];
+      ZD Hh[(ORDER >= 2) ? N : 1][(ORDER >= 2) ? N : 1];
+      static_for<NF>([&](auto F)
+      {
+         constexpr int fi = decltype(F)::value;
+         using Fd = typename Cfg::template field<fi>;
+         if constexpr (Cfg::template is_input<fi>())
+         {
+            constexpr int sd = Cfg::template sd<fi>(), xo = Cfg::template xoff<fi>();
+            constexpr int gofs = Fd::HAS_VALUE ? 1 : 0;
+#pragma unroll
+            for (int c = 0; c < Fd::VDIM; c++)
+            {
+               const int base = xo + c * sd;
+               if constexpr (Fd::HAS_VALUE) { gh[base] = zmulc(res.G(base), w); }
+               if constexpr (Fd::HAS_GRAD)
+               {
+#pragma unroll
+                  for (int k = 0; k < DIM; k++)
+                  {
+                     ZD s {0.0, true};
+#pragma unroll
+                     for (int j = 0; j < DIM; j++) { s = zfmac(res.G(base + gofs + j), Ji[k][j], s); }
+                     gh[base + gofs + k] = zmulc(s, w);
+                  }
+               }
+            }
+         }
+      });
+      if constexpr (ORDER >= 2)
+      {
+         // M = H T (columns), then H^ = w T^T M (rows)
+         ZD M[N][N];
+         static_for<NF>([&](auto F)
+         {
+            constexpr int fi = decltype(F)::value;
+            using Fd = typename Cfg::template field<fi>;
+            if constexpr (Cfg::template is_input<fi>())
+            {
+               constexpr int sd = Cfg::template sd<fi>(), xo = Cfg::template xoff<fi>();
+               constexpr int gofs = Fd::HAS_VALUE ? 1 : 0;
+#pragma unroll
+               for (int c = 0; c < Fd::VDIM; c++)
+               {
+                  const int base = xo + c * sd;
+#pragma unroll
+                  for (int m = 0; m < N; m++)
+                  {
+                     if constexpr (Fd::HAS_VALUE) { M[m][base] = res.H(symidx_h<N>(m, base)); }
+                     if constexpr (Fd::HAS_GRAD)
+                     {
+#pragma unroll
+                        for (int k = 0; k < DIM; k++)
+                        {
+                           ZD s {0.0, true};
+#pragma unroll
+                           for (int j = 0; j < DIM; j++) { s = zfmac(res.H(symidx_h<N>(m, base + gofs + j)), Ji[k][j], s); }
+                           M[m][base + gofs + k] = s;
+                        }
+                     }
+                  }
+               }
+            }
+         });
+         static_for<NF>([&](auto F)
+         {
+            constexpr int fi = decltype(F)::value;
+            using Fd = typename Cfg::template field<fi>;
+            if constexpr (Cfg::template is_input<fi>())
+            {
+               constexpr int sd = Cfg::template sd<fi>(), xo = Cfg::template xoff<fi>();
+               constexpr int gofs = Fd::HAS_VALUE ? 1 : 0;
+#pragma unroll
+               for (int c = 0; c < Fd::VDIM; c++)
+               {
+                  const int base = xo + c * sd;
+#pragma unroll
+                  for (int n = 0; n < N; n++)
+                  {
+                     if constexpr (Fd::HAS_VALUE) { Hh[base][n] = zmulc(M[base][n], w); }
+                     if constexpr (Fd::HAS_GRAD)
+                     {
+#pragma unroll
+                        for (int k = 0; k < DIM; k++)
+                        {
+                           ZD s {0.0, true};
+#pragma unroll
+                           for (int j = 0; j < DIM; j++) { s = zfmac(M[base + gofs + j][n], Ji[k][j], s); }
+                           Hh[base + gofs + k][n] = zmulc(s, w);
+                        }
+                     }
+                  }
+               }
+            }
+         });
+      }
+
+      // ---- MODE_ACT: y^ = H^ v^ with v^ the reference-space inputs of the direction --
+      ZD yh[(MODE & MODE_ACT) ? N : 1];
+      if constexpr ((MODE & MODE_ACT) != 0)
+      {
+         double vh[N];
+         static_for<NF>([&](auto F)
+         {
+            constexpr int fi = decltype(F)::value;
+            using Fd = typename Cfg::template field<fi>;
+            if constexpr (Cfg::template is_input<fi>())
+            {
+               constexpr int nd = Cfg::template nd<fi>(), sd = Cfg::template sd<fi>();
+               constexpr int toff = Cfg::template toff<fi>(), vo = Cfg::template voff<fi>(), xo = Cfg::template xoff<fi>();
+#pragma unroll
+               for (int c = 0; c < Fd::VDIM; c++)
+               {
+                  double val = 0.0, rg[DIM];
+#pragma unroll
+                  for (int k = 0; k < DIM; k++) { rg[k] = 0.0; }
+#pragma unroll
+                  for (int i = 0; i < nd; i++)
+                  {
+                     const double vi = vdir[vo + c * nd + i];
+                     if constexpr (Fd::HAS_VALUE) { val = fma(a.tab.phi[q][toff + i], vi, val); }
+                     if constexpr (Fd::HAS_GRAD)
+                     {
+#pragma unroll
+                        for (int k = 0; k < DIM; k++) { rg[k] = fma(a.tab.dphi[q][toff + i][k], vi, rg[k]); }
+                     }
+                  }
+                  int slot = xo + c * sd;
+                  if constexpr (Fd::HAS_VALUE) { vh[slot++] = val; }
+                  if constexpr (Fd::HAS_GRAD)
+                  {
+#pragma unroll
+                     for (int k = 0; k < DIM; k++) { vh[slot + k] = rg[k]; }
+                  }
+               }
+            }
+         });
+#pragma unroll
+         for (int m = 0; m < N; m++)
+         {
+            ZD s {0.0, true};
+#pragma unroll
+            for (int n = 0; n < N; n++) { s = zfmac(Hh[m][n], vh[n], s); }
+            yh[m] = s;
+         }
+      }
+
+      // ---- test-function contraction: elvect += B g^ ; elmat += B H^ B^T ----------
+      static_for<NF>([&](auto FB)
+      {
+         constexpr int fb = decltype(FB)::value;
+         using Fb = typename Cfg::template field<fb>;
+         if constexpr (Cfg::template is_input<fb>())
+         {
+            constexpr int ndb = Cfg::template nd<fb>(), sdb = Cfg::template sd<fb>();
+            constexpr int tob = Cfg::template toff<fb>(), vob = Cfg::template voff<fb>(), xob = Cfg::template xoff<fb>();
+#pragma unroll
+            for (int jb = 0; jb < ndb; jb++)
+            {
+               // reference basis vector of trial/test dof jb: [phi?, dphi/dxi_k?]
+               double bv[sdb];
+               {
+                  int s = 0;
+                  if constexpr (Fb::HAS_VALUE) { bv[s++] = a.tab.phi[q][tob + jb]; }
+                  if constexpr (Fb::HAS_GRAD)
+                  {
+#pragma unroll
+                     for (int k = 0; k < DIM; k++) { bv[s + k] = a.tab.dphi[q][tob + jb][k]; }
+                  }
+               }
+#pragma unroll
+               for (int cb = 0; cb < Fb::VDIM; cb++)
+               {
+                  const int b = vob + cb * ndb + jb;
+                  const int sb = xob + cb * sdb;
+                  if constexpr ((MODE & MODE_RES) != 0)
+                  {
+                     ZD s {0.0, true};
+#pragma unroll
+                     for (int k = 0; k < sdb; k++) { s = zfmac(gh[sb + k], bv[k], s); }
+                     if (!s.z) { r[b] += s.v; }
+                  }
+                  if constexpr ((MODE & MODE_ACT) != 0)
+                  {
+                     ZD s {0.0, true};
+#pragma unroll
+                     for (int k = 0; k < sdb; k++) { s = zfmac(yh[sb + k], bv[k], s); }
+                     if (!s.z) { r[b] += s.v; }
+                  }
+                  if constexpr ((MODE & MODE_JAC) != 0)
+                  {
+                     // tcol[m] = sum_k H^[m][sb+k] bv[k]
+                     ZD tcol[N];
+#pragma unroll
+                     for (int m = 0; m < N; m++)
+                     {
+                        ZD s {0.0, true};
+#pragma unroll
+                        for (int k = 0; k < sdb; k++) { s = zfmac(Hh[m][sb + k], bv[k], s); }
+                        tcol[m] = s;
+                     }
+                     static_for<NF>([&](auto FA)
+                     {
+                        constexpr int fa = decltype(FA)::value;
+                        using Fa = typename Cfg::template field<fa>;
+                        if constexpr (Cfg::template is_input<fa>() && fa <= fb)
+                        {
+                           constexpr int nda = Cfg::template nd<fa>(), sda = Cfg::template sd<fa>();
+                           constexpr int toa = Cfg::template toff<fa>(), voa = Cfg::template voff<fa>(), xoa = Cfg::template xoff<fa>();
+#pragma unroll
+                           for (int ca = 0; ca < Fa::VDIM; ca++)
+                           {
+#pragma unroll
+                              for (int ia = 0; ia < nda; ia++)
+                              {
+                                 const int aa = voa + ca * nda + ia;
+                                 if (aa <= b)
+                                 {
+                                    const int sa = xoa + ca * sda;
+                                    ZD s {0.0, true};
+                                    int k0 = 0;
+                                    if constexpr (Fa::HAS_VALUE) { s = zfmac(tcol[sa], a.tab.phi[q][toa + ia], s); k0 = 1; }
+                                    if constexpr (Fa::HAS_GRAD)
+                                    {
+#pragma unroll
+                                       for (int k = 0; k < DIM; k++) { s = zfmac(tcol[sa + k0 + k], a.tab.dphi[q][toa + ia][k], s); }
+                                    }
+                                    if (!s.z) { A[symidx(aa, b)] += s.v; }
+                                 }
+                              }
+                           }
+                        }
+                     });
+                  }
+               }
+            }
+         }
+      });
+   }
+}
+
+template <class Func, class Cfg, int MODE, bool UNROLLQ>
+__global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs<Func, Cfg> a)
+{
+   constexpr int DIM = Cfg::DIM, NVD = Cfg::NVD;
+   const int t = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= a.end) { return; }
+
+   // ---- gather: vertices, dofs of all fields ---------------------------------------
+   double X[Cfg::NGN][DIM];
+#pragma unroll
+   for (int k = 0; k < Cfg::NGN; k++)
+   {
+      const int n = a.e2n[(size_t)k * a.stride + t];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) { X[k][d] = a.coords[(size_t)n * DIM + d]; }
+   }
+   double u[Cfg::NDOF_ALL];
+   double vdir[(MODE & MODE_ACT) ? NVD : 1];
+   static_for<Cfg::NF>([&](auto F)
+   {
+      constexpr int fi = decltype(F)::value;
+      using Fd = typename Cfg::template field<fi>;
+      constexpr int n = Cfg::template nd<fi>() * Fd::VDIM, doff = Cfg::template doff<fi>();
+      if constexpr (Cfg::template is_input<fi>())
+      {
+         constexpr int vo = Cfg::template voff<fi>();
+#pragma unroll
+         for (int i = 0; i < n; i++)
+         {
+            const int idx = a.vmap[(size_t)(vo + i) * a.stride + t] & 0x7fffffff;
+            u[doff + i] = a.x[idx];
+            if constexpr ((MODE & MODE_ACT) != 0) { vdir[vo + i] = a.v[idx]; }
+         }
+      }
+      else
+      {
+         constexpr int po = doff - Cfg::template voff<fi>();
+#pragma unroll
+         for (int i = 0; i < n; i++) { u[doff + i] = a.pdata[fi][a.pmap[(size_t)(po + i) * a.stride + t]]; }
+      }
+   });
+
+   Func f;
+   f.load(a.fparams);
+
+   double r[(MODE & (MODE_RES | MODE_ACT)) ? NVD : 1];
+   double A[(MODE & MODE_JAC) ? Cfg::NSYM : 1];
+   double energy = 0.0;
+   if constexpr ((MODE & (MODE_RES | MODE_ACT)) != 0)
+   {
+#pragma unroll
+      for (int i = 0; i < NVD; i++) { r[i] = 0.0; }
+   }
+   if constexpr ((MODE & MODE_JAC) != 0)
+   {
+#pragma unroll
+      for (int i = 0; i < Cfg::NSYM; i++) { A[i] = 0.0; }
+   }
+
+   if constexpr (UNROLLQ)
+   {
+#pragma unroll
+      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE>(a, q, t, X, u, vdir, f, r, A, energy); }
+   }
+   else
+   {
+#pragma unroll 1
+      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE>(a, q, t, X, u, vdir, f, r, A, energy); }
+   }
+
+   // ---- scatter --------------------------------------------------------------------
+   if constexpr (MODE == MODE_ENERGY) { a.energy[t] = energy; }
+   if constexpr ((MODE & (MODE_RES | MODE_ACT)) != 0)
+   {
+      if (a.write_y)
+      {
+#pragma unroll
+         for (int i = 0; i < NVD; i++)
+         {
+            const int m = a.vmap[(size_t)i * a.stride + t];
+            const int idx = m & 0x7fffffff;
+            a.y[idx] = (m < 0) ? r[i] : a.y[idx] + r[i];
+         }
+      }
+   }
+   if constexpr ((MODE & MODE_JAC) != 0)
+   {
+      if (a.write_vals)
+      {
+#pragma unroll
+         for (int i = 0; i < NVD; i++)
+         {
+#pragma unroll
+            for (int j = 0; j < NVD; j++)
+            {
+               const int m = a.e2csr[(size_t)(i * NVD + j) * a.stride + t];
+               const int p = m & 0x7fffffff;
+               const double val = A[symidx(i, j)];
+               a.vals[p] = (m < 0) ? val : a.vals[p] + val;
+            }
+         }
+      }
+   }
+}
+
+} // namespace madb

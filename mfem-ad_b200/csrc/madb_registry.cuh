@@ -1,0 +1,93 @@
+// madb_registry.cuh -- glue between the typed kernels and the run-time registry.
+#pragma once
+#include "madb_host.hpp"
+#include "madb_kernels.cuh"
+
+#include <cstring>
+#include <string>
+
+namespace madb
+{
+
+template <class Cfg> std::string config_key()
+{
+   std::string k = "d" + std::to_string(Cfg::DIM) + "q" + std::to_string(Cfg::NQ1D);
+   static_for<Cfg::NF>([&](auto F)
+   {
+      constexpr int fi = decltype(F)::value;
+      using Fd = typename Cfg::template field<fi>;
+      k += "|" + std::to_string(Fd::ND1D) + "." + std::to_string(Fd::VDIM) + "." +
+           std::to_string((int)(Fd::MODE & (EV_VALUE | EV_GRAD))) + "." + std::to_string(Fd::ROLE);
+   });
+   return k;
+}
+
+template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &L, int mode)
+{
+   using Args = AsmArgs<Func, Cfg>;
+   static Args a; // ~tens of KB: keep off the stack; calls are single-threaded per context
+   a.stride = L.stride;
+   a.write_y = L.write_y;
+   a.write_vals = L.write_vals;
+   a.e2n = L.e2n;
+   a.coords = L.coords;
+   a.vmap = L.vmap;
+   a.pmap = L.pmap;
+   for (int f = 0; f < Cfg::NF; f++) { a.pdata[f] = L.pdata[f]; }
+   a.qf = L.qf;
+   a.e2csr = L.e2csr;
+   a.x = L.x;
+   a.v = L.v;
+   a.y = L.y;
+   a.vals = L.vals;
+   a.energy = L.energy;
+   for (int i = 0; i < Func::N_PARAM; i++) { a.fparams[i] = L.fparams[i]; }
+   std::memcpy(a.tab.phi, L.phi, sizeof(a.tab.phi));
+   std::memcpy(a.tab.dphi, L.dphi, sizeof(a.tab.dphi));
+   std::memcpy(a.tab.gdphi, L.gdphi, sizeof(a.tab.gdphi));
+   std::memcpy(a.tab.w, L.w, sizeof(a.tab.w));
+   const int nlaunch = (mode == MODE_ENERGY) ? 1 : L.ncolors;
+   for (int c = 0; c < nlaunch; c++)
+   {
+      a.begin = (mode == MODE_ENERGY) ? 0 : L.color_off[c];
+      a.end = (mode == MODE_ENERGY) ? L.ne : L.color_off[c + 1];
+      const int n = a.end - a.begin;
+      if (n <= 0) { continue; }
+      const int grid = (n + 127) / 128;
+      switch (mode)
+      {
+         case MODE_RES: k_element<Func, Cfg, MODE_RES, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
+         case MODE_RES | MODE_JAC: k_element<Func, Cfg, MODE_RES | MODE_JAC, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
+         case MODE_ACT: k_element<Func, Cfg, MODE_ACT, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
+         case MODE_ENERGY: k_element<Func, Cfg, MODE_ENERGY, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
+         default: return -1;
+      }
+   }
+   return (int)cudaGetLastError();
+}
+
+template <class Func, class Cfg, bool UNROLLQ> KernelOps make_ops()
+{
+   KernelOps o;
+   o.launch = &launch_impl<Func, Cfg, UNROLLQ>;
+   o.n_input = Cfg::N_INPUT;
+   o.n_fparam = Func::N_PARAM;
+   o.n_qprm = Func::N_QPRM;
+   o.n_field_qprm = Cfg::N_FIELD_QPRM;
+   o.nvd = Cfg::NVD;
+   o.ndof_all = Cfg::NDOF_ALL;
+   o.nq = Cfg::NQ;
+   o.ntab = Cfg::NTAB;
+   o.dim = Cfg::DIM;
+   return o;
+}
+
+#define MADB_CAT2(a, b) a##b
+#define MADB_CAT(a, b) MADB_CAT2(a, b)
+/// Register the fused kernels of functional type FUNC (run-time key KIND) on
+/// element configuration CFG (a madb::Config<...>; wrap in parentheses-free alias).
+#define MADB_INSTANCE(KIND, FUNC, CFG, UNROLLQ)                                                         \
+   static ::madb::Registrar MADB_CAT(madb_reg_, __COUNTER__)(std::string(KIND) + "|" + ::madb::config_key<CFG>(), \
+                                                             ::madb::make_ops<FUNC, CFG, UNROLLQ>());
+
+} // namespace madb

@@ -1,0 +1,682 @@
+// madb_runtime.cu -- C ABI entry points (include/mfemad_b200.h) and run-time plumbing.
+#include "../../include/mfemad_b200.h"
+#include "madb_config.cuh"
+#include "madb_eval.cuh"
+#include "madb_host.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace madb
+{
+
+static thread_local std::string g_err;
+const char *last_error() { return g_err.c_str(); }
+void set_error(const std::string &s) { g_err = s; }
+
+std::map<std::string, KernelOps> &registry()
+{
+   static std::map<std::string, KernelOps> r;
+   return r;
+}
+Registrar::Registrar(const std::string &key, const KernelOps &ops) { registry()[key] = ops; }
+
+std::map<std::string, EvalOps> &eval_registry()
+{
+   static std::map<std::string, EvalOps> r;
+   return r;
+}
+EvalRegistrar::EvalRegistrar(const std::string &key, const EvalOps &ops) { eval_registry()[key] = ops; }
+
+std::string Functional::key() const
+{
+   std::string k = kind;
+   for (size_t i = 0; i < iparams.size(); i++) { k += (i == 0 ? ":" : ",") + std::to_string(iparams[i]); }
+   if (!children.empty())
+   {
+      k += "[";
+      for (size_t i = 0; i < children.size(); i++) { k += (i ? "," : "") + children[i]->key(); }
+      k += "]";
+   }
+   return k;
+}
+void Functional::flat_params(std::vector<double> &out) const
+{
+   out.insert(out.end(), params.begin(), params.end());
+   for (const Functional *c : children) { c->flat_params(out); }
+}
+
+Integrator::~Integrator()
+{
+   cudaFree(d_e2n); cudaFree(d_vmap); cudaFree(d_pmap); cudaFree(d_e2csr);
+   cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_energy); cudaFree(d_esum);
+   cudaFree(d_x); cudaFree(d_v); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
+   for (double *p : d_pstage) { cudaFree(p); }
+}
+
+#define CUDA_OK(call)                                                                                 \
+   do {                                                                                               \
+      cudaError_t e_ = (call);                                                                        \
+      if (e_ != cudaSuccess)                                                                          \
+      {                                                                                               \
+         set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                               \
+         return 2;                                                                                    \
+      }                                                                                               \
+   } while (0)
+
+static bool is_device_ptr(const void *p)
+{
+   if (!p) { return false; }
+   cudaPointerAttributes at;
+   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// deterministic fixed-tree sum: one block, fixed strided partials, shared-memory tree
+__global__ void __launch_bounds__(1024) k_reduce_sum(const double *in, int n, double *out)
+{
+   __shared__ double s[1024];
+   double acc = 0.0;
+   for (int i = threadIdx.x; i < n; i += 1024) { acc += in[i]; }
+   s[threadIdx.x] = acc;
+   __syncthreads();
+   for (int k = 512; k > 0; k >>= 1)
+   {
+      if ((int)threadIdx.x < k) { s[threadIdx.x] += s[threadIdx.x + k]; }
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) { out[0] = s[0]; }
+}
+
+// y[ess] = 0  (NonlinearForm::Mult [MFEM-upstream])
+__global__ void k_ess_zero(const int *ess, int n, double *y)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { y[ess[i]] = 0.0; }
+}
+// SparseMatrix::EliminateRowCol(rc, DIAG_ONE) on a symmetric pattern with sorted columns
+__global__ void k_ess_rowcol(const int *ess, int n, const int *rowptr, const int *colidx, double *vals)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   const int rc = ess[i];
+   for (int p = rowptr[rc]; p < rowptr[rc + 1]; p++)
+   {
+      const int j = colidx[p];
+      vals[p] = (j == rc) ? 1.0 : 0.0;
+      if (j != rc)
+      {
+         int lo = rowptr[j], hi = rowptr[j + 1];
+         while (lo < hi)
+         {
+            const int mid = (lo + hi) >> 1;
+            if (colidx[mid] < rc) { lo = mid + 1; } else { hi = mid; }
+         }
+         if (lo < rowptr[j + 1] && colidx[lo] == rc) { vals[lo] = 0.0; }
+      }
+   }
+}
+
+template <class T> static int upload(const std::vector<T> &h, T **d)
+{
+   CUDA_OK(cudaMalloc((void **)d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+   CUDA_OK(cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+   return 0;
+}
+
+static int setup_integrator(Integrator &I)
+{
+   const int dim = I.mesh->dim;
+   I.ne = I.mesh->ne;
+   I.stride = (I.ne + 31) / 32 * 32;
+   // sizes and block offsets
+   I.nvd = 0; I.ndof_all = 0; I.ntotal = 0;
+   I.goff.clear();
+   for (const FieldDesc &f : I.fields)
+   {
+      const int n = f.space->nd_el() * f.space->vdim;
+      I.ndof_all += n;
+      if (f.role == ROLE_INPUT)
+      {
+         I.nvd += n;
+         I.goff.push_back(I.ntotal);
+         I.ntotal += f.space->vsize();
+      }
+   }
+   I.npd = I.ndof_all - I.nvd;
+   if (I.ntotal >= 0x7fffffffL) { set_error("more than 2^31 dofs per rank"); return 1; }
+
+   // colouring, sorted order
+   std::vector<int> color;
+   int ncolors = 0;
+   color_elements(I, color, ncolors);
+   I.color_off.assign(ncolors + 1, 0);
+   for (int e = 0; e < I.ne; e++) { I.color_off[color[e] + 1]++; }
+   for (int c = 0; c < ncolors; c++) { I.color_off[c + 1] += I.color_off[c]; }
+   I.perm.resize(I.ne);
+   {
+      std::vector<int> fill(I.color_off.begin(), I.color_off.end() - 1);
+      for (int e = 0; e < I.ne; e++) { I.perm[fill[color[e]]++] = e; }
+   }
+
+   // device maps in sorted order
+   const int ngn = 1 << dim;
+   std::vector<int> e2n((size_t)ngn * I.stride, 0), vmap((size_t)I.nvd * I.stride, 0),
+       pmap((size_t)std::max(I.npd, 1) * I.stride, 0);
+   std::vector<unsigned char> touched(I.ntotal, 0);
+   std::vector<int> vd;
+   for (int t = 0; t < I.ne; t++)
+   {
+      const int e = I.perm[t];
+      for (int k = 0; k < ngn; k++) { e2n[(size_t)k * I.stride + t] = I.mesh->e2n[(size_t)e * ngn + k]; }
+      build_vdofs(I, e, vd);
+      for (int i = 0; i < I.nvd; i++)
+      {
+         int m = vd[i];
+         if (!touched[m]) { touched[m] = 1; m |= 0x80000000; } // colours ascend with t
+         vmap[(size_t)i * I.stride + t] = m;
+      }
+      int k = 0;
+      for (const FieldDesc &f : I.fields)
+      {
+         if (f.role == ROLE_INPUT) { continue; }
+         const Space &S = *f.space;
+         const int nd = S.nd_el();
+         for (int c = 0; c < S.vdim; c++)
+         {
+            for (int i = 0; i < nd; i++)
+            {
+               const int d = S.e2l[(size_t)e * nd + i];
+               pmap[(size_t)k * I.stride + t] = (S.ordering == ORD_BYNODES) ? d + S.ndofs * c : d * S.vdim + c;
+               k++;
+            }
+         }
+      }
+   }
+   if (upload(e2n, &I.d_e2n) || upload(vmap, &I.d_vmap) || upload(pmap, &I.d_pmap)) { return 2; }
+
+   // basis tables at the quadrature points: [q][toff_f + i], x fastest in q and i
+   std::vector<double> xq, wq;
+   gauss_legendre_01(I.nq1d, xq, wq);
+   I.nq = 1;
+   for (int d = 0; d < dim; d++) { I.nq *= I.nq1d; }
+   int ntab = 0;
+   for (const FieldDesc &f : I.fields) { ntab += f.space->nd_el(); }
+   I.phi.assign((size_t)I.nq * ntab, 0.0);
+   I.dphi.assign((size_t)I.nq * ntab * dim, 0.0);
+   I.gdphi.assign((size_t)I.nq * ngn * dim, 0.0);
+   I.w.assign(I.nq, 0.0);
+   auto fill_tables = [&](const std::vector<double> &nodes, int toff, int ncols, double *phi, double *dphi)
+   {
+      const int nn = (int)nodes.size();
+      std::vector<double> B, G;
+      lagrange_tables(nodes, xq, B, G);
+      int nd = 1;
+      for (int d = 0; d < dim; d++) { nd *= nn; }
+      for (int q = 0; q < I.nq; q++)
+      {
+         int qd[3], r = q;
+         for (int d = 0; d < dim; d++) { qd[d] = r % I.nq1d; r /= I.nq1d; }
+         for (int i = 0; i < nd; i++)
+         {
+            int id[3], s = i;
+            for (int d = 0; d < dim; d++) { id[d] = s % nn; s /= nn; }
+            double v = 1.0;
+            for (int d = 0; d < dim; d++) { v *= B[(size_t)qd[d] * nn + id[d]]; }
+            if (phi) { phi[(size_t)q * ncols + toff + i] = v; }
+            for (int k = 0; k < dim; k++)
+            {
+               double g = 1.0;
+               for (int d = 0; d < dim; d++) { g *= (d == k) ? G[(size_t)qd[d] * nn + id[d]] : B[(size_t)qd[d] * nn + id[d]]; }
+               dphi[((size_t)q * ncols + toff + i) * dim + k] = g;
+            }
+         }
+      }
+   };
+   int toff = 0;
+   for (const FieldDesc &f : I.fields)
+   {
+      std::vector<double> nodes, wtmp;
+      if (f.space->basis == BASIS_H1) { gauss_lobatto_01(f.space->order + 1, nodes); }
+      else { gauss_legendre_01(f.space->order + 1, nodes, wtmp); }
+      fill_tables(nodes, toff, ntab, I.phi.data(), I.dphi.data());
+      toff += f.space->nd_el();
+   }
+   fill_tables(std::vector<double> {0.0, 1.0}, 0, ngn, nullptr, I.gdphi.data());
+   for (int q = 0; q < I.nq; q++)
+   {
+      int r = q;
+      double ww = 1.0;
+      for (int d = 0; d < dim; d++) { ww *= wq[r % I.nq1d]; r /= I.nq1d; }
+      I.w[q] = ww;
+   }
+   I.pdata.assign(I.fields.size(), nullptr);
+   I.d_pstage.assign(I.fields.size(), nullptr);
+   return 0;
+}
+
+static int ensure_pattern_device(Integrator &I)
+{
+   if (I.d_e2csr) { return 0; }
+   build_pattern(I);
+   if (!I.have_pattern) { return 1; }
+   std::vector<int> e2csr;
+   build_e2csr(I, std::vector<int>(), e2csr);
+   if (upload(e2csr, &I.d_e2csr) || upload(I.rowptr, &I.d_rowptr) || upload(I.colidx, &I.d_colidx)) { return 2; }
+   return 0;
+}
+
+// stage a caller vector: returns the device pointer to use
+static int stage_in(Integrator &I, const double *p, size_t n, double **buf, const double **out)
+{
+   if (is_device_ptr(p)) { *out = p; return 0; }
+   if (!*buf) { CUDA_OK(cudaMalloc((void **)buf, std::max<size_t>(n, 1) * sizeof(double))); }
+   CUDA_OK(cudaMemcpyAsync(*buf, p, n * sizeof(double), cudaMemcpyHostToDevice, I.ctx->stream));
+   *out = *buf;
+   return 0;
+}
+static int stage_out_begin(Integrator &I, double *p, size_t n, double **buf, double **out)
+{
+   if (is_device_ptr(p)) { *out = p; return 0; }
+   if (!*buf) { CUDA_OK(cudaMalloc((void **)buf, std::max<size_t>(n, 1) * sizeof(double))); }
+   *out = *buf;
+   return 0;
+}
+
+static int run(Integrator &I, int mode, const double *x, const double *v, double *y, double *vals, double *energy)
+{
+   CUDA_OK(cudaSetDevice(I.ctx->device));
+   const size_t N = (size_t)I.ntotal;
+   LaunchCtx L;
+   std::memset(&L, 0, sizeof(L));
+   L.stream = I.ctx->stream;
+   L.ne = I.ne; L.stride = I.stride;
+   L.ncolors = (int)I.color_off.size() - 1;
+   L.color_off = I.color_off.data();
+   L.e2n = I.d_e2n; L.vmap = I.d_vmap; L.pmap = I.d_pmap;
+   L.coords = I.mesh->d_coords;
+   for (size_t f = 0; f < I.fields.size(); f++)
+   {
+      L.pdata[f] = I.pdata[f];
+      if (I.fields[f].role == ROLE_PARAM && !I.pdata[f]) { set_error("parameter field " + std::to_string(f) + " was never set (madb_integrator_set_param_field)"); return 1; }
+   }
+   if (I.ops.n_qprm - I.ops.n_field_qprm > 0)
+   {
+      if (!I.d_qf || I.qf_count != (size_t)(I.ops.n_qprm - I.ops.n_field_qprm)) { set_error("quadrature-function parameters were never set (madb_integrator_set_param_qf)"); return 1; }
+      L.qf = I.d_qf;
+   }
+   std::vector<double> fp;
+   I.fn->flat_params(fp);
+   if ((int)fp.size() != I.ops.n_fparam)
+   {
+      set_error("functional '" + I.fn->key() + "' carries " + std::to_string(fp.size()) + " parameters, the compiled kernel expects " + std::to_string(I.ops.n_fparam));
+      return 1;
+   }
+   fp.push_back(0.0);
+   L.fparams = fp.data();
+   L.phi = I.phi.data(); L.dphi = I.dphi.data(); L.gdphi = I.gdphi.data(); L.w = I.w.data();
+
+   if (stage_in(I, x, N, &I.d_x, &L.x)) { return 2; }
+   if (mode == MODE_ACT) { if (stage_in(I, v, N, &I.d_v, &L.v)) { return 2; } }
+   double *dy = nullptr, *dvals = nullptr;
+   if (y) { if (stage_out_begin(I, y, N, &I.d_y, &dy)) { return 2; } }
+   if (vals)
+   {
+      if (ensure_pattern_device(I)) { return 1; }
+      if (stage_out_begin(I, vals, I.colidx.size(), &I.d_vals, &dvals)) { return 2; }
+      L.e2csr = I.d_e2csr;
+   }
+   L.y = dy; L.vals = dvals;
+   L.write_y = dy != nullptr; L.write_vals = dvals != nullptr;
+   if (mode == MODE_ENERGY)
+   {
+      if (!I.d_energy)
+      {
+         CUDA_OK(cudaMalloc((void **)&I.d_energy, (size_t)I.stride * sizeof(double)));
+         CUDA_OK(cudaMalloc((void **)&I.d_esum, sizeof(double)));
+      }
+      L.energy = I.d_energy;
+   }
+   const int rc = I.ops.launch(L, mode);
+   if (rc != 0) { set_error(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
+
+   if (mode == MODE_ENERGY)
+   {
+      k_reduce_sum<<<1, 1024, 0, L.stream>>>(I.d_energy, I.ne, I.d_esum);
+      CUDA_OK(cudaMemcpyAsync(energy, I.d_esum, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+      CUDA_OK(cudaStreamSynchronize(L.stream));
+      return 0;
+   }
+   if (I.ness > 0)
+   {
+      const int g = (I.ness + 127) / 128;
+      if (dy) { k_ess_zero<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, dy); }
+      if (dvals) { k_ess_rowcol<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, I.d_rowptr, I.d_colidx, dvals); }
+   }
+   bool sync = false;
+   if (y && dy != y) { CUDA_OK(cudaMemcpyAsync(y, dy, N * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); sync = true; }
+   if (vals && dvals != vals) { CUDA_OK(cudaMemcpyAsync(vals, dvals, I.colidx.size() * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); sync = true; }
+   if (sync) { CUDA_OK(cudaStreamSynchronize(L.stream)); }
+   CUDA_OK(cudaGetLastError());
+   return 0;
+}
+
+} // namespace madb
+
+using namespace madb;
+
+struct madb_ctx : Ctx {};
+struct madb_mesh : Mesh {};
+struct madb_space : Space {};
+struct madb_functional : Functional {};
+struct madb_integrator : Integrator {};
+
+extern "C"
+{
+
+   int madb_version(void) { return 100; }
+   const char *madb_last_error(void) { return last_error(); }
+
+   int madb_ctx_create(int device, madb_ctx **out)
+   {
+      int ndev = 0;
+      if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      {
+         cudaGetLastError();
+         set_error("no CUDA device: the mfem-ad B200 path has no CPU fallback");
+         return 2;
+      }
+      CUDA_OK(cudaSetDevice(device));
+      madb_ctx *c = new madb_ctx;
+      c->device = device;
+      CUDA_OK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      *out = c;
+      return 0;
+   }
+   int madb_ctx_destroy(madb_ctx *c)
+   {
+      if (!c) { return 0; }
+      cudaStreamDestroy(c->stream);
+      delete c;
+      return 0;
+   }
+   int madb_ctx_sync(madb_ctx *c)
+   {
+      CUDA_OK(cudaStreamSynchronize(c->stream));
+      return 0;
+   }
+   void *madb_ctx_stream(madb_ctx *c) { return (void *)c->stream; }
+
+   int madb_mesh_create(madb_ctx *ctx, int dim, int ne, const int32_t *e2n, int nnodes, const double *coords,
+                        madb_mesh **out)
+   {
+      if (dim < 1 || dim > 3 || ne <= 0 || !e2n || !coords) { set_error("madb_mesh_create: bad arguments"); return 1; }
+      CUDA_OK(cudaSetDevice(ctx->device));
+      madb_mesh *m = new madb_mesh;
+      m->ctx = ctx; m->dim = dim; m->ne = ne; m->geom_order = 1; m->nnodes = nnodes;
+      m->e2n.assign(e2n, e2n + (size_t)ne * (1 << dim));
+      m->coords.assign(coords, coords + (size_t)nnodes * dim);
+      for (int v : m->e2n) { if (v < 0 || v >= nnodes) { delete m; set_error("madb_mesh_create: vertex id out of range"); return 1; } }
+      if (upload(m->coords, &m->d_coords)) { delete m; return 2; }
+      *out = m;
+      return 0;
+   }
+   int madb_mesh_destroy(madb_mesh *m)
+   {
+      if (m) { cudaFree(m->d_coords); delete m; }
+      return 0;
+   }
+
+   int madb_space_create(madb_ctx *ctx, madb_mesh *mesh, int basis, int order, int vdim, int ordering, int ndofs,
+                         const int32_t *e2l, madb_space **out)
+   {
+      if (!mesh || order < 0 || vdim < 1 || ndofs <= 0 || !e2l || (basis != BASIS_H1 && basis != BASIS_L2) || (basis == BASIS_H1 && order < 1))
+      {
+         set_error("madb_space_create: bad arguments");
+         return 1;
+      }
+      madb_space *s = new madb_space;
+      s->ctx = ctx; s->mesh = mesh; s->basis = basis; s->order = order; s->vdim = vdim; s->ordering = ordering; s->ndofs = ndofs;
+      s->e2l.assign(e2l, e2l + (size_t)mesh->ne * s->nd_el());
+      for (int v : s->e2l) { if (v < 0 || v >= ndofs) { delete s; set_error("madb_space_create: dof id out of range"); return 1; } }
+      *out = s;
+      return 0;
+   }
+   int madb_space_destroy(madb_space *s) { delete s; return 0; }
+
+   int madb_functional_create(madb_ctx *, const char *kind, int nparams, const double *params, int niparams,
+                              const int *iparams, int nchildren, madb_functional *const *children, madb_functional **out)
+   {
+      madb_functional *f = new madb_functional;
+      f->kind = kind;
+      if (nparams > 0) { f->params.assign(params, params + nparams); }
+      if (niparams > 0) { f->iparams.assign(iparams, iparams + niparams); }
+      for (int i = 0; i < nchildren; i++) { f->children.push_back(children[i]); }
+      *out = f;
+      return 0;
+   }
+   int madb_functional_set_params(madb_functional *f, int nparams, const double *params)
+   {
+      if ((size_t)nparams != f->params.size())
+      {
+         // same rule as Evaluator::Replace (src/ad_native.cpp:109-118): sizes must match
+         set_error("madb_functional_set_params: size mismatch: expected " + std::to_string(f->params.size()) + ", got " + std::to_string(nparams));
+         return 1;
+      }
+      f->params.assign(params, params + nparams);
+      return 0;
+   }
+   int madb_functional_destroy(madb_functional *f) { delete f; return 0; }
+
+   int madb_functional_eval(madb_ctx *ctx, madb_functional *f, int n_input, int npts, const double *x,
+                            const double *qprm, double *value, double *grad, double *hess)
+   {
+      CUDA_OK(cudaSetDevice(ctx->device));
+      const std::string key = f->key() + "|n" + std::to_string(n_input);
+      auto it = eval_registry().find(key);
+      if (it == eval_registry().end())
+      {
+         set_error("no pointwise AD kernel compiled for '" + key + "' (add MADB_EVAL_INSTANCE)");
+         return 1;
+      }
+      const EvalOps &E = it->second;
+      std::vector<double> fp;
+      f->flat_params(fp);
+      if ((int)fp.size() != E.n_fparam) { set_error("functional '" + key + "': wrong number of parameters"); return 1; }
+      fp.push_back(0.0);
+      const int n = n_input;
+      double *dx = nullptr, *dq = nullptr, *dv = nullptr, *dg = nullptr, *dh = nullptr;
+      CUDA_OK(cudaMalloc((void **)&dx, (size_t)npts * n * sizeof(double)));
+      CUDA_OK(cudaMemcpy(dx, x, (size_t)npts * n * sizeof(double), cudaMemcpyDefault));
+      if (E.n_qprm > 0)
+      {
+         if (!qprm) { set_error("functional '" + key + "' needs per-point parameters"); cudaFree(dx); return 1; }
+         CUDA_OK(cudaMalloc((void **)&dq, (size_t)npts * E.n_qprm * sizeof(double)));
+         CUDA_OK(cudaMemcpy(dq, qprm, (size_t)npts * E.n_qprm * sizeof(double), cudaMemcpyDefault));
+      }
+      CUDA_OK(cudaMalloc((void **)&dv, (size_t)npts * sizeof(double)));
+      CUDA_OK(cudaMalloc((void **)&dg, (size_t)npts * n * sizeof(double)));
+      CUDA_OK(cudaMalloc((void **)&dh, (size_t)npts * n * n * sizeof(double)));
+      const int rc = E.launch(ctx->stream, npts, fp.data(), dx, dq, dv, dg, dh);
+      if (rc) { set_error(std::string("eval kernel: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
+      CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      if (value) { CUDA_OK(cudaMemcpy(value, dv, (size_t)npts * sizeof(double), cudaMemcpyDefault)); }
+      if (grad) { CUDA_OK(cudaMemcpy(grad, dg, (size_t)npts * n * sizeof(double), cudaMemcpyDefault)); }
+      if (hess) { CUDA_OK(cudaMemcpy(hess, dh, (size_t)npts * n * n * sizeof(double), cudaMemcpyDefault)); }
+      cudaFree(dx); cudaFree(dq); cudaFree(dv); cudaFree(dg); cudaFree(dh);
+      return 0;
+   }
+
+   int madb_integrator_create(madb_ctx *ctx, int nfields, madb_space *const *spaces, const int *modes,
+                              const int *roles, madb_functional *f, int quad_order, madb_integrator **out)
+   {
+      if (nfields < 1 || nfields > 8 || !spaces || !modes || !f) { set_error("madb_integrator_create: bad arguments"); return 1; }
+      CUDA_OK(cudaSetDevice(ctx->device));
+      madb_integrator *I = new madb_integrator;
+      I->ctx = ctx;
+      I->mesh = spaces[0]->mesh;
+      I->fn = f;
+      int max_order = 0;
+      for (int i = 0; i < nfields; i++)
+      {
+         const unsigned m = (unsigned)modes[i];
+         // isValidADEval (src/_ad_intg.hpp:55-66) + the modes the reference marks "not yet implemented" (:29-34)
+         if (m & (EV_HESSIAN | EV_DIV | EV_CURL | EV_VECFE | EV_QVALUE))
+         {
+            delete I;
+            set_error("madb_integrator_create: ADEval modes QVALUE/DIV/CURL/Hessian/VECFE are not supported by the B200 path");
+            return 1;
+         }
+         if (!(m & (EV_VALUE | EV_GRAD))) { delete I; set_error("madb_integrator_create: a field needs VALUE and/or GRAD"); return 1; }
+         if (spaces[i]->vdim > 1 && !(m & EV_VECTOR) && (!roles || roles[i] == ROLE_INPUT))
+         {
+            // src/ad_intg.hpp:165-167: vdim must be 1 or the mode must be VECTOR
+            delete I;
+            set_error("madb_integrator_create: vdim must be 1 or the mode must be VECTOR");
+            return 1;
+         }
+         if (spaces[i]->mesh != I->mesh) { delete I; set_error("madb_integrator_create: all spaces must live on one mesh"); return 1; }
+         FieldDesc fd;
+         fd.space = spaces[i];
+         fd.mode = m;
+         fd.role = roles ? roles[i] : ROLE_INPUT;
+         I->fields.push_back(fd);
+         if (fd.role == ROLE_INPUT) { max_order = std::max(max_order, spaces[i]->order); }
+      }
+      I->quad_order = quad_order >= 0 ? quad_order : 2 * max_order + 2; // src/_ad_intg.hpp:103-104, :303-312
+      I->nq1d = rule_npts_1d(I->quad_order);
+      std::string key = f->key() + "|d" + std::to_string(I->mesh->dim) + "q" + std::to_string(I->nq1d);
+      for (const FieldDesc &fd : I->fields)
+      {
+         key += "|" + std::to_string(fd.space->order + 1) + "." + std::to_string(fd.space->vdim) + "." +
+                std::to_string((int)(fd.mode & (EV_VALUE | EV_GRAD))) + "." + std::to_string(fd.role);
+      }
+      I->key = key;
+      auto it = registry().find(key);
+      if (it == registry().end())
+      {
+         std::string have;
+         for (auto &kv : registry()) { if (kv.first.compare(0, f->kind.size(), f->kind) == 0) { have += "\n    " + kv.first; } }
+         set_error("no fused kernel compiled for configuration '" + key + "'. Add a MADB_INSTANCE line (csrc/instances_*.cu) and rebuild." +
+                   (have.empty() ? "" : " Compiled variants of this functional:" + have));
+         delete I;
+         return 1;
+      }
+      I->ops = it->second;
+      const int rc = setup_integrator(*I);
+      if (rc) { delete I; return rc; }
+      if (I->nvd != I->ops.nvd || I->ndof_all != I->ops.ndof_all || I->nq != I->ops.nq)
+      {
+         set_error("internal: run-time sizes disagree with the compiled configuration '" + key + "'");
+         delete I;
+         return 1;
+      }
+      *out = I;
+      return 0;
+   }
+   int madb_integrator_destroy(madb_integrator *I) { delete I; return 0; }
+
+   int madb_integrator_sizes(madb_integrator *I, int64_t *ntotal, int *nq_el, int *ncolors)
+   {
+      if (ntotal) { *ntotal = I->ntotal; }
+      if (nq_el) { *nq_el = I->nq; }
+      if (ncolors) { *ncolors = (int)I->color_off.size() - 1; }
+      return 0;
+   }
+
+   int madb_integrator_set_param_field(madb_integrator *I, int field, const double *dofs)
+   {
+      if (field < 0 || field >= (int)I->fields.size() || I->fields[field].role != ROLE_PARAM)
+      {
+         set_error("madb_integrator_set_param_field: field is not a parameter field");
+         return 1;
+      }
+      CUDA_OK(cudaSetDevice(I->ctx->device));
+      const size_t n = (size_t)I->fields[field].space->vsize();
+      if (is_device_ptr(dofs)) { I->pdata[field] = dofs; return 0; }
+      if (!I->d_pstage[field]) { CUDA_OK(cudaMalloc((void **)&I->d_pstage[field], n * sizeof(double))); }
+      CUDA_OK(cudaMemcpyAsync(I->d_pstage[field], dofs, n * sizeof(double), cudaMemcpyHostToDevice, I->ctx->stream));
+      CUDA_OK(cudaStreamSynchronize(I->ctx->stream));
+      I->pdata[field] = I->d_pstage[field];
+      return 0;
+   }
+
+   int madb_integrator_set_param_qf(madb_integrator *I, int nqf, const double *qf)
+   {
+      const int need = I->ops.n_qprm - I->ops.n_field_qprm;
+      if (nqf != need) { set_error("madb_integrator_set_param_qf: functional expects " + std::to_string(need) + " quadrature-function parameters, got " + std::to_string(nqf)); return 1; }
+      CUDA_OK(cudaSetDevice(I->ctx->device));
+      // caller layout (QuadratureFunction): qf[(e*nq + q)*nqf + k]  ->  device [k][q][sorted t]
+      const size_t cnt = (size_t)I->ne * I->nq * nqf;
+      std::vector<double> h(cnt);
+      CUDA_OK(cudaMemcpy(h.data(), qf, cnt * sizeof(double), cudaMemcpyDefault));
+      std::vector<double> tr((size_t)nqf * I->nq * I->stride, 0.0);
+      for (int t = 0; t < I->ne; t++)
+      {
+         const int e = I->perm[t];
+         for (int q = 0; q < I->nq; q++)
+         {
+            for (int k = 0; k < nqf; k++) { tr[((size_t)k * I->nq + q) * I->stride + t] = h[((size_t)e * I->nq + q) * nqf + k]; }
+         }
+      }
+      if (!I->d_qf) { CUDA_OK(cudaMalloc((void **)&I->d_qf, tr.size() * sizeof(double))); }
+      CUDA_OK(cudaMemcpy(I->d_qf, tr.data(), tr.size() * sizeof(double), cudaMemcpyHostToDevice));
+      I->qf_count = nqf;
+      return 0;
+   }
+
+   int madb_integrator_set_essential(madb_integrator *I, int n, const int32_t *dofs)
+   {
+      CUDA_OK(cudaSetDevice(I->ctx->device));
+      cudaFree(I->d_ess);
+      I->d_ess = nullptr;
+      I->ness = n;
+      if (n > 0)
+      {
+         for (int i = 0; i < n; i++) { if (dofs[i] < 0 || dofs[i] >= I->ntotal) { set_error("madb_integrator_set_essential: dof out of range"); I->ness = 0; return 1; } }
+         CUDA_OK(cudaMalloc((void **)&I->d_ess, (size_t)n * sizeof(int)));
+         CUDA_OK(cudaMemcpy(I->d_ess, dofs, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+      }
+      return 0;
+   }
+
+   int madb_integrator_energy(madb_integrator *I, const double *x, double *energy)
+   {
+      return run(*I, MODE_ENERGY, x, nullptr, nullptr, nullptr, energy);
+   }
+   int madb_integrator_mult(madb_integrator *I, const double *x, double *y)
+   {
+      return run(*I, MODE_RES, x, nullptr, y, nullptr, nullptr);
+   }
+   int madb_integrator_pattern(madb_integrator *I, int64_t *nrows, int64_t *nnz, int32_t *rowptr, int32_t *colidx)
+   {
+      build_pattern(*I);
+      if (!I->have_pattern) { return 1; }
+      if (nrows) { *nrows = I->ntotal; }
+      if (nnz) { *nnz = (int64_t)I->colidx.size(); }
+      if (rowptr)
+      {
+         if (is_device_ptr(rowptr)) { CUDA_OK(cudaMemcpy(rowptr, I->rowptr.data(), I->rowptr.size() * sizeof(int), cudaMemcpyHostToDevice)); }
+         else { std::memcpy(rowptr, I->rowptr.data(), I->rowptr.size() * sizeof(int)); }
+      }
+      if (colidx)
+      {
+         if (is_device_ptr(colidx)) { CUDA_OK(cudaMemcpy(colidx, I->colidx.data(), I->colidx.size() * sizeof(int), cudaMemcpyHostToDevice)); }
+         else { std::memcpy(colidx, I->colidx.data(), I->colidx.size() * sizeof(int)); }
+      }
+      return 0;
+   }
+   int madb_integrator_grad_assemble(madb_integrator *I, const double *x, double *vals)
+   {
+      return run(*I, MODE_RES | MODE_JAC, x, nullptr, nullptr, vals, nullptr);
+   }
+   int madb_integrator_assemble(madb_integrator *I, const double *x, double *y, double *vals)
+   {
+      return run(*I, MODE_RES | MODE_JAC, x, nullptr, y, vals, nullptr);
+   }
+   int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y)
+   {
+      return run(*I, MODE_ACT, x, v, y, nullptr, nullptr);
+   }
+} // extern "C"

@@ -1,0 +1,138 @@
+"""Synthetic Cartesian meshes and tensor-product H1/L2 dof maps (numpy, host side).
+
+Stand-in for Mesh::MakeCartesian2D/3D + FiniteElementSpace numbering of the
+reference's drivers (ex1.cpp:36-41, ex4.cpp:78-101): MFEM is not available, so
+benchmarks and tests generate the element->vertex and element->dof maps here
+and hand the SAME arrays to the CUDA path and to the CPU oracle.
+All local orderings are lexicographic (x fastest).
+"""
+import numpy as np
+
+
+def gauss_lobatto_01(n):
+    """n Gauss-Lobatto points on [0,1] (H1 closed basis nodes)."""
+    if n == 1:
+        return np.array([0.5])
+    if n == 2:
+        return np.array([0.0, 1.0])
+    N = n - 1
+    # interior nodes: roots of P_N'
+    c = np.zeros(N + 1)
+    c[N] = 1.0
+    r = np.polynomial.legendre.Legendre(c).deriv().roots()
+    x = np.concatenate([[-1.0], np.sort(r.real), [1.0]])
+    x = 0.5 * (x - x[::-1])  # symmetrise
+    return 0.5 * (x + 1.0)
+
+
+def gauss_legendre_01(n):
+    x, w = np.polynomial.legendre.leggauss(n)
+    return 0.5 * (x + 1.0), 0.5 * w
+
+
+def cartesian_mesh(n, lengths=None, perturb=0.0):
+    """n = (nx, ny[, nz]) elements.  Returns dict(dim, e2n[ne,2^dim], coords[nv,dim]).
+
+    perturb > 0 displaces interior vertices smoothly (non-affine elements)."""
+    n = tuple(int(v) for v in n)
+    dim = len(n)
+    lengths = tuple(lengths) if lengths is not None else (1.0,) * dim
+    nv1 = [k + 1 for k in n]
+    grids = np.meshgrid(*[np.arange(k) for k in nv1[::-1]], indexing="ij")  # z,y,x order
+    idx = [g.ravel() for g in grids[::-1]]  # x fastest
+    coords = np.stack([idx[d] * (lengths[d] / n[d]) for d in range(dim)], axis=1).astype(np.float64)
+    if perturb:
+        s = np.ones(len(coords))
+        for d in range(dim):
+            s = s * np.sin(np.pi * coords[:, d] / lengths[d])
+        base = coords.copy()
+        for d in range(dim):
+            h = lengths[d] / n[d]
+            phase = sum((k + 1.3) * base[:, k] / lengths[k] for k in range(dim) if k != d) if dim > 1 else 0.0
+            coords[:, d] += perturb * h * s * np.cos(2.0 * np.pi * phase + d)
+    eg = np.meshgrid(*[np.arange(k) for k in n[::-1]], indexing="ij")
+    eidx = [g.ravel() for g in eg[::-1]]  # ex fastest
+    e2n = np.zeros((len(eidx[0]), 2 ** dim), dtype=np.int32)
+    for loc in range(2 ** dim):
+        v = np.zeros_like(eidx[0])
+        stride = 1
+        for d in range(dim):
+            v = v + (eidx[d] + ((loc >> d) & 1)) * stride
+            stride *= nv1[d]
+        e2n[:, loc] = v
+    return dict(dim=dim, n=n, lengths=lengths, e2n=e2n, coords=coords, geom_order=1)
+
+
+def h1_space(mesh, p, vdim=1, ordering=0, mode=0):
+    """Continuous tensor space of order p on a cartesian_mesh; dofs numbered
+    lexicographically on the global (n*p+1)^dim node grid."""
+    n, dim = mesh["n"], mesh["dim"]
+    ng = [k * p + 1 for k in n]
+    eg = np.meshgrid(*[np.arange(k) for k in n[::-1]], indexing="ij")
+    eidx = [g.ravel() for g in eg[::-1]]
+    nd = (p + 1) ** dim
+    e2l = np.zeros((len(eidx[0]), nd), dtype=np.int32)
+    for loc in range(nd):
+        r, v, stride = loc, np.zeros_like(eidx[0]), 1
+        for d in range(dim):
+            i = r % (p + 1)
+            r //= (p + 1)
+            v = v + (eidx[d] * p + i) * stride
+            stride *= ng[d]
+        e2l[:, loc] = v
+    return dict(basis=0, order=p, vdim=vdim, ordering=ordering, ndofs=int(np.prod(ng)), e2l=e2l, mode=mode)
+
+
+def l2_space(mesh, p, vdim=1, ordering=0, mode=0):
+    ne = mesh["e2n"].shape[0]
+    nd = (p + 1) ** mesh["dim"]
+    e2l = (np.arange(ne, dtype=np.int64)[:, None] * nd + np.arange(nd)[None, :]).astype(np.int32)
+    return dict(basis=1, order=p, vdim=vdim, ordering=ordering, ndofs=ne * nd, e2l=e2l, mode=mode)
+
+
+def permute_dofs(space, seed):
+    """Random renumbering of the scalar dofs (tests: nothing may depend on the numbering)."""
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(space["ndofs"]).astype(np.int32)
+    out = dict(space)
+    out["e2l"] = perm[space["e2l"]]
+    out["perm"] = perm
+    return out
+
+
+def _lagrange(nodes, t):
+    t = np.atleast_1d(t)
+    B = np.ones((len(t), len(nodes)))
+    for j in range(len(nodes)):
+        for k in range(len(nodes)):
+            if k != j:
+                B[:, j] *= (t - nodes[k]) / (nodes[j] - nodes[k])
+    return B
+
+
+def dof_coords(mesh, space):
+    """Physical coordinates of the scalar dofs (nodes mapped through the vertex map)."""
+    dim, p = mesh["dim"], space["order"]
+    nodes = gauss_lobatto_01(p + 1) if space["basis"] == 0 else gauss_legendre_01(p + 1)[0]
+    N = _lagrange(np.array([0.0, 1.0]), nodes)  # [p+1, 2]
+    X = mesh["coords"][mesh["e2n"]]  # [ne, 2^dim, dim]
+    nd = (p + 1) ** dim
+    out = np.zeros((space["ndofs"], dim))
+    for loc in range(nd):
+        r, wgt = loc, np.ones(2 ** dim)
+        for d in range(dim):
+            i = r % (p + 1)
+            r //= (p + 1)
+            for v in range(2 ** dim):
+                wgt[v] *= N[i, (v >> d) & 1]
+        out[space["e2l"][:, loc]] = np.einsum("v,evd->ed", wgt, X)
+    return out
+
+
+def boundary_dofs(mesh, space, tol=1e-12):
+    """Scalar dofs on the boundary of the Cartesian box (by coordinates of the unperturbed grid)."""
+    xc = dof_coords(dict(mesh, coords=cartesian_mesh(mesh["n"], mesh["lengths"])["coords"]), space)
+    on = np.zeros(space["ndofs"], dtype=bool)
+    for d in range(mesh["dim"]):
+        on |= (np.abs(xc[:, d]) < tol) | (np.abs(xc[:, d] - mesh["lengths"][d]) < tol)
+    return np.nonzero(on)[0].astype(np.int32)

@@ -1,0 +1,115 @@
+"""One description of a functional / form, convertible to the CPU oracle and to the CUDA path."""
+import numpy as np
+
+from oracle import oracle as O
+
+
+class FSpec:
+    def __init__(self, kind, n_input, params=(), iparams=(), children=(), qoff=-1):
+        self.kind, self.n_input = kind, n_input
+        self.params, self.iparams, self.children, self.qoff = list(params), list(iparams), list(children), qoff
+
+    # ---- CPU oracle ----
+    _OK = dict(ex0=O.K_EX0, mass=O.K_MASS, diffusion=O.K_DIFFUSION, diff=O.K_DIFF, elasticity=O.K_ELASTICITY,
+               minsurf=O.K_MINSURF, obstacle=O.K_OBSTACLE, gradobstacle=O.K_GRADOBSTACLE, pg=O.K_PG,
+               lambdapg=O.K_LAMBDAPG, shannon=O.K_SHANNON, fermidirac=O.K_FERMIDIRAC, hellinger=O.K_HELLINGER,
+               simplex=O.K_SIMPLEX, simp=O.K_SIMP, paramcompliance=O.K_PARAMCOMPLIANCE, empty=O.K_EMPTY)
+
+    def _add(self, F):
+        ch = [c._add(F) for c in self.children]
+        p, ip = list(self.params), list(self.iparams)
+        k = self.kind
+        if k == "shannon":  # oracle: param bound, iparam sign
+            p, ip = [self.params[0]], [int(self.params[1])]
+        elif k == "elasticity":
+            ip = [int(round(np.sqrt(self.n_input)))]
+        elif k == "paramcompliance":
+            ip = [int(round(np.sqrt(self.n_input)))]
+        elif k == "hellinger":
+            ip = [self.n_input]
+        return F.add(self._OK[k], self.n_input, params=p, iparams=ip, children=ch, qoff=self.qoff)
+
+    def oracle(self):
+        F = O.Functional()
+        self._add(F)
+        return F
+
+    # ---- CUDA path ----
+    def madb(self, ctx):
+        import mfem_ad_b200 as M
+        ch = [c.madb(ctx) for c in self.children]
+        ip = list(self.iparams)
+        return M.Functional(ctx, self.kind, params=self.params, iparams=ip, children=ch)
+
+
+def minsurf(dim, eps=0.5):
+    return FSpec("minsurf", dim, [eps])
+
+
+def diffusion(dim, K=()):
+    return FSpec("diffusion", dim, list(K), [len(K)])
+
+
+def mass(n):
+    return FSpec("mass", n)
+
+
+def elasticity(dim, lam, mu):
+    return FSpec("elasticity", dim * dim, [lam, mu])
+
+
+def obstacle(dim):
+    return FSpec("obstacle", dim + 1)
+
+
+def gradobstacle(dim):
+    return FSpec("gradobstacle", dim)
+
+
+def fermidirac(lower, upper):
+    return FSpec("fermidirac", 1, [lower, upper])
+
+
+def shannon(bound, sign=1):
+    return FSpec("shannon", 1, [bound, sign])
+
+
+def hellinger(dim, scale, qoff=-1):
+    return FSpec("hellinger", dim, [scale] if qoff < 0 else [], qoff=qoff)
+
+
+def simplex(n, scale=1.0):
+    return FSpec("simplex", n, [scale])
+
+
+def simp(E, p):
+    return FSpec("simp", len(E), list(E) + [p])
+
+
+def pg(f, entropy, alpha, primal_idx=0):
+    """ADPGFunctional(f, entropy, psi_k, idx): psi_k is the first per-point parameter."""
+    return FSpec("pg", f.n_input + entropy.n_input, [alpha], [primal_idx], [f, entropy], qoff=0)
+
+
+def make_pair(ctx, mesh, spaces, fspec, quad_order=-1, params=(), ess=(), block=None):
+    """Builds (oracle form, CUDA integrator) from the same arrays.
+
+    spaces: list of dicts from meshgen with 'mode' and optional 'role' (0 input, 1 param).
+    params: list of oracle parameter dicts for the PARAM fields / quadrature functions."""
+    import mfem_ad_b200 as M
+    inputs = [s for s in spaces if s.get("role", 0) == 0]
+    of = O.OracleForm(mesh, inputs, fspec.oracle(), quad_order=quad_order, params=params, block=block, ess=ess)
+    gm = M.Mesh(ctx, mesh)
+    gs = [M.Space(ctx, gm, s) for s in spaces]
+    gf = fspec.madb(ctx)
+    gi = M.Integrator(ctx, [(gs[i], spaces[i]["mode"], spaces[i].get("role", 0)) for i in range(len(spaces))], gf,
+                      quad_order=quad_order)
+    if len(ess):
+        gi.set_essential(ess)
+    gi._keepalive = (gm, gs, gf)
+    return of, gi
+
+
+def csr_rel_err(vals, ref):
+    """max |vals-ref| relative to the largest reference entry (norm-relative, SURVEY 7 'Determinism + 1e-12')."""
+    return np.max(np.abs(vals - ref)) / max(np.max(np.abs(ref)), 1e-300)
