@@ -134,7 +134,7 @@ struct Integrator
    int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
    int *d_rowptr = nullptr, *d_colidx = nullptr;
    double *d_energy = nullptr, *d_esum = nullptr;
-   double *d_x = nullptr, *d_v = nullptr, *d_y = nullptr, *d_vals = nullptr; // staging for host callers
+   double *d_x = nullptr, *d_v = nullptr, *d_v2 = nullptr, *d_y = nullptr, *d_vals = nullptr; // staging for host callers
    std::vector<double *> d_pstage;                                           // staging of parameter fields
    double *d_qf = nullptr;
    size_t qf_count = 0;

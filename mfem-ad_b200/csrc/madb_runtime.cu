@@ -51,7 +51,7 @@ Integrator::~Integrator()
 {
    cudaFree(d_e2n); cudaFree(d_vmap); cudaFree(d_pmap); cudaFree(d_e2csr);
    cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_energy); cudaFree(d_esum);
-   cudaFree(d_x); cudaFree(d_v); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
+   cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
 }
 
@@ -94,6 +94,12 @@ __global__ void k_ess_zero(const int *ess, int n, double *y)
 {
    const int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i < n) { y[ess[i]] = 0.0; }
+}
+// y[ess] = v[ess]: rows of the eliminated Jacobian are unit rows
+__global__ void k_ess_copy(const int *ess, int n, const double *v, double *y)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { y[ess[i]] = v[ess[i]]; }
 }
 // SparseMatrix::EliminateRowCol(rc, DIAG_ONE) on a symmetric pattern with sorted columns
 __global__ void k_ess_rowcol(const int *ess, int n, const int *rowptr, const int *colidx, double *vals)
@@ -318,7 +324,20 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    L.phi = I.phi.data(); L.dphi = I.dphi.data(); L.gdphi = I.gdphi.data(); L.w = I.w.data();
 
    if (stage_in(I, x, N, &I.d_x, &L.x)) { return 2; }
-   if (mode == MODE_ACT) { if (stage_in(I, v, N, &I.d_v, &L.v)) { return 2; } }
+   const double *v_orig = nullptr; // device copy of the caller's direction
+   if (mode == MODE_ACT)
+   {
+      if (stage_in(I, v, N, &I.d_v, &L.v)) { return 2; }
+      v_orig = L.v;
+      if (I.ness > 0)
+      {
+         // action of the eliminated Jacobian (EliminateRowCol): columns of essential dofs drop out
+         if (!I.d_v2) { CUDA_OK(cudaMalloc((void **)&I.d_v2, std::max<size_t>(N, 1) * sizeof(double))); }
+         CUDA_OK(cudaMemcpyAsync(I.d_v2, L.v, N * sizeof(double), cudaMemcpyDeviceToDevice, I.ctx->stream));
+         k_ess_zero<<<(I.ness + 127) / 128, 128, 0, I.ctx->stream>>>(I.d_ess, I.ness, I.d_v2);
+         L.v = I.d_v2;
+      }
+   }
    double *dy = nullptr, *dvals = nullptr;
    if (y) { if (stage_out_begin(I, y, N, &I.d_y, &dy)) { return 2; } }
    if (vals)
@@ -351,7 +370,8 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    if (I.ness > 0)
    {
       const int g = (I.ness + 127) / 128;
-      if (dy) { k_ess_zero<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, dy); }
+      if (dy && mode == MODE_ACT) { k_ess_copy<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, v_orig, dy); }
+      else if (dy) { k_ess_zero<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, dy); }
       if (dvals) { k_ess_rowcol<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, I.d_rowptr, I.d_colidx, dvals); }
    }
    bool sync = false;
