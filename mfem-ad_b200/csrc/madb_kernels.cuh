@@ -498,35 +498,48 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs
    }
 
    // ---- scatter --------------------------------------------------------------------
+   // Map entries are read through the read-only path in row batches, ahead of the
+   // dependent loads/stores, so that a warp keeps NVD independent requests in flight
+   // (the first version serialised 81 map-load -> store round trips: 75 % of all
+   // stall samples, profiles/r01_v1_k_element.md).
    if constexpr (MODE == MODE_ENERGY) { a.energy[t] = energy; }
    if constexpr ((MODE & (MODE_RES | MODE_ACT)) != 0)
    {
       if (a.write_y)
       {
+         double *__restrict__ y = a.y;
+         int m[NVD];
+         double old[NVD];
 #pragma unroll
-         for (int i = 0; i < NVD; i++)
-         {
-            const int m = a.vmap[(size_t)i * a.stride + t];
-            const int idx = m & 0x7fffffff;
-            a.y[idx] = (m < 0) ? r[i] : a.y[idx] + r[i];
-         }
+         for (int i = 0; i < NVD; i++) { m[i] = __ldg(a.vmap + (size_t)i * a.stride + t); }
+#pragma unroll
+         for (int i = 0; i < NVD; i++) { old[i] = (m[i] < 0) ? 0.0 : y[m[i] & 0x7fffffff]; }
+#pragma unroll
+         for (int i = 0; i < NVD; i++) { y[m[i] & 0x7fffffff] = old[i] + r[i]; }
       }
    }
    if constexpr ((MODE & MODE_JAC) != 0)
    {
       if (a.write_vals)
       {
+         double *__restrict__ vals = a.vals;
+         const int *__restrict__ e2csr = a.e2csr + t;
+         int m[2][NVD];
+#pragma unroll
+         for (int j = 0; j < NVD; j++) { m[0][j] = __ldg(e2csr + (size_t)j * a.stride); }
 #pragma unroll
          for (int i = 0; i < NVD; i++)
          {
-#pragma unroll
-            for (int j = 0; j < NVD; j++)
+            if (i + 1 < NVD)
             {
-               const int m = a.e2csr[(size_t)(i * NVD + j) * a.stride + t];
-               const int p = m & 0x7fffffff;
-               const double val = A[symidx(i, j)];
-               a.vals[p] = (m < 0) ? val : a.vals[p] + val;
+#pragma unroll
+               for (int j = 0; j < NVD; j++) { m[(i + 1) & 1][j] = __ldg(e2csr + (size_t)((i + 1) * NVD + j) * a.stride); }
             }
+            double old[NVD];
+#pragma unroll
+            for (int j = 0; j < NVD; j++) { old[j] = (m[i & 1][j] < 0) ? 0.0 : vals[m[i & 1][j] & 0x7fffffff]; }
+#pragma unroll
+            for (int j = 0; j < NVD; j++) { vals[m[i & 1][j] & 0x7fffffff] = old[j] + A[symidx(i, j)]; }
          }
       }
    }
