@@ -1,0 +1,10 @@
+// Fused-kernel instances: vector H1 spaces, ADEval::GRAD | ADEval::VECTOR (ex3, config-4 state block).
+#include "madb_functionals.cuh"
+#include "madb_registry.cuh"
+using namespace madb;
+
+using Elast2 = LinearElasticityEnergy<2>;
+using V1 = Config<2, 3, Field<2, 2, EV_GRAD>>; // order 1
+using V2 = Config<2, 4, Field<3, 2, EV_GRAD>>; // order 2
+MADB_INSTANCE("elasticity", Elast2, V1, true)
+MADB_INSTANCE("elasticity", Elast2, V2, false)

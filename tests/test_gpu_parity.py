@@ -138,3 +138,66 @@ def test_missing_configuration_fails_loudly(ctx):
         M.Integrator(ctx, [(gs, O.GRAD)], S.FSpec("nosuchenergy", 2).madb(ctx))
     with pytest.raises(M.MadbError, match="not supported"):
         M.Integrator(ctx, [(gs, O.HESSIAN)], S.diffusion(2).madb(ctx))  # isValidADEval, src/_ad_intg.hpp:58-59
+
+
+def _block_state(mesh, spaces, seed=7):
+    rng = np.random.default_rng(seed)
+    parts = []
+    for s in spaces:
+        parts.append(rng.uniform(-1, 1, s["ndofs"] * s.get("vdim", 1)))
+    return np.concatenate(parts)
+
+
+@pytest.mark.parametrize("order,perturb", [(1, 0.0), (1, 0.2), (2, 0.15)])
+def test_ex4_obstacle_pg_block(ctx, order, perturb):
+    """ex4.cpp:99-142: H1(p+1) x L2(p-1), ADPGFunctional(ObstacleEnergy, FermiDirac(0,0.5), psi_k),
+    ADBlockNonlinearFormIntegrator<VALUE|GRAD, VALUE>, rule order 3p+3; essential bc on the H1 block."""
+    mesh = G.cartesian_mesh((5, 4), perturb=perturb)
+    h1 = G.permute_dofs(G.h1_space(mesh, order + 1, mode=O.VALUE | O.GRAD), 3)
+    l2 = G.l2_space(mesh, order - 1, mode=O.VALUE)
+    alpha = 0.4
+    fs = S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), alpha)
+    rng = np.random.default_rng(11)
+    psik = rng.normal(0, 1, l2["ndofs"])
+    ess = h1["perm"][G.boundary_dofs(mesh, G.h1_space(mesh, order + 1))]
+    spaces = [h1, l2, dict(l2, role=1)]
+    of, gi = S.make_pair(ctx, mesh, spaces, fs, quad_order=3 * order + 3, ess=ess,
+                         params=[dict(type=O.PRM_GF, size=1, data=psik, space=l2)])
+    gi.set_param_field(2, psik)
+    x = _block_state(mesh, [h1, l2])
+    _compare(of, gi, x)
+    # alpha changes every PG step (ex4.cpp:185-187), psi_k too (:188-189)
+    psik2 = x[h1["ndofs"]:].copy()
+    gi.fn.set_params([3.2])
+    gi.set_param_field(2, psik2)
+    of2 = O.OracleForm(mesh, [h1, l2], S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), 3.2).oracle(),
+                       quad_order=3 * order + 3, ess=ess, params=[dict(type=O.PRM_GF, size=1, data=psik2, space=l2)])
+    assert S.csr_rel_err(gi.mult(x), of2.mult(x)) <= TOL
+    assert S.csr_rel_err(gi.grad(x), of2.grad(x)[2]) <= TOL
+
+
+def test_ex5_gradient_constraint_pg_block_on_quads(ctx):
+    """ex5.cpp:88-140 on quadrilaterals: H1(p) x H1(p-1)^dim, modes GRAD / VALUE|VECTOR, HellingerEntropy."""
+    mesh = G.cartesian_mesh((4, 5), perturb=0.15)
+    u = G.h1_space(mesh, 2, mode=O.GRAD)
+    lat = G.h1_space(mesh, 1, vdim=2, mode=O.VALUE | O.VECTOR)
+    fs = S.pg(S.gradobstacle(2), S.hellinger(2, 0.6), 0.8)
+    psik = np.random.default_rng(2).normal(0, 1, 2 * lat["ndofs"])
+    spaces = [u, lat, dict(lat, role=1)]
+    of, gi = S.make_pair(ctx, mesh, spaces, fs, params=[dict(type=O.PRM_GF, size=2, data=psik, space=lat)])
+    gi.set_param_field(2, psik)
+    _compare(of, gi, _block_state(mesh, [u, lat]))
+
+
+@pytest.mark.parametrize("p,ordering", [(1, 0), (2, 0), (1, 1)])
+def test_ex3_vector_elasticity(ctx, p, ordering):
+    """ex3.cpp:50-63: vector H1 space, GRAD|VECTOR, LinearElasticityEnergy.  The CUDA path implements the
+    index-consistent contraction (= the block integrator, src/ad_intg.hpp:700-727); it equals the
+    single-space code (src/ad_intg.hpp:310-326) exactly when lambda == mu (ex3's case), see SURVEY H1."""
+    mesh = G.cartesian_mesh((4, 3), perturb=0.1)
+    s = G.h1_space(mesh, p, vdim=2, ordering=ordering, mode=O.GRAD | O.VECTOR)
+    x = _block_state(mesh, [s])
+    of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 1.0, 1.0), block=0)  # reference single-space arithmetic
+    _compare(of, gi, x)
+    of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 2.0, 0.7), block=1)  # consistent variant, lambda != mu
+    _compare(of, gi, x)
