@@ -1,0 +1,70 @@
+"""Host-side outer loops that drive the batched assembly: Newton and the LVPP /
+proximal-Galerkin iteration of the reference's drivers.
+
+    newton()      <-> mfem::NewtonSolver::Mult [MFEM-upstream] as configured at ex4.cpp:166-176
+    lvpp_solve()  <-> the outer loop of ex4.cpp:183-219 / ex5.cpp:174-212
+
+The linear solve inside Newton is out of scope of the hot path;
+both the CUDA path and the CPU oracle are driven through the same SuperLU
+factorisation (scipy) so that iteration counts are comparable.  `op` is any object
+with  mult(x) -> residual,  grad(x) -> CSR values,  pattern() -> (rowptr, colidx).
+"""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+def newton(op, b, x, abs_tol=1e-9, rel_tol=0.0, max_iter=20):
+    """x is updated in place (iterative_mode = true).  Returns (converged, iterations, final_norm)."""
+    rowptr, colidx = op.pattern()
+    n = x.size
+    r = op.mult(x) - b
+    norm = np.linalg.norm(r)
+    norm_goal = max(rel_tol * norm, abs_tol)
+    it = 0
+    while True:
+        if norm <= norm_goal:
+            return True, it, norm
+        if it >= max_iter:
+            return False, it, norm
+        vals = op.grad(x)
+        J = sp.csr_matrix((vals, colidx, rowptr), shape=(n, n)).tocsc()
+        c = spla.splu(J).solve(r)
+        x -= c
+        r = op.mult(x) - b
+        norm = np.linalg.norm(r)
+        it += 1
+
+
+def lvpp_solve(op, set_alpha, set_latent_k, alpha_rule, b, x, latent_slice, l1_norm, max_pg=100, tol=1e-10,
+               newton_kw=None, log=None):
+    """Outer proximal-Galerkin loop (ex4.cpp:183-219).
+
+    set_alpha(alpha), set_latent_k(psi_k) update the functional between steps;
+    latent_slice selects psi inside x; l1_norm(v) = || v ||_{L1(Omega)} of a latent-space function.
+    Returns dict(pg_iterations, newton_iterations[list], converged, lambda_diff[list])."""
+    newton_kw = newton_kw or {}
+    psi = x[latent_slice]
+    lam_prev = np.zeros_like(psi)
+    hist = dict(pg_iterations=0, newton_iterations=[], lambda_diff=[], converged=False, newton_failed=False)
+    for i in range(max_pg):
+        alpha = alpha_rule.get(i)
+        set_alpha(alpha)
+        psik = x[latent_slice].copy()
+        set_latent_k(psik)
+        ok, its, nrm = newton(op, b, x, **newton_kw)
+        hist["newton_iterations"].append(its)
+        hist["pg_iterations"] = i + 1
+        if not ok:
+            hist["newton_failed"] = True
+            break
+        lam = (x[latent_slice] - psik) / alpha
+        diff = l1_norm(lam - lam_prev)
+        hist["lambda_diff"].append(diff)
+        if log:
+            log("PG %d alpha=%g newton=%d res=%.3e lambda_diff=%.3e" % (i + 1, alpha, its, nrm, diff))
+        if diff < tol:
+            hist["converged"] = True
+            break
+        lam_prev = lam
+    return hist

@@ -136,3 +136,67 @@ def boundary_dofs(mesh, space, tol=1e-12):
     for d in range(mesh["dim"]):
         on |= (np.abs(xc[:, d]) < tol) | (np.abs(xc[:, d] - mesh["lengths"][d]) < tol)
     return np.nonzero(on)[0].astype(np.int32)
+
+
+def _tables(space, dim, xq):
+    nodes = gauss_lobatto_01(space["order"] + 1) if space["basis"] == 0 else gauss_legendre_01(space["order"] + 1)[0]
+    B = _lagrange(nodes, xq)  # [nq1, nn]
+    nn, nq1 = len(nodes), len(xq)
+    nd, nq = nn ** dim, nq1 ** dim
+    phi = np.ones((nq, nd))
+    for q in range(nq):
+        for i in range(nd):
+            rq, ri, v = q, i, 1.0
+            for d in range(dim):
+                v *= B[rq % nq1, ri % nn]
+                rq //= nq1
+                ri //= nn
+            phi[q, i] = v
+    return phi
+
+
+def load_vector(mesh, space, f, nq1d=None):
+    """b_i = int f phi_i  (DomainLFIntegrator, ex4.cpp:145-148) with a tensor Gauss rule; host numpy."""
+    dim = mesh["dim"]
+    nq1d = nq1d or space["order"] + 3
+    xq, wq = gauss_legendre_01(nq1d)
+    phi = _tables(space, dim, xq)
+    geo = dict(basis=0, order=1)
+    gphi = _tables(geo, dim, xq)  # vertex (bilinear) shape values at the points
+    N2 = _lagrange(np.array([0.0, 1.0]), xq)
+    dN2 = np.stack([-np.ones_like(xq), np.ones_like(xq)], axis=1)
+    nq = nq1d ** dim
+    X = mesh["coords"][mesh["e2n"]]  # [ne, nv, dim]
+    xphys = np.einsum("qv,evd->eqd", gphi, X)
+    # Jacobian determinants
+    dg = np.zeros((nq, 2 ** dim, dim))
+    for q in range(nq):
+        for v in range(2 ** dim):
+            for k in range(dim):
+                rq, val = q, 1.0
+                for d in range(dim):
+                    t = rq % nq1d
+                    rq //= nq1d
+                    val *= dN2[t, (v >> d) & 1] if d == k else N2[t, (v >> d) & 1]
+                dg[q, v, k] = val
+    J = np.einsum("evi,qvk->eqik", X, dg)
+    det = np.linalg.det(J)
+    w = np.ones(nq)
+    for q in range(nq):
+        rq = q
+        for d in range(dim):
+            w[q] *= wq[rq % nq1d]
+            rq //= nq1d
+    fq = f(xphys)  # [ne, nq]
+    be = np.einsum("eq,q,eq,qi->ei", fq, w, det, phi)
+    b = np.zeros(space["ndofs"])
+    np.add.at(b, space["e2l"], be)
+    return b
+
+
+def lumped_weights(mesh, space):
+    """Nodal quadrature weights (reference weight x |det J| at the node) of an L2 Gauss-Legendre space."""
+    dim, p = mesh["dim"], space["order"]
+    xq, wq = gauss_legendre_01(p + 1)
+    one = load_vector(mesh, space, lambda x: np.ones(x.shape[:2]), nq1d=p + 1)
+    return one  # with the collocated rule phi_i(x_q) = delta_iq, so b_i = w_i det J_i
