@@ -33,12 +33,17 @@ struct LaunchCtx
    const double *fparams; // host
    // host tables, laid out exactly as madb::Tables<Cfg>
    const double *phi, *dphi, *gdphi, *w;
+   // 1-D tables per field [nq1d][nd1d], 1-D points and weights (sum-factorised kernels)
+   const double *b1d[8], *g1d[8];
+   const double *xq1d, *w1d;
 };
 
 struct KernelOps
 {
    int (*launch)(const LaunchCtx &, int mode);
    int n_input, n_fparam, n_qprm, n_field_qprm, nvd, ndof_all, nq, ntab, dim;
+   int map_aos = 0;          // element maps stored [t][k] instead of [k][stride]
+   int matrix_free_only = 0; // no assembled Jacobian (use grad_mult)
 };
 
 std::map<std::string, KernelOps> &registry();
@@ -140,6 +145,8 @@ struct Integrator
    size_t qf_count = 0;
    std::vector<const double *> pdata; // device pointers of the parameter fields (per field)
    std::vector<double> phi, dphi, gdphi, w;
+   std::vector<std::vector<double>> b1d, g1d;
+   std::vector<double> xq1d, w1d;
 
    // essential dofs
    int ness = 0;

@@ -69,6 +69,8 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
 template <class Func, class Cfg, bool UNROLLQ> KernelOps make_ops()
 {
    KernelOps o;
+   o.map_aos = 0;
+   o.matrix_free_only = 0;
    o.launch = &launch_impl<Func, Cfg, UNROLLQ>;
    o.n_input = Cfg::N_INPUT;
    o.n_fparam = Func::N_PARAM;

@@ -172,16 +172,17 @@ static int setup_integrator(Integrator &I)
        pmap((size_t)std::max(I.npd, 1) * I.stride, 0);
    std::vector<unsigned char> touched(I.ntotal, 0);
    std::vector<int> vd;
+   const bool aos = I.ops.map_aos != 0;
    for (int t = 0; t < I.ne; t++)
    {
       const int e = I.perm[t];
-      for (int k = 0; k < ngn; k++) { e2n[(size_t)k * I.stride + t] = I.mesh->e2n[(size_t)e * ngn + k]; }
+      for (int k = 0; k < ngn; k++) { e2n[aos ? (size_t)t * ngn + k : (size_t)k * I.stride + t] = I.mesh->e2n[(size_t)e * ngn + k]; }
       build_vdofs(I, e, vd);
       for (int i = 0; i < I.nvd; i++)
       {
          int m = vd[i];
          if (!touched[m]) { touched[m] = 1; m |= 0x80000000; } // colours ascend with t
-         vmap[(size_t)i * I.stride + t] = m;
+         vmap[aos ? (size_t)t * I.nvd + i : (size_t)i * I.stride + t] = m;
       }
       int k = 0;
       for (const FieldDesc &f : I.fields)
@@ -194,7 +195,7 @@ static int setup_integrator(Integrator &I)
             for (int i = 0; i < nd; i++)
             {
                const int d = S.e2l[(size_t)e * nd + i];
-               pmap[(size_t)k * I.stride + t] = (S.ordering == ORD_BYNODES) ? d + S.ndofs * c : d * S.vdim + c;
+               pmap[aos ? (size_t)t * I.npd + k : (size_t)k * I.stride + t] = (S.ordering == ORD_BYNODES) ? d + S.ndofs * c : d * S.vdim + c;
                k++;
             }
          }
@@ -241,6 +242,8 @@ static int setup_integrator(Integrator &I)
       }
    };
    int toff = 0;
+   I.b1d.clear(); I.g1d.clear();
+   I.xq1d = xq; I.w1d = wq;
    for (const FieldDesc &f : I.fields)
    {
       std::vector<double> nodes, wtmp;
@@ -248,6 +251,10 @@ static int setup_integrator(Integrator &I)
       else { gauss_legendre_01(f.space->order + 1, nodes, wtmp); }
       fill_tables(nodes, toff, ntab, I.phi.data(), I.dphi.data());
       toff += f.space->nd_el();
+      std::vector<double> B, Gd;
+      lagrange_tables(nodes, xq, B, Gd);
+      I.b1d.push_back(B);
+      I.g1d.push_back(Gd);
    }
    fill_tables(std::vector<double> {0.0, 1.0}, 0, ngn, nullptr, I.gdphi.data());
    for (int q = 0; q < I.nq; q++)
@@ -322,6 +329,8 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    fp.push_back(0.0);
    L.fparams = fp.data();
    L.phi = I.phi.data(); L.dphi = I.dphi.data(); L.gdphi = I.gdphi.data(); L.w = I.w.data();
+   for (size_t f = 0; f < I.fields.size(); f++) { L.b1d[f] = I.b1d[f].data(); L.g1d[f] = I.g1d[f].data(); }
+   L.xq1d = I.xq1d.data(); L.w1d = I.w1d.data();
 
    if (stage_in(I, x, N, &I.d_x, &L.x)) { return 2; }
    const double *v_orig = nullptr; // device copy of the caller's direction
@@ -342,6 +351,7 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    if (y) { if (stage_out_begin(I, y, N, &I.d_y, &dy)) { return 2; } }
    if (vals)
    {
+      if (I.ops.matrix_free_only) { set_error("configuration '" + I.key + "' is matrix-free only: use madb_integrator_grad_mult"); return 1; }
       if (ensure_pattern_device(I)) { return 1; }
       if (stage_out_begin(I, vals, I.colidx.size(), &I.d_vals, &dvals)) { return 2; }
       L.e2csr = I.d_e2csr;

