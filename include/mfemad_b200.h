@@ -105,6 +105,24 @@ int madb_functional_destroy(madb_functional *f);
 int madb_functional_eval(madb_ctx *ctx, madb_functional *f, int n_input, int npts, const double *x,
                          const double *qprm, double *value, double *grad, double *hess);
 
+/* DOF-collocated proximal-Galerkin terms of ADDofPGNonlinearFormIntegrator
+ * (src/_dof_pg.hpp:17-63, src/dof_pg.hpp:66-128 residual, :131-231 Jacobian diagonals) for one
+ * primal/latent pair with a scalar entropy, one thread per dof:
+ *   r_u[j] += (psi_j-psi_k,j) w_j/alpha ; r_psi[j] = (u_j - E*'(psi_j)) w_j/alpha ;
+ *   d_pp[j] = -E*''(psi_j) w_j/alpha ; d_up[j] = w_j/alpha.
+ * w = nodal (lumped) weights: the reference takes them from FiniteElement::GetNodes(), whose
+ * weights are zero in MFEM; zeros reproduce the reference, lumped-mass weights make
+ * the variant useful.  Outputs may be NULL. */
+int madb_dofpg_nodal(madb_ctx *ctx, madb_functional *entropy, int n, double alpha, const double *u,
+                     const double *psi, const double *psik, const double *w, double *r_u, double *r_psi,
+                     double *d_pp, double *d_up);
+
+/* Fused LVPP latent-variable update between proximal steps (ex4.cpp:188-189, :203-218):
+ *   lambda = (psi-psi_k)/alpha ; *lambda_diff = sum_j w_j |lambda_j - lambda_prev_j| ;
+ *   lambda_prev <- lambda ; psi_k <- psi.   w may be NULL (unit weights). */
+int madb_lvpp_update(madb_ctx *ctx, int n, double alpha, const double *psi, double *psik, double *lambda_prev,
+                     const double *w, double *lambda_diff);
+
 /* AD(Block)NonlinearFormIntegrator<modes...>(f, ir) attached to its form
  * (src/_ad_intg.hpp:71-155, :157-327).  fields: spaces[i] with ADEval modes[i];
  * roles[i] = MADB_ROLE_INPUT for a differentiated unknown (a block of x), or
@@ -139,6 +157,10 @@ int madb_integrator_pattern(madb_integrator *I, int64_t *nrows, int64_t *nnz, in
 int madb_integrator_grad_assemble(madb_integrator *I, const double *x, double *vals);
 /* residual + Jacobian at the same state in one pass (one Newton iteration's assembly) */
 int madb_integrator_assemble(madb_integrator *I, const double *x, double *y, double *vals);
+/* DifferentiableCoefficient::Eval and ::Gradient().Eval projected to the rule's points
+ * (src/ad_native.hpp:267-323; ex4.cpp:124-128,200: the latent->primal map grad E*(psi) as a
+ * QuadratureFunction).  value [ne*nq] and/or grad [ne*nq*n_input] (may be NULL), layout [e][q][.] */
+int madb_integrator_coefficient(madb_integrator *I, const double *x, double *value, double *grad);
 /* matrix-free Jacobian action y = J(x) v (no reference equivalent; config 3) */
 int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y);
 

@@ -56,6 +56,8 @@ def lib():
         L.madb_functional_set_params.argtypes = [vp, C.c_int, dp]
         L.madb_functional_destroy.argtypes = [vp]
         L.madb_functional_eval.argtypes = [vp, vp, C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        L.madb_dofpg_nodal.argtypes = [vp, vp, C.c_int, C.c_double, dp, dp, dp, dp, dp, dp, dp, dp]
+        L.madb_lvpp_update.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_double)]
         L.madb_integrator_create.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, pp]
         L.madb_integrator_destroy.argtypes = [vp]
         L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -68,6 +70,7 @@ def lib():
         L.madb_integrator_grad_assemble.argtypes = [vp, dp, dp]
         L.madb_integrator_assemble.argtypes = [vp, dp, dp, dp]
         L.madb_integrator_grad_mult.argtypes = [vp, dp, dp, dp]
+        L.madb_integrator_coefficient.argtypes = [vp, dp, dp, dp]
         _lib = L
     return _lib
 
@@ -258,6 +261,17 @@ class Integrator:
         _check(lib().madb_integrator_assemble(self.h, _ptr(x), _ptr(y), _ptr(vals)))
         return y, vals
 
+    def coefficient(self, x, want_value=True, want_grad=True):
+        """f and grad f at every quadrature point, [ne, nq] and [ne, nq, n] (DifferentiableCoefficient)."""
+        x = _f64(x)
+        ne = self.fields[0][0].mesh.ne
+        n_in = sum((1 if m & VALUE else 0) + (s.mesh.dim if m & GRAD else 0) for s, m, r in self.fields if r == ROLE_INPUT
+                   for _ in range(s.desc.get("vdim", 1)))
+        val = np.empty((ne, self.nq_el)) if want_value else None
+        grd = np.empty((ne, self.nq_el, n_in)) if want_grad else None
+        _check(lib().madb_integrator_coefficient(self.h, _ptr(x), _ptr(val), _ptr(grd)))
+        return val, grd
+
     def grad_mult(self, x, v, y=None):
         if isinstance(x, np.ndarray):
             x, v = _f64(x), _f64(v)
@@ -270,6 +284,25 @@ class Integrator:
             lib().madb_integrator_destroy(self.h)
         except Exception:
             pass
+
+
+def dofpg_nodal(ctx, entropy, alpha, u, psi, psik, w, r_u=None):
+    """Nodal PG terms (src/dof_pg.hpp); returns r_u (accumulated into the given array), r_psi, d_pp, d_up."""
+    u, psi, psik, w = _f64(u), _f64(psi), _f64(psik), _f64(w)
+    n = u.size
+    r_u = np.zeros(n) if r_u is None else r_u
+    r_psi, d_pp, d_up = np.empty(n), np.empty(n), np.empty(n)
+    _check(lib().madb_dofpg_nodal(ctx.h, entropy.h, n, alpha, _ptr(u), _ptr(psi), _ptr(psik), _ptr(w), _ptr(r_u),
+                                  _ptr(r_psi), _ptr(d_pp), _ptr(d_up)))
+    return r_u, r_psi, d_pp, d_up
+
+
+def lvpp_update(ctx, alpha, psi, psik, lambda_prev, w=None):
+    """Fused latent update; psik and lambda_prev are overwritten; returns the weighted l1 change of lambda."""
+    d = C.c_double()
+    n = psi.numel() if hasattr(psi, "numel") else psi.size
+    _check(lib().madb_lvpp_update(ctx.h, n, alpha, _ptr(psi), _ptr(psik), _ptr(lambda_prev), _ptr(w), C.byref(d)))
+    return d.value
 
 
 class PGStepSizeRule:

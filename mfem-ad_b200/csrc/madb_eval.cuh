@@ -18,6 +18,9 @@ struct EvalOps
    int (*launch)(cudaStream_t, int npts, const double *fparams_host, const double *x, const double *qprm,
                  double *value, double *grad, double *hess);
    int n_input, n_fparam, n_qprm;
+   // nodal proximal-Galerkin terms (scalar entropies only, else null)
+   int (*dofpg)(cudaStream_t, int n, const double *fparams_host, double alpha, const double *u, const double *psi,
+                const double *psik, const double *w, double *r_u, double *r_psi, double *d_pp, double *d_up);
 };
 std::map<std::string, EvalOps> &eval_registry();
 struct EvalRegistrar
@@ -48,15 +51,65 @@ template <class Func> __global__ void __launch_bounds__(128) k_eval(const EvalAr
 #pragma unroll
    for (int m = 0; m < N; m++) { xs[m] = ad_seed<N, 2>(a.x[(size_t)p * N + m], m); }
    const T r = f(xs, qp);
-   a.value[p] = r.v;
-#pragma unroll
-   for (int i = 0; i < N; i++) { a.grad[(size_t)p * N + i] = r.g[i]; }
-#pragma unroll
-   for (int i = 0; i < N; i++)
+   if (a.value) { a.value[p] = r.v; }
+   if (a.grad)
    {
 #pragma unroll
-      for (int j = 0; j < N; j++) { a.hess[((size_t)p * N + i) * N + j] = r.hess(i, j); }
+      for (int i = 0; i < N; i++) { a.grad[(size_t)p * N + i] = r.g[i]; }
    }
+   if (a.hess)
+   {
+#pragma unroll
+      for (int i = 0; i < N; i++)
+      {
+#pragma unroll
+         for (int j = 0; j < N; j++) { a.hess[((size_t)p * N + i) * N + j] = r.hess(i, j); }
+      }
+   }
+}
+
+// DOF-collocated proximal-Galerkin terms (ADDofPGNonlinearFormIntegrator, src/dof_pg.hpp:113-125,
+// :210-228): one thread per dof j with nodal weight w_j (an explicit input):
+//   r_u[j]  += (psi_j - psi_k,j) w_j/alpha        r_psi[j]  = (u_j - E*'(psi_j)) w_j/alpha
+//   d_pp[j]  = -E*''(psi_j) w_j/alpha             d_up[j]   = w_j/alpha
+template <class Func> struct DofPGArgs
+{
+   int n;
+   double alpha;
+   const double *u, *psi, *psik, *w;
+   double *r_u, *r_psi, *d_pp, *d_up;
+   double fparams[Func::N_PARAM > 0 ? Func::N_PARAM : 1];
+};
+template <class Func> __global__ void __launch_bounds__(256) k_dofpg(const DofPGArgs<Func> a)
+{
+   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+   if (j >= a.n) { return; }
+   Func f;
+   f.load(a.fparams);
+   const double ps = a.psi[j];
+   AD<1, 2> xs[1] = {ad_seed<1, 2>(ps, 0)};
+   const AD<1, 2> r = f(xs, (const double *)nullptr);
+   const double ww = a.w[j] / a.alpha;
+   if (a.r_u) { a.r_u[j] += (ps - a.psik[j]) * ww; }
+   if (a.r_psi) { a.r_psi[j] = (a.u[j] - r.g[0]) * ww; }
+   if (a.d_pp) { a.d_pp[j] = -r.h[0] * ww; }
+   if (a.d_up) { a.d_up[j] = ww; }
+}
+template <class Func> int dofpg_launch(cudaStream_t s, int n, const double *fp, double alpha, const double *u,
+                                       const double *psi, const double *psik, const double *w, double *r_u,
+                                       double *r_psi, double *d_pp, double *d_up)
+{
+   DofPGArgs<Func> a;
+   a.n = n; a.alpha = alpha; a.u = u; a.psi = psi; a.psik = psik; a.w = w;
+   a.r_u = r_u; a.r_psi = r_psi; a.d_pp = d_pp; a.d_up = d_up;
+   for (int i = 0; i < Func::N_PARAM; i++) { a.fparams[i] = fp[i]; }
+   k_dofpg<Func><<<(n + 255) / 256, 256, 0, s>>>(a);
+   return (int)cudaGetLastError();
+}
+template <class Func> constexpr auto dofpg_ptr()
+{
+   if constexpr (Func::N_INPUT == 1 && Func::N_QPRM == 0) { return &dofpg_launch<Func>; }
+   else { return (decltype(&dofpg_launch<Func>))nullptr; }
 }
 
 template <class Func> int eval_launch(cudaStream_t s, int npts, const double *fp, const double *x, const double *qprm,
@@ -74,6 +127,6 @@ template <class Func> int eval_launch(cudaStream_t s, int npts, const double *fp
 #define MADB_EVAL_INSTANCE(KIND, FUNC)                                                                              \
    static ::madb::EvalRegistrar MADB_EVAL_CAT(madb_evreg_, __COUNTER__)(                                            \
       std::string(KIND) + "|n" + std::to_string(FUNC::N_INPUT),                                                     \
-      ::madb::EvalOps {&::madb::eval_launch<FUNC>, FUNC::N_INPUT, FUNC::N_PARAM, FUNC::N_QPRM});
+      ::madb::EvalOps {&::madb::eval_launch<FUNC>, FUNC::N_INPUT, FUNC::N_PARAM, FUNC::N_QPRM, ::madb::dofpg_ptr<FUNC>()});
 
 } // namespace madb

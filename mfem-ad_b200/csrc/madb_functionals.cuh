@@ -349,4 +349,53 @@ template <int DIM> struct ParametrizedCompliance
    }
 };
 
+
+// ParametrizedCompliance whose lambda(rho), mu(rho) are evaluated in-kernel from the design
+// field at the point (src/mmto.hpp:43-109 "normal mode": only the f_i(design) are evaluated,
+// :103-108).  FL, FM: the parameter functions (e.g. SIMPFunction); qp = rho at the point.
+template <int DIM, class FL, class FM> struct ParametrizedComplianceOf
+{
+   static_assert(FL::N_INPUT == FM::N_INPUT, "lambda and mu take the same design vector");
+   static constexpr int N_INPUT = DIM * DIM, N_PARAM = FL::N_PARAM + FM::N_PARAM, N_QPRM = FL::N_INPUT;
+   FL fl;
+   FM fm;
+   MADB_HD void load(const double *p) { fl.load(p); fm.load(p + FL::N_PARAM); }
+   template <class T> MADB_HD T operator()(const T *gradu, const double *rho) const
+   {
+      const double lambda = fl(rho, (const double *)nullptr), mu = fm(rho, (const double *)nullptr);
+      return LinearElasticityEnergy<DIM>::body(gradu, lambda, mu);
+   }
+};
+
+// The same energy as a function of the DESIGN with the state gradient as per-point
+// parameter: its gradient w.r.t. rho is the design sensitivity dF/drho_j; the reference's
+// ParamGradient (src/mmto.cpp:25-37) returns dF/drho_j + (m-1) F with m = 2 parameter
+// functions -- both are formed from value and gradient of this functional.
+template <int DIM, class FL, class FM> struct DesignComplianceOf
+{
+   static constexpr int N_INPUT = FL::N_INPUT, N_PARAM = FL::N_PARAM + FM::N_PARAM, N_QPRM = DIM * DIM;
+   FL fl;
+   FM fm;
+   MADB_HD void load(const double *p) { fl.load(p); fm.load(p + FL::N_PARAM); }
+   template <class T> MADB_HD T operator()(const T *rho, const double *gradu) const
+   {
+      const T lambda = fl(rho, (const double *)nullptr), mu = fm(rho, (const double *)nullptr);
+      double div = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; i++) { div += gradu[i * DIM + i]; }
+      double h1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < DIM; i++)
+      {
+#pragma unroll
+         for (int j = 0; j < DIM; j++)
+         {
+            const double s = 0.5 * (gradu[i * DIM + j] + gradu[j * DIM + i]);
+            h1 += s * s;
+         }
+      }
+      return (0.5 * div * div) * lambda + h1 * mu;
+   }
+};
+
 } // namespace madb

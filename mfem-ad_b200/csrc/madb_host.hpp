@@ -10,7 +10,7 @@
 namespace madb
 {
 
-enum { MODE_RES = 1, MODE_JAC = 2, MODE_ACT = 4, MODE_ENERGY = 8 };
+enum { MODE_RES = 1, MODE_JAC = 2, MODE_ACT = 4, MODE_ENERGY = 8, MODE_COEF = 16 };
 
 // ---- kernel registry -------------------------------------------------------------
 // Fused kernels are templates on <functional type, element configuration>.  Each
@@ -29,6 +29,8 @@ struct LaunchCtx
    const double *qf;
    const double *x, *v;
    double *y, *vals, *energy;
+   const int *perm;        // sorted position -> element (MODE_COEF output order)
+   double *cvalue, *cgrad; // MODE_COEF outputs [e][q], [e][q][n]
    int write_y, write_vals;
    const double *fparams; // host
    // host tables, laid out exactly as madb::Tables<Cfg>
@@ -137,7 +139,8 @@ struct Integrator
 
    // device data
    int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
-   int *d_rowptr = nullptr, *d_colidx = nullptr;
+   int *d_rowptr = nullptr, *d_colidx = nullptr, *d_perm = nullptr;
+   double *d_cvalue = nullptr, *d_cgrad = nullptr;
    double *d_energy = nullptr, *d_esum = nullptr;
    double *d_x = nullptr, *d_v = nullptr, *d_v2 = nullptr, *d_y = nullptr, *d_vals = nullptr; // staging for host callers
    std::vector<double *> d_pstage;                                           // staging of parameter fields

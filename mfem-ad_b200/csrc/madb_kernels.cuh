@@ -46,6 +46,8 @@ template <class Func, class Cfg> struct AsmArgs
    double *y;
    double *vals;
    double *energy; // [stride] per-element energies (sorted order)
+   const int *perm; // sorted position -> element
+   double *cvalue, *cgrad; // MODE_COEF: value [e][q] and gradient [e][q][N] at the points
    double fparams[Func::N_PARAM > 0 ? Func::N_PARAM : 1];
    Tables<Cfg> tab;
 };
@@ -89,17 +91,15 @@ MADB_HD constexpr int symidx(int a, int b) { return a <= b ? b * (b + 1) / 2 + a
 
 /// Everything the functional needs at one quadrature point, then the
 /// contribution of that point to the element vector / matrix.
-template <class Func, class Cfg, int MODE>
-__device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q, const int t,
-                                       const double (&X)[Cfg::NGN][Cfg::DIM],
-                                       const double (&u)[Cfg::NDOF_ALL],
-                                       const double (&vdir)[(MODE & MODE_ACT) ? Cfg::NVD : 1],
-                                       const Func &f,
-                                       double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
-                                       double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1],
-                                       double &energy)
+template <class Func, class Cfg>
+__device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const int q, const int t,
+                                              const double (&X)[Cfg::NGN][Cfg::DIM],
+                                              const double (&u)[Cfg::NDOF_ALL],
+                                              double (&xin)[Cfg::N_INPUT],
+                                              double (&qp)[Func::N_QPRM > 0 ? Func::N_QPRM : 1],
+                                              double (&Ji)[Cfg::DIM][Cfg::DIM], double &w)
 {
-   constexpr int DIM = Cfg::DIM, NF = Cfg::NF, N = Cfg::N_INPUT;
+   constexpr int DIM = Cfg::DIM, NF = Cfg::NF;
    using Args = AsmArgs<Func, Cfg>;
 
    // ---- geometry: J = sum_k X_k (x) dN_k/dxi ; Weight = det J ; J^-1 ------------
@@ -121,13 +121,11 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
          for (int i = 0; i < DIM; i++) { J[i][j] = fma(X[k][i], g, J[i][j]); }
       }
    }
-   double Ji[DIM][DIM], detJ;
+   double detJ;
    invert<DIM>(J, Ji, detJ);
-   const double w = a.tab.w[q] * detJ; // ip.weight * Tr.Weight()
+   w = a.tab.w[q] * detJ; // ip.weight * Tr.Weight()
 
    // ---- inputs x (physical) and field parameters ---------------------------------
-   double xin[N];
-   double qp[Func::N_QPRM > 0 ? Func::N_QPRM : 1];
    static_for<NF>([&](auto F)
    {
       constexpr int fi = decltype(F)::value;
@@ -170,8 +168,44 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
    });
 #pragma unroll
    for (int k = 0; k < Args::NQF; k++) { qp[Cfg::N_FIELD_QPRM + k] = a.qf[((size_t)k * Cfg::NQ + q) * a.stride + t]; }
+}
 
-   if constexpr (MODE == MODE_ENERGY)
+/// Contribution of one quadrature point to the element vector / matrix / energy.
+template <class Func, class Cfg, int MODE>
+__device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q, const int t,
+                                       const double (&X)[Cfg::NGN][Cfg::DIM],
+                                       const double (&u)[Cfg::NDOF_ALL],
+                                       const double (&vdir)[(MODE & MODE_ACT) ? Cfg::NVD : 1],
+                                       const Func &f,
+                                       double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
+                                       double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1],
+                                       double &energy)
+{
+   constexpr int DIM = Cfg::DIM, NF = Cfg::NF, N = Cfg::N_INPUT;
+   double xin[N];
+   double qp[Func::N_QPRM > 0 ? Func::N_QPRM : 1];
+   double Ji[DIM][DIM], w;
+   qpoint_inputs<Func, Cfg>(a, q, t, X, u, xin, qp, Ji, w);
+
+   if constexpr (MODE == MODE_COEF)
+   {
+      // DifferentiableCoefficient::Eval / Gradient().Eval at the point (src/ad_native.hpp:272-283,315-317):
+      // value and gradient of f w.r.t. its inputs, stored as quadrature functions [e][q][.]
+      using T = AD<N, 1>;
+      T xs[N];
+#pragma unroll
+      for (int m = 0; m < N; m++) { xs[m] = ad_seed<N, 1>(xin[m], m); }
+      const T res = f(xs, qp);
+      const size_t pt = (size_t)a.perm[t] * Cfg::NQ + q;
+      if (a.cvalue) { a.cvalue[pt] = res.v; }
+      if (a.cgrad)
+      {
+#pragma unroll
+         for (int m = 0; m < N; m++) { a.cgrad[pt * N + m] = res.g[m]; }
+      }
+      return;
+   }
+   else if constexpr (MODE == MODE_ENERGY)
    {
       energy += f(xin, qp) * w; // src/ad_intg.hpp:196
       return;

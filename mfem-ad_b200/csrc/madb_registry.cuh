@@ -41,16 +41,20 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
    a.y = L.y;
    a.vals = L.vals;
    a.energy = L.energy;
+   a.perm = L.perm;
+   a.cvalue = L.cvalue;
+   a.cgrad = L.cgrad;
    for (int i = 0; i < Func::N_PARAM; i++) { a.fparams[i] = L.fparams[i]; }
    std::memcpy(a.tab.phi, L.phi, sizeof(a.tab.phi));
    std::memcpy(a.tab.dphi, L.dphi, sizeof(a.tab.dphi));
    std::memcpy(a.tab.gdphi, L.gdphi, sizeof(a.tab.gdphi));
    std::memcpy(a.tab.w, L.w, sizeof(a.tab.w));
-   const int nlaunch = (mode == MODE_ENERGY) ? 1 : L.ncolors;
+   const bool whole = (mode == MODE_ENERGY || mode == MODE_COEF);
+   const int nlaunch = whole ? 1 : L.ncolors;
    for (int c = 0; c < nlaunch; c++)
    {
-      a.begin = (mode == MODE_ENERGY) ? 0 : L.color_off[c];
-      a.end = (mode == MODE_ENERGY) ? L.ne : L.color_off[c + 1];
+      a.begin = whole ? 0 : L.color_off[c];
+      a.end = whole ? L.ne : L.color_off[c + 1];
       const int n = a.end - a.begin;
       if (n <= 0) { continue; }
       const int grid = (n + 127) / 128;
@@ -60,6 +64,7 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
          case MODE_RES | MODE_JAC: k_element<Func, Cfg, MODE_RES | MODE_JAC, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
          case MODE_ACT: k_element<Func, Cfg, MODE_ACT, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
          case MODE_ENERGY: k_element<Func, Cfg, MODE_ENERGY, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
+         case MODE_COEF: k_element<Func, Cfg, MODE_COEF, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
          default: return -1;
       }
    }

@@ -50,7 +50,7 @@ void Functional::flat_params(std::vector<double> &out) const
 Integrator::~Integrator()
 {
    cudaFree(d_e2n); cudaFree(d_vmap); cudaFree(d_pmap); cudaFree(d_e2csr);
-   cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_energy); cudaFree(d_esum);
+   cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_perm); cudaFree(d_cvalue); cudaFree(d_cgrad); cudaFree(d_energy); cudaFree(d_esum);
    cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
 }
@@ -87,6 +87,33 @@ __global__ void __launch_bounds__(1024) k_reduce_sum(const double *in, int n, do
       __syncthreads();
    }
    if (threadIdx.x == 0) { out[0] = s[0]; }
+}
+
+// Fused LVPP latent-variable update (ex4.cpp:188-189,203-218):
+//    lambda = (psi - psi_k)/alpha ;  diff += w |lambda - lambda_prev| ;  lambda_prev <- lambda ;  psi_k <- psi
+// One pass over the latent vector; block partials are summed in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) k_lvpp_update(int n, double alpha, const double *psi, double *psik,
+                                                     double *lam_prev, const double *w, double *partial)
+{
+   __shared__ double s[256];
+   double acc = 0.0;
+   const double ia = 1.0 / alpha;
+   for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+   {
+      const double p = psi[i];
+      const double lam = (p - psik[i]) * ia;
+      acc += (w ? w[i] : 1.0) * fabs(lam - lam_prev[i]);
+      lam_prev[i] = lam;
+      psik[i] = p;
+   }
+   s[threadIdx.x] = acc;
+   __syncthreads();
+   for (int k = 128; k > 0; k >>= 1)
+   {
+      if ((int)threadIdx.x < k) { s[threadIdx.x] += s[threadIdx.x + k]; }
+      __syncthreads();
+   }
+   if (threadIdx.x == 0) { partial[blockIdx.x] = s[0]; }
 }
 
 // y[ess] = 0  (NonlinearForm::Mult [MFEM-upstream])
@@ -201,7 +228,7 @@ static int setup_integrator(Integrator &I)
          }
       }
    }
-   if (upload(e2n, &I.d_e2n) || upload(vmap, &I.d_vmap) || upload(pmap, &I.d_pmap)) { return 2; }
+   if (upload(e2n, &I.d_e2n) || upload(vmap, &I.d_vmap) || upload(pmap, &I.d_pmap) || upload(I.perm, &I.d_perm)) { return 2; }
 
    // basis tables at the quadrature points: [q][toff_f + i], x fastest in q and i
    std::vector<double> xq, wq;
@@ -297,7 +324,8 @@ static int stage_out_begin(Integrator &I, double *p, size_t n, double **buf, dou
    return 0;
 }
 
-static int run(Integrator &I, int mode, const double *x, const double *v, double *y, double *vals, double *energy)
+static int run(Integrator &I, int mode, const double *x, const double *v, double *y, double *vals, double *energy,
+               double *cvalue = nullptr, double *cgrad = nullptr)
 {
    CUDA_OK(cudaSetDevice(I.ctx->device));
    const size_t N = (size_t)I.ntotal;
@@ -367,6 +395,15 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
       }
       L.energy = I.d_energy;
    }
+   double *dcv = nullptr, *dcg = nullptr;
+   const size_t npts = (size_t)I.ne * I.nq;
+   if (mode == MODE_COEF)
+   {
+      L.perm = I.d_perm;
+      if (cvalue) { if (stage_out_begin(I, cvalue, npts, &I.d_cvalue, &dcv)) { return 2; } }
+      if (cgrad) { if (stage_out_begin(I, cgrad, npts * I.ops.n_input, &I.d_cgrad, &dcg)) { return 2; } }
+      L.cvalue = dcv; L.cgrad = dcg;
+   }
    const int rc = I.ops.launch(L, mode);
    if (rc != 0) { set_error(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
 
@@ -374,6 +411,13 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    {
       k_reduce_sum<<<1, 1024, 0, L.stream>>>(I.d_energy, I.ne, I.d_esum);
       CUDA_OK(cudaMemcpyAsync(energy, I.d_esum, sizeof(double), cudaMemcpyDeviceToHost, L.stream));
+      CUDA_OK(cudaStreamSynchronize(L.stream));
+      return 0;
+   }
+   if (mode == MODE_COEF)
+   {
+      if (cvalue && dcv != cvalue) { CUDA_OK(cudaMemcpyAsync(cvalue, dcv, npts * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); }
+      if (cgrad && dcg != cgrad) { CUDA_OK(cudaMemcpyAsync(cgrad, dcg, npts * I.ops.n_input * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); }
       CUDA_OK(cudaStreamSynchronize(L.stream));
       return 0;
    }
@@ -499,6 +543,39 @@ extern "C"
    }
    int madb_functional_destroy(madb_functional *f) { delete f; return 0; }
 
+   // scratch device buffer for a host-side argument (slow path; device pointers are used in place)
+   struct Staged
+   {
+      double *d = nullptr;
+      double *host = nullptr;
+      size_t n = 0;
+      bool owned = false;
+      int in(const double *p, size_t cnt)
+      {
+         n = cnt;
+         if (!p) { return 0; }
+         if (is_device_ptr(p)) { d = const_cast<double *>(p); return 0; }
+         owned = true;
+         if (cudaMalloc((void **)&d, std::max<size_t>(cnt, 1) * sizeof(double)) != cudaSuccess) { return 2; }
+         return cudaMemcpy(d, p, cnt * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess ? 0 : 2;
+      }
+      int out(double *p, size_t cnt, bool copy_in = false)
+      {
+         host = nullptr;
+         const int rc = in(p, cnt);
+         if (rc == 0 && owned) { host = p; }
+         (void)copy_in;
+         return rc;
+      }
+      int finish()
+      {
+         int rc = 0;
+         if (owned && host) { rc = cudaMemcpy(host, d, n * sizeof(double), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2; }
+         if (owned) { cudaFree(d); }
+         return rc;
+      }
+   };
+
    int madb_functional_eval(madb_ctx *ctx, madb_functional *f, int n_input, int npts, const double *x,
                             const double *qprm, double *value, double *grad, double *hess)
    {
@@ -515,26 +592,72 @@ extern "C"
       f->flat_params(fp);
       if ((int)fp.size() != E.n_fparam) { set_error("functional '" + key + "': wrong number of parameters"); return 1; }
       fp.push_back(0.0);
-      const int n = n_input;
-      double *dx = nullptr, *dq = nullptr, *dv = nullptr, *dg = nullptr, *dh = nullptr;
-      CUDA_OK(cudaMalloc((void **)&dx, (size_t)npts * n * sizeof(double)));
-      CUDA_OK(cudaMemcpy(dx, x, (size_t)npts * n * sizeof(double), cudaMemcpyDefault));
-      if (E.n_qprm > 0)
+      if (E.n_qprm > 0 && !qprm) { set_error("functional '" + key + "' needs per-point parameters"); return 1; }
+      const size_t n = n_input, P = npts;
+      Staged sx, sq, sv, sg, sh;
+      if (sx.in(x, P * n) || sq.in(E.n_qprm > 0 ? qprm : nullptr, P * E.n_qprm) || sv.out(value, P) ||
+          sg.out(grad, P * n) || sh.out(hess, P * n * n))
       {
-         if (!qprm) { set_error("functional '" + key + "' needs per-point parameters"); cudaFree(dx); return 1; }
-         CUDA_OK(cudaMalloc((void **)&dq, (size_t)npts * E.n_qprm * sizeof(double)));
-         CUDA_OK(cudaMemcpy(dq, qprm, (size_t)npts * E.n_qprm * sizeof(double), cudaMemcpyDefault));
+         set_error("madb_functional_eval: device staging failed");
+         return 2;
       }
-      CUDA_OK(cudaMalloc((void **)&dv, (size_t)npts * sizeof(double)));
-      CUDA_OK(cudaMalloc((void **)&dg, (size_t)npts * n * sizeof(double)));
-      CUDA_OK(cudaMalloc((void **)&dh, (size_t)npts * n * n * sizeof(double)));
-      const int rc = E.launch(ctx->stream, npts, fp.data(), dx, dq, dv, dg, dh);
+      const int rc = E.launch(ctx->stream, npts, fp.data(), sx.d, sq.d, sv.d, sg.d, sh.d);
       if (rc) { set_error(std::string("eval kernel: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
+      if (sx.owned || sv.owned || sg.owned || sh.owned) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
+      sx.finish(); sq.finish();
+      if (sv.finish() || sg.finish() || sh.finish()) { set_error("madb_functional_eval: copy back failed"); return 2; }
+      return 0;
+   }
+
+   int madb_dofpg_nodal(madb_ctx *ctx, madb_functional *entropy, int n, double alpha, const double *u,
+                        const double *psi, const double *psik, const double *w, double *r_u, double *r_psi,
+                        double *d_pp, double *d_up)
+   {
+      CUDA_OK(cudaSetDevice(ctx->device));
+      const std::string key = entropy->key() + "|n1";
+      auto it = eval_registry().find(key);
+      if (it == eval_registry().end() || !it->second.dofpg)
+      {
+         set_error("no nodal PG kernel compiled for entropy '" + key + "' (scalar entropies; add MADB_EVAL_INSTANCE)");
+         return 1;
+      }
+      std::vector<double> fp;
+      entropy->flat_params(fp);
+      if ((int)fp.size() != it->second.n_fparam) { set_error("entropy '" + key + "': wrong number of parameters"); return 1; }
+      fp.push_back(0.0);
+      Staged su, sp, sk, sw, ru, rp, dp, du;
+      if (su.in(u, n) || sp.in(psi, n) || sk.in(psik, n) || sw.in(w, n) || ru.out(r_u, n) || rp.out(r_psi, n) ||
+          dp.out(d_pp, n) || du.out(d_up, n))
+      {
+         set_error("madb_dofpg_nodal: device staging failed");
+         return 2;
+      }
+      if (ru.owned && r_u) { CUDA_OK(cudaMemcpy(ru.d, r_u, (size_t)n * sizeof(double), cudaMemcpyHostToDevice)); } // r_u is accumulated
+      const int rc = it->second.dofpg(ctx->stream, n, fp.data(), alpha, su.d, sp.d, sk.d, sw.d, ru.d, rp.d, dp.d, du.d);
+      if (rc) { set_error(std::string("dofpg kernel: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
+      if (ru.owned || rp.owned || dp.owned || du.owned) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
+      su.finish(); sp.finish(); sk.finish(); sw.finish();
+      if (ru.finish() || rp.finish() || dp.finish() || du.finish()) { set_error("madb_dofpg_nodal: copy back failed"); return 2; }
+      return 0;
+   }
+
+   int madb_lvpp_update(madb_ctx *ctx, int n, double alpha, const double *psi, double *psik, double *lambda_prev,
+                        const double *w, double *lambda_diff)
+   {
+      CUDA_OK(cudaSetDevice(ctx->device));
+      Staged sp, sk, sl, sw;
+      if (sp.in(psi, n) || sk.out(psik, n) || sl.out(lambda_prev, n) || sw.in(w, n)) { set_error("madb_lvpp_update: device staging failed"); return 2; }
+      const int nb = std::min(1024, (n + 255) / 256);
+      double *partial = nullptr, *dsum = nullptr;
+      CUDA_OK(cudaMalloc((void **)&partial, (size_t)(nb + 1) * sizeof(double)));
+      dsum = partial + nb;
+      k_lvpp_update<<<nb, 256, 0, ctx->stream>>>(n, alpha, sp.d, sk.d, sl.d, sw.d, partial);
+      k_reduce_sum<<<1, 1024, 0, ctx->stream>>>(partial, nb, dsum);
+      CUDA_OK(cudaMemcpyAsync(lambda_diff, dsum, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_OK(cudaStreamSynchronize(ctx->stream));
-      if (value) { CUDA_OK(cudaMemcpy(value, dv, (size_t)npts * sizeof(double), cudaMemcpyDefault)); }
-      if (grad) { CUDA_OK(cudaMemcpy(grad, dg, (size_t)npts * n * sizeof(double), cudaMemcpyDefault)); }
-      if (hess) { CUDA_OK(cudaMemcpy(hess, dh, (size_t)npts * n * n * sizeof(double), cudaMemcpyDefault)); }
-      cudaFree(dx); cudaFree(dq); cudaFree(dv); cudaFree(dg); cudaFree(dh);
+      cudaFree(partial);
+      sp.finish(); sw.finish();
+      if (sk.finish() || sl.finish()) { set_error("madb_lvpp_update: copy back failed"); return 2; }
       return 0;
    }
 
@@ -704,6 +827,11 @@ extern "C"
    int madb_integrator_assemble(madb_integrator *I, const double *x, double *y, double *vals)
    {
       return run(*I, MODE_RES | MODE_JAC, x, nullptr, y, vals, nullptr);
+   }
+   int madb_integrator_coefficient(madb_integrator *I, const double *x, double *value, double *grad)
+   {
+      if (I->ops.map_aos) { set_error("madb_integrator_coefficient: not available for the sum-factorised kernels"); return 1; }
+      return run(*I, MODE_COEF, x, nullptr, nullptr, nullptr, nullptr, value, grad);
    }
    int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y)
    {

@@ -1492,4 +1492,78 @@ extern "C"
          }
       }
    }
+
+   // ParametrizedFunctional::ParamGradient::Eval: src/mmto.cpp:4-38 (incl. SURVEY H6).
+   // Form F: spaces[0] = the design GridFunction rho (VALUE, vdim = param_dim) used as the
+   // parameter source of every f_i; params[0] = PRM_GF_GRAD of the state (VectorGradientGridFunction);
+   // nodes[F->root] = the parent functional (reads its f_i values at qprm[n_state + i]);
+   // fi[0..nfi) = node ids of the parameter functions f_i (ADFunctions of rho).
+   // out[ne*nq*param_dim].
+   void orc_mmto_param_gradient(const orc_form_t *F, const double *rho, int nfi, const int *fi, double *out)
+   {
+      ElemCtx C(*F);
+      const int param_dim = C.n_input; // rho components
+      const int n_state = C.F.params[0].size;
+      std::vector<std::vector<double>> elfun, allshapes(F->nspaces);
+      for (int s = 0; s < F->nspaces; s++) { allshapes[s].resize(C.dof[s] * C.sd[s]); }
+      std::vector<double> rq(param_dim), val(n_state + nfi), dfdc(param_dim);
+      for (int e = 0; e < F->mesh.ne; e++)
+      {
+         gather(C, e, rho, elfun);
+         for (int q = 0; q < C.ir.np; q++)
+         {
+            const double *ip = &C.ir.pts[q * C.dim];
+            PointGeom g;
+            eval_geom(C, e, ip, g);
+            for (int s = 0; s < F->nspaces; s++) { calc_input_shapes(C, s, ip, q, g, allshapes[s].data()); }
+            interp_inputs(C, allshapes, elfun, rq.data()); // param_coeffs[i]'s evaluator: rho at the point
+            double *J = out + ((size_t)e * C.ir.np + q) * param_dim;
+            for (int j = 0; j < param_dim; j++) { J[j] = 0.0; }
+            // parent.ProcessParameters: evaluate the f_i (:15); then the states (:17-20)
+            Ctx cf {F->fn, nullptr};
+            for (int i = 0; i < nfi; i++) { val[n_state + i] = fn_value(cf, fi[i], rq.data()); }
+            eval_params(C, e, q, ip, g, val.data()); // state block at offset 0
+            Ctx cp {F->fn, val.data()};
+            for (int i = 0; i < nfi; i++)
+            {
+               fn_gradient(cf, fi[i], rq.data(), dfdc.data()); // param_coeffs[i]->Gradient().Eval (:27)
+               const double keep = val[n_state + i];           // :29
+               for (int j = 0; j < param_dim; j++)
+               {
+                  val[n_state + i] = dfdc[j];                  // :32
+                  J[j] += fn_value(cp, F->root, val.data());   // :33  parent(state)
+               }
+               val[n_state + i] = keep;                        // :36
+            }
+         }
+      }
+   }
+
+   // ADDofPGNonlinearFormIntegrator nodal terms: src/dof_pg.hpp:66-128 (vector), :131-231 (grad).
+   // One primal/dual pair of scalar spaces with identical element dof maps (dof_pg.hpp:107-109).
+   // The reference takes the weights from primal_fe.GetNodes() (zero in MFEM); here the
+   // per-(element,node) weights w[e*nd + j] = Tr.Weight()*ip.weight are an explicit input, and the
+   // entropy parameters are processed in both paths.
+   // r_u, r_psi: global vectors (accumulated, element order); d_pp, d_up: diagonal Jacobian entries.
+   void orc_dofpg_nodal(const orc_fn_t *nodes, int entropy, int ne, int nd, const int *e2l, const double *w,
+                        double alpha, const double *u, const double *psi, const double *psik,
+                        double *r_u, double *r_psi, double *d_pp, double *d_up)
+   {
+      Ctx c {nodes, nullptr};
+      for (int e = 0; e < ne; e++)
+      {
+         for (int j = 0; j < nd; j++)
+         {
+            const int d = e2l[(size_t)e * nd + j];
+            const double ww = w[(size_t)e * nd + j] / alpha; // :119
+            double Jv, Hv;
+            fn_gradient(c, entropy, &psi[d], &Jv);           // :123
+            fn_hessian(c, entropy, &psi[d], &Hv);            // :223
+            r_u[d] += (psi[d] - psik[d]) * ww;               // :124
+            r_psi[d] += (u[d] - Jv) * ww;                    // :125 (assigned per element, then AddElementVector)
+            d_pp[d] += -Hv * ww;                             // :226
+            d_up[d] += ww;                                   // :227-228
+         }
+      }
+   }
 } // extern "C"

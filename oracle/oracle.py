@@ -98,6 +98,8 @@ def lib():
         L.orc_form_grad_range.argtypes = [fp, dp, ip, ip, dp, C.c_int, C.c_int, C.c_int]
         L.orc_form_inputs_at_qpts.argtypes = [fp, dp, dp]
         L.orc_form_coefficient.argtypes = [fp, dp, C.c_int, dp]
+        L.orc_mmto_param_gradient.argtypes = [fp, dp, C.c_int, ip, dp]
+        L.orc_dofpg_nodal.argtypes = [np_, C.c_int, C.c_int, C.c_int, ip, dp, C.c_double, dp, dp, dp, dp, dp, dp, dp]
         _LIB = L
     return _LIB
 
@@ -294,6 +296,13 @@ class OracleForm:
         lib().orc_form_inputs_at_qpts(C.byref(self.F), _dp(x), _dp(out))
         return out
 
+    def mmto_param_gradient(self, rho, fi):
+        rho = _f64(rho)
+        fi = _i32(fi)
+        out = np.zeros((self.ne, self.nq, self.n_input))
+        lib().orc_mmto_param_gradient(C.byref(self.F), _dp(rho), fi.size, _ip(fi), _dp(out))
+        return out
+
     def coefficient(self, x, which):
         x = _f64(x)
         n = self.n_input
@@ -301,6 +310,17 @@ class OracleForm:
         out = np.zeros(shape)
         lib().orc_form_coefficient(C.byref(self.F), _dp(x), which, _dp(out))
         return out
+
+
+def dofpg_nodal(functional, e2l, w, alpha, u, psi, psik):
+    """Nodal PG terms of ADDofPGNonlinearFormIntegrator (src/dof_pg.hpp); returns r_u, r_psi, d_pp, d_up."""
+    e2l, w = _i32(e2l), _f64(w)
+    u, psi, psik = _f64(u), _f64(psi), _f64(psik)
+    n = u.size
+    out = [np.zeros(n) for _ in range(4)]
+    lib().orc_dofpg_nodal(functional.carray(), functional.root, e2l.shape[0], e2l.shape[1], _ip(e2l), _dp(w), alpha,
+                          _dp(u), _dp(psi), _dp(psik), *[_dp(o) for o in out])
+    return out
 
 
 def pg_step(rule, alpha0, max_alpha, ratio, ratio2, it):

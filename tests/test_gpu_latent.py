@@ -1,0 +1,64 @@
+"""Latent-variable kernels: nodal (DOF-collocated) PG terms (src/dof_pg.hpp) and the fused LVPP update."""
+import numpy as np
+import pytest
+
+import spec as S
+from mfem_ad_b200 import meshgen as G
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("fs", [S.fermidirac(0.0, 0.5), S.shannon(0.1, 1)])
+def test_dofpg_nodal_terms(ctx, fs):
+    import mfem_ad_b200 as M
+    mesh = G.cartesian_mesh((5, 4), perturb=0.1)
+    s = G.h1_space(mesh, 2)
+    nd, ne = s["ndofs"], s["e2l"].shape[0]
+    rng = np.random.default_rng(8)
+    u, psi, psik = rng.uniform(0, 0.5, nd), rng.normal(0, 2, nd), rng.normal(0, 2, nd)
+    w_el = rng.uniform(0.1, 1.0, s["e2l"].shape)  # per (element, node) weights Tr.Weight()*ip.weight
+    alpha = 0.37
+    r_u, r_psi, d_pp, d_up = O.dofpg_nodal(fs.oracle(), s["e2l"], w_el, alpha, u, psi, psik)
+    W = np.zeros(nd)
+    np.add.at(W, s["e2l"], w_el)  # lumped nodal weights
+    base = rng.normal(0, 1, nd)   # r_u is accumulated on top of the objective's residual
+    g = M.dofpg_nodal(ctx, fs.madb(ctx), alpha, u, psi, psik, W, r_u=base.copy())
+    for a, b in ((g[0] - base, r_u), (g[1], r_psi), (g[2], d_pp), (g[3], d_up)):
+        assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(b)))
+    # zero weights reproduce the reference as written (element nodes carry no quadrature weight)
+    g0 = M.dofpg_nodal(ctx, fs.madb(ctx), alpha, u, psi, psik, np.zeros(nd))
+    assert all(np.all(a == 0.0) for a in g0)
+
+
+def test_fused_lvpp_update(ctx):
+    import mfem_ad_b200 as M
+    rng = np.random.default_rng(9)
+    n = 100003
+    psi, psik, lam_prev, w = rng.normal(0, 1, n), rng.normal(0, 1, n), rng.normal(0, 1, n), rng.uniform(0, 1, n)
+    alpha = 0.8
+    lam = (psi - psik) / alpha
+    ref = np.sum(w * np.abs(lam - lam_prev))
+    pk, lp = psik.copy(), lam_prev.copy()
+    d = M.lvpp_update(ctx, alpha, psi, pk, lp, w)
+    assert abs(d - ref) <= 1e-12 * ref
+    assert np.max(np.abs(lp - lam)) <= 1e-15 and np.array_equal(pk, psi)
+    pk2, lp2 = psik.copy(), lam_prev.copy()
+    assert M.lvpp_update(ctx, alpha, psi, pk2, lp2, w) == d  # deterministic reduction
+    # device-resident path
+    import torch
+    t = [torch.from_numpy(a).cuda() for a in (psi, psik.copy(), lam_prev.copy(), w)]
+    d3 = M.lvpp_update(ctx, alpha, *t)
+    assert d3 == d and np.array_equal(t[1].cpu().numpy(), psi)
+
+
+def test_ex4_mapped_primal_coefficient(ctx):
+    """ex4.cpp:124-128,200: x_mapped = grad E*(psi) projected to a quadrature function."""
+    mesh = G.cartesian_mesh((5, 4), perturb=0.1)
+    l2 = G.l2_space(mesh, 1, mode=O.VALUE)
+    psi = np.random.default_rng(3).normal(0, 3, l2["ndofs"])
+    of, gi = S.make_pair(ctx, mesh, [l2], S.fermidirac(0.0, 0.5), quad_order=9)
+    val, grd = gi.coefficient(psi)
+    ref = of.coefficient(psi, 1)
+    assert np.max(np.abs(grd - ref)) <= 1e-13
+    assert grd.min() > 0.0 and grd.max() < 0.5
