@@ -37,12 +37,12 @@ def test_fused_lvpp_update(ctx):
     n = 100003
     psi, psik, lam_prev, w = rng.normal(0, 1, n), rng.normal(0, 1, n), rng.normal(0, 1, n), rng.uniform(0, 1, n)
     alpha = 0.8
-    lam = (psi - psik) / alpha
+    lam = (psi - psik) * (1.0 / alpha)  # ex4.cpp:204: lambda *= 1.0/alpha
     ref = np.sum(w * np.abs(lam - lam_prev))
     pk, lp = psik.copy(), lam_prev.copy()
     d = M.lvpp_update(ctx, alpha, psi, pk, lp, w)
     assert abs(d - ref) <= 1e-12 * ref
-    assert np.max(np.abs(lp - lam)) <= 1e-15 and np.array_equal(pk, psi)
+    assert np.array_equal(lp, lam) and np.array_equal(pk, psi)
     pk2, lp2 = psik.copy(), lam_prev.copy()
     assert M.lvpp_update(ctx, alpha, psi, pk2, lp2, w) == d  # deterministic reduction
     # device-resident path
