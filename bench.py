@@ -177,13 +177,11 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
 
     nx = args.n
-    px = {1: 1, 2: 2, 4: 2, 8: 4}.get(world, world)
-    py = world // px
-    rx, ry = rank % px, rank // px
-    # this rank's block of the global (px*nx) x (py*nx) mesh on [0,px]x[0,py]
-    mesh = G.cartesian_mesh((nx, nx), lengths=(1.0, 1.0))
-    mesh["coords"] = mesh["coords"] + np.array([rx, ry], dtype=np.float64)
-    space = G.h1_space(mesh, P, mode=M.GRAD)
+    from mfem_ad_b200 import parallel as PAR
+    blk = PAR.cartesian_block(rank, world, nx, P)  # this rank's block of the (px*nx) x (py*nx) mesh
+    px, py = blk["px"], blk["py"]
+    mesh = blk["mesh"]
+    space = dict(blk["space"], mode=M.GRAD)
     ndof = space["ndofs"]
     ctx = M.Context(local)
     gm = M.Mesh(ctx, mesh)
@@ -203,30 +201,12 @@ def run_gpu(args):
     yp = torch.empty(ndof, dtype=torch.float64).pin_memory()
     vp = torch.empty(nnz, dtype=torch.float64).pin_memory()
 
-    # shared-dof exchange (P^T y): interface dofs of neighbouring blocks, summed in fixed neighbour order
-    nbrs = []
-    if world > 1:
-        ng = nx * P + 1
-        ids = np.arange(ndof, dtype=np.int64).reshape(ng, ng)  # [iy, ix]
-        for (dx, dy, sl) in ((-1, 0, ids[:, 0]), (1, 0, ids[:, -1]), (0, -1, ids[0, :]), (0, 1, ids[-1, :])):
-            qx, qy = rx + dx, ry + dy
-            if 0 <= qx < px and 0 <= qy < py:
-                idx = torch.from_numpy(np.ascontiguousarray(sl)).to(dev)
-                nbrs.append((qy * px + qx, idx, torch.empty(idx.numel(), dtype=torch.float64, device=dev),
-                             torch.empty(idx.numel(), dtype=torch.float64, device=dev)))
+    # shared-dof exchange P^T y: interface dofs summed on their owner rank, fixed order (deterministic)
+    ex = PAR.SharedDofExchange(blk["l2g"], blk["candidates"], dev, ctx=ctx) if world > 1 else None
 
     def exchange():
-        if not nbrs:
-            return
-        ops = []
-        for (peer, idx, sbuf, rbuf) in nbrs:
-            torch.index_select(y, 0, idx, out=sbuf)
-            ops.append(dist.P2POp(dist.isend, sbuf, peer))
-            ops.append(dist.P2POp(dist.irecv, rbuf, peer))
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-        for (peer, idx, sbuf, rbuf) in nbrs:  # fixed neighbour order: deterministic
-            y.index_add_(0, idx, rbuf)
+        if ex is not None:
+            ex.reduce_to_owner(y)
 
     def step_device():
         gi.assemble(x, y, vals)

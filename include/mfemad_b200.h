@@ -123,6 +123,13 @@ int madb_dofpg_nodal(madb_ctx *ctx, madb_functional *entropy, int n, double alph
 int madb_lvpp_update(madb_ctx *ctx, int n, double alpha, const double *psi, double *psik, double *lambda_prev,
                      const double *w, double *lambda_diff);
 
+/* Shared-dof exchange between element partitions (ParMesh + conforming prolongation P,
+ * ex4.cpp:85,136 [MFEM-upstream]): pack dst[i] = src[idx[i]] into a contiguous send buffer and
+ * unpack dst[idx[i]] (+)= src[i] from a receive buffer, on the context stream.  DEVICE pointers;
+ * the transfer itself is NCCL send/recv between neighbours (mfem-ad_b200/parallel.py). */
+int madb_pack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, double *dst);
+int madb_unpack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, double *dst, int add);
+
 /* AD(Block)NonlinearFormIntegrator<modes...>(f, ir) attached to its form
  * (src/_ad_intg.hpp:71-155, :157-327).  fields: spaces[i] with ADEval modes[i];
  * roles[i] = MADB_ROLE_INPUT for a differentiated unknown (a block of x), or

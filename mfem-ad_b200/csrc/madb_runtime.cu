@@ -116,6 +116,18 @@ __global__ void __launch_bounds__(256) k_lvpp_update(int n, double alpha, const 
    if (threadIdx.x == 0) { partial[blockIdx.x] = s[0]; }
 }
 
+// shared-dof exchange: contiguous send buffer <- y[idx] ; y[idx] += / = recv buffer (fixed order)
+__global__ void k_pack(int n, const int *idx, const double *src, double *dst)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { dst[i] = src[idx[i]]; }
+}
+__global__ void k_unpack(int n, const int *idx, const double *src, double *dst, int add)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n) { dst[idx[i]] = add ? dst[idx[i]] + src[i] : src[i]; }
+}
+
 // y[ess] = 0  (NonlinearForm::Mult [MFEM-upstream])
 __global__ void k_ess_zero(const int *ess, int n, double *y)
 {
@@ -638,6 +650,25 @@ extern "C"
       if (ru.owned || rp.owned || dp.owned || du.owned) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
       su.finish(); sp.finish(); sk.finish(); sw.finish();
       if (ru.finish() || rp.finish() || dp.finish() || du.finish()) { set_error("madb_dofpg_nodal: copy back failed"); return 2; }
+      return 0;
+   }
+
+   // Shared-dof exchange kernels (ParGridFunction / ParNonlinearForm P and P^T [MFEM-upstream]):
+   // all pointers are DEVICE pointers; idx lists are unique within one call, so no two threads collide.
+   int madb_pack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, double *dst)
+   {
+      if (n <= 0) { return 0; }
+      CUDA_OK(cudaSetDevice(ctx->device));
+      k_pack<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, idx, src, dst);
+      CUDA_OK(cudaGetLastError());
+      return 0;
+   }
+   int madb_unpack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, double *dst, int add)
+   {
+      if (n <= 0) { return 0; }
+      CUDA_OK(cudaSetDevice(ctx->device));
+      k_unpack<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, idx, src, dst, add);
+      CUDA_OK(cudaGetLastError());
       return 0;
    }
 

@@ -1,0 +1,143 @@
+"""Element-partition parallelism: one process per GPU, shared-dof exchange over NCCL.
+
+Mirrors what the reference gets from MFEM's ParMesh / ParFiniteElementSpace (ex4.cpp:85,99-101,136):
+every interface dof has one OWNER rank (the lowest rank that holds it);
+    reduce_to_owner(y)       = P^T : sharers -> owner, summed in ascending rank order (deterministic)
+    broadcast_from_owner(x)  = P   : owner -> sharers
+Messages are neighbour point-to-point (grouped isend/irecv = ncclSend/ncclRecv inside one
+ncclGroup), packed/unpacked by the CUDA kernels madb_pack / madb_unpack on the context stream.
+On CPU tensors (gloo, used by the CPU tests of this host logic) packing is plain torch indexing.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def rank_grid(world):
+    """Block layout of the weak-scaled runs: 1x1 / 2x1 / 2x2 / 4x2."""
+    px = {1: 1, 2: 2, 4: 2, 8: 4}.get(world)
+    if px is None:
+        px = int(np.floor(np.sqrt(world)))
+        while world % px:
+            px -= 1
+    return px, world // px
+
+
+def cartesian_block(rank, world, n, p, lengths=(1.0, 1.0)):
+    """This rank's n x n block of the (px*n) x (py*n) mesh and the local->global dof map of the
+    order-p H1 space (global lexicographic numbering on the fine node grid)."""
+    from . import meshgen as G
+    px, py = rank_grid(world)
+    rx, ry = rank % px, rank // px
+    mesh = G.cartesian_mesh((n, n), lengths=lengths)
+    mesh["coords"] = mesh["coords"] + np.array([rx * lengths[0], ry * lengths[1]])
+    space = G.h1_space(mesh, p)
+    ng = n * p + 1
+    NG = px * n * p + 1
+    iy, ix = np.divmod(np.arange(space["ndofs"], dtype=np.int64), ng)
+    l2g = (iy + ry * n * p) * NG + (ix + rx * n * p)
+    boundary = (ix == 0) | (ix == ng - 1) | (iy == 0) | (iy == ng - 1)
+    return dict(mesh=mesh, space=space, l2g=l2g, candidates=np.nonzero(boundary)[0], px=px, py=py, rx=rx, ry=ry)
+
+
+class SharedDofExchange:
+    """candidates: local dof indices that may be shared; l2g: their global ids come from l2g[candidates]."""
+
+    def __init__(self, l2g, candidates, device, ctx=None, group=None):
+        self.group, self.device, self.ctx = group, torch.device(device), ctx
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        cand = np.asarray(candidates, dtype=np.int64)
+        gids = np.asarray(l2g, dtype=np.int64)[cand]
+        order = np.argsort(gids)
+        gids, cand = gids[order], cand[order]
+        allg = [None] * self.world
+        dist.all_gather_object(allg, gids, group=group)
+        # sharers of every candidate dof
+        self.nbr = {}  # peer -> local indices (ascending global id: both sides agree on the order)
+        owner = np.full(gids.size, self.rank, dtype=np.int64)
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            common, ia, _ = np.intersect1d(gids, allg[r], assume_unique=True, return_indices=True)
+            if common.size:
+                self.nbr[r] = cand[ia]
+                owner[ia] = np.minimum(owner[ia], r)
+        self.owner_of_candidate = dict(zip(cand.tolist(), owner.tolist()))
+        own = {c: o for c, o in zip(cand, owner)}
+        # P^T: I send dofs I do not own to their owner; I receive (as owner) from every sharer
+        self.send_up, self.recv_up = {}, {}
+        for r, idx in self.nbr.items():
+            mine = np.array([own[i] == self.rank for i in idx], dtype=bool)
+            theirs = np.array([own[i] == r for i in idx], dtype=bool)
+            if theirs.any():
+                self.send_up[r] = idx[theirs]
+            if mine.any():
+                self.recv_up[r] = idx[mine]
+        self.peers = sorted(self.nbr)
+        self._bufs = {}
+        self.n_owned_shared = int(sum(1 for c in cand if own[c] == self.rank and any(c in v for v in self.nbr.values())))
+        self.is_owner_mask = None
+
+    def owned_mask(self, ndofs):
+        """True for dofs whose owner is this rank (true dofs)."""
+        m = np.ones(ndofs, dtype=bool)
+        for c, o in self.owner_of_candidate.items():
+            if o != self.rank:
+                m[c] = False
+        return m
+
+    # ---- packing -------------------------------------------------------------------------
+    def _idx(self, key, arr):
+        k = (key, id(arr))
+        if k not in self._bufs:
+            self._bufs[k] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int32)).to(self.device)
+        return self._bufs[k]
+
+    def _buf(self, key, n):
+        k = ("buf", key)
+        if k not in self._bufs or self._bufs[k].numel() != n:
+            self._bufs[k] = torch.empty(n, dtype=torch.float64, device=self.device)
+        return self._bufs[k]
+
+    def _pack(self, vec, idx_t, out):
+        if vec.is_cuda:
+            from . import lib, _check
+            _check(lib().madb_pack(self.ctx.h, idx_t.numel(), idx_t.data_ptr(), vec.data_ptr(), out.data_ptr()))
+        else:
+            torch.index_select(vec, 0, idx_t.long(), out=out)
+
+    def _unpack(self, vec, idx_t, src, add):
+        if vec.is_cuda:
+            from . import lib, _check
+            _check(lib().madb_unpack(self.ctx.h, idx_t.numel(), idx_t.data_ptr(), src.data_ptr(), vec.data_ptr(), int(add)))
+        elif add:
+            vec.index_add_(0, idx_t.long(), src)
+        else:
+            vec.index_copy_(0, idx_t.long(), src)
+
+    def _exchange(self, vec, send, recv, add, tag):
+        ops, rbufs = [], []
+        for r in self.peers:
+            if r in send:
+                it = self._idx(("s", tag, r), send[r])
+                sb = self._buf(("s", tag, r), it.numel())
+                self._pack(vec, it, sb)
+                ops.append(dist.P2POp(dist.isend, sb, r, self.group))
+            if r in recv:
+                it = self._idx(("r", tag, r), recv[r])
+                rb = self._buf(("r", tag, r), it.numel())
+                ops.append(dist.P2POp(dist.irecv, rb, r, self.group))
+                rbufs.append((it, rb))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for it, rb in rbufs:  # ascending peer rank: fixed summation order
+            self._unpack(vec, it, rb, add)
+
+    def reduce_to_owner(self, y):
+        """P^T: the owner's copy becomes the sum over all sharers (own value first, then ascending rank)."""
+        self._exchange(y, self.send_up, self.recv_up, True, "up")
+
+    def broadcast_from_owner(self, x):
+        """P: every sharer's copy is overwritten with the owner's value."""
+        self._exchange(x, self.recv_up, self.send_up, False, "down")
