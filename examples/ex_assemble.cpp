@@ -35,7 +35,7 @@ int main()
          SparseMatrix &K = nlf.GetGradient(x);
          double s = 0;
          for (double v : K.A) { s += v * v; }
-         std::printf("ex2 eps %.4f energy %.17g |y|^2 %.17g |K|_F^2 %.17g nnz %zu\n", energy.eps, nlf.GetEnergy(x), dot(y, y), s, K.A.size());
+         std::printf("ex2 eps=%.4f energy=%.17g y2=%.17g K2=%.17g nnz=%zu\n", energy.eps, nlf.GetEnergy(x), dot(y, y), s, K.A.size());
          energy.eps *= 0.5;
       }
    }
@@ -60,7 +60,7 @@ int main()
       SparseMatrix &K = bnlf.GetGradient(x);
       double s = 0;
       for (double v : K.A) { s += v * v; }
-      std::printf("ex4 alpha %.4f |y|^2 %.17g |K|_F^2 %.17g nnz %zu\n", pg.GetAlpha(), dot(y, y), s, K.A.size());
+      std::printf("ex4 alpha=%.4f y2=%.17g K2=%.17g nnz=%zu\n", pg.GetAlpha(), dot(y, y), s, K.A.size());
    }
    return 0;
 }

@@ -19,6 +19,10 @@ def _nums(line):
     return [float(v) for v in re.findall(r"[-+]?\d+\.?\d*(?:[eE][-+]?\d+)?", line)]
 
 
+def _kv(line):
+    return {k: float(v) for k, v in re.findall(r"(\w+)=([-+0-9.eE]+)", line)}
+
+
 def test_cpp_examples_match(ctx):
     exe = os.path.join(ROOT, "examples", "ex_assemble")
     assert os.path.exists(exe), "run python __graft_entry__.py first"
@@ -33,12 +37,13 @@ def test_cpp_examples_match(ctx):
     x = np.sin(0.37 * np.arange(s["ndofs"])) * 0.3
     for k, eps in enumerate((0.5, 0.25)):
         of = O.OracleForm(mesh, [s], S.minsurf(2, eps).oracle())
-        vals = _nums(out[3 + k])
+        kv = _kv(out[3 + k])
         y, v = of.mult(x), of.grad(x)[2]
-        assert abs(vals[2] - of.energy(x)) <= 1e-12 * abs(of.energy(x))
-        assert abs(vals[4] - y @ y) <= 1e-12 * (y @ y)
-        assert abs(vals[7] - v @ v) <= 1e-12 * (v @ v)
-        assert int(vals[8]) == v.size
+        assert abs(kv["eps"] - eps) < 1e-12
+        assert abs(kv["energy"] - of.energy(x)) <= 1e-12 * abs(of.energy(x))
+        assert abs(kv["y2"] - y @ y) <= 1e-12 * (y @ y)
+        assert abs(kv["K2"] - v @ v) <= 1e-12 * (v @ v)
+        assert int(kv["nnz"]) == v.size
     # ex4 block
     order = 2
     mesh = G.cartesian_mesh((6, 5))
@@ -49,8 +54,8 @@ def test_cpp_examples_match(ctx):
     psik = np.sin(0.23 * np.arange(l2["ndofs"]))
     of = O.OracleForm(mesh, [h1, l2], S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), 0.8).oracle(), quad_order=9,
                       params=[dict(type=O.PRM_GF, size=1, data=psik, space=l2)])
-    vals = _nums(out[5])
+    kv = _kv(out[5])
     y, v = of.mult(x), of.grad(x)[2]
-    assert abs(vals[1] - 0.8) < 1e-12
-    assert abs(vals[3] - y @ y) <= 1e-12 * (y @ y)
-    assert abs(vals[6] - v @ v) <= 1e-12 * (v @ v)
+    assert abs(kv["alpha"] - 0.8) < 1e-12
+    assert abs(kv["y2"] - y @ y) <= 1e-12 * (y @ y)
+    assert abs(kv["K2"] - v @ v) <= 1e-12 * (v @ v)
