@@ -142,6 +142,10 @@ int madb_integrator_destroy(madb_integrator *I);
 
 /* sizes: total dofs of the concatenated input blocks, quadrature points per element */
 int madb_integrator_sizes(madb_integrator *I, int64_t *ntotal, int *nq_el, int *ncolors);
+/* Patch-assembly statistics (diagnostics): out[0..7] = patches (0: colour-scatter path in use), max rows
+ * and max matrix slots per patch, interface dofs, interface matrix entries, staged residual and matrix
+ * partials, CSR runs.  Matrix-side figures are 0 until the sparsity pattern has been built. */
+int madb_integrator_patch_stats(madb_integrator *I, int64_t *out);
 
 /* Evaluator sources that vary in space (src/ad_native.hpp:56-61):
  * GridFunction parameter of field `field` (dof vector of that space), and

@@ -63,6 +63,7 @@ def lib():
         L.madb_integrator_create.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, pp]
         L.madb_integrator_destroy.argtypes = [vp]
         L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.madb_integrator_patch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.madb_integrator_set_param_field.argtypes = [vp, C.c_int, dp]
         L.madb_integrator_set_param_qf.argtypes = [vp, C.c_int, dp]
         L.madb_integrator_set_essential.argtypes = [vp, C.c_int, ip]
@@ -206,6 +207,13 @@ class Integrator:
         self.ntotal, self.nq_el, self.ncolors = nt.value, nq.value, nc.value
         self._pattern = None
         self._keep = []
+
+    def patch_stats(self):
+        """Patch-assembly diagnostics (madb_integrator_patch_stats)."""
+        out = (C.c_int64 * 8)()
+        _check(lib().madb_integrator_patch_stats(self.h, out))
+        keys = ("patches", "max_rows", "max_slots", "ifc_dofs", "ifc_entries", "staged_y", "staged_vals", "runs")
+        return dict(zip(keys, [int(v) for v in out]))
 
     def set_param_field(self, field, dofs):
         if isinstance(dofs, np.ndarray):

@@ -18,6 +18,51 @@ enum { MODE_RES = 1, MODE_JAC = 2, MODE_ACT = 4, MODE_ENERGY = 8, MODE_COEF = 16
 // run-time descriptors the C ABI receives, e.g.
 //    "minsurf|d2q4|3.1.4.0"          (kind | DIM,NQ1D | nd1d.vdim.mode.role per field)
 // A missing key is a loud error naming the MADB_INSTANCE line to add.
+// ---- patch assembly (madb_patch.cpp / madb_patch.cuh) ------------------------------
+// Elements are grouped into compact patches of PATCH_PE elements = one CTA.  A CTA
+// assembles complete CSR rows of its patch in shared memory and writes them once,
+// coalesced; rows shared with other patches ("interface") go to a staging buffer and
+// are summed in a fixed order by a second small kernel.
+constexpr int PATCH_PE = 128;
+constexpr int PATCH_MAXCOL = 31;
+// Shared-memory index of slot s: the low 4 bits are hashed with higher bits so that the slots of the
+// elements of one colour (regularly strided on structured meshes) spread over the banks; a permutation
+// inside each aligned group of 16 doubles, so consecutive slots stay conflict-free.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int patch_swz(int s) { return s ^ (((s >> 4) ^ (s >> 8)) & 15); }
+// the rows of one patch (at most PATCH_PE * nvd^2 matrix slots) must fit in shared memory, two CTAs per SM
+constexpr bool patch_eligible(int nvd) { return (long)PATCH_PE * nvd * nvd * 8 <= 100L * 1024; }
+struct PatchDesc
+{
+   int ne;                // elements of this patch (all PATCH_PE except possibly the last patch)
+   int nrow_int, nrows;   // local rows: interior first, then interface
+   int y_off;             // ylist[y_off + lr] = global dof of interior local row lr
+   int ystage_off;        // ystage[ystage_off + (lr - nrow_int)] <- interface rows
+   int nint, nslots;      // matrix slots: interior [0,nint) in CSR order, interface [nint,nslots)
+   int run_off, nruns;    // runs of consecutive CSR positions covering [0,nint)
+   int reserved;
+   int stage_off;         // vstage[stage_off + (s - nint)] <- interface slots
+   int ncol;              // element colours inside the patch
+   unsigned char col_off[PATCH_MAXCOL + 1]; // thread ranges per colour
+};
+struct PatchDev
+{
+   int npatch;
+   int max_rows, max_slots, max_runs; // shared-memory sizing
+   const PatchDesc *desc;
+   const unsigned short *yslot; // [NVD][stride]
+   const unsigned short *pslot; // [NVD*NVD][stride]
+   const int *ylist;
+   const int *run_s, *run_g;
+   double *ystage, *vstage;
+   // interface reductions: out[dst[i]] = sum_{k in ptr[i]..ptr[i+1]} stage[src[k]]
+   int ny_ifc, nv_ifc;
+   const int *y_ptr, *y_src, *y_dst;
+   const int *v_ptr, *v_src, *v_dst;
+};
+
 struct LaunchCtx
 {
    cudaStream_t stream;
@@ -38,6 +83,7 @@ struct LaunchCtx
    // 1-D tables per field [nq1d][nd1d], 1-D points and weights (sum-factorised kernels)
    const double *b1d[8], *g1d[8];
    const double *xq1d, *w1d;
+   const PatchDev *patch; // non-null: patch assembly (elements in patch order)
 };
 
 struct KernelOps
@@ -46,6 +92,7 @@ struct KernelOps
    int n_input, n_fparam, n_qprm, n_field_qprm, nvd, ndof_all, nq, ntab, dim;
    int map_aos = 0;          // element maps stored [t][k] instead of [k][stride]
    int matrix_free_only = 0; // no assembled Jacobian (use grad_mult)
+   int patch_ok = 0;         // patch-assembly kernels are compiled for this configuration
 };
 
 std::map<std::string, KernelOps> &registry();
@@ -151,6 +198,20 @@ struct Integrator
    std::vector<std::vector<double>> b1d, g1d;
    std::vector<double> xq1d, w1d;
 
+   // patch assembly
+   bool use_patches = false;
+   std::vector<PatchDesc> pdesc;
+   std::vector<int> prows;      // concatenated local row lists (global dof ids), per patch [nrows]
+   std::vector<int> prow_off;   // [npatch+1]
+   int max_rows = 0, max_slots = 0, max_runs = 0;
+   bool have_patch_vals = false;
+   PatchDev pdev {};
+   PatchDesc *d_pdesc = nullptr;
+   unsigned short *d_yslot = nullptr, *d_pslot = nullptr;
+   int *d_ylist = nullptr, *d_run_s = nullptr, *d_run_g = nullptr;
+   double *d_ystage = nullptr, *d_vstage = nullptr;
+   int *d_yptr = nullptr, *d_ysrc = nullptr, *d_ydst = nullptr, *d_vptr = nullptr, *d_vsrc = nullptr, *d_vdst = nullptr;
+
    // essential dofs
    int ness = 0;
    int *d_ess = nullptr;
@@ -166,5 +227,22 @@ void build_vdofs(const Integrator &I, int e, std::vector<int> &vd);
 void color_elements(const Integrator &I, std::vector<int> &color, int &ncolors);
 void build_pattern(Integrator &I);
 void build_e2csr(const Integrator &I, const std::vector<int> &color, std::vector<int> &e2csr);
+
+// patch assembly (madb_patch.cpp)
+struct PatchHostY // residual-side maps, built at setup
+{
+   std::vector<unsigned short> yslot; // [NVD][stride]
+   std::vector<int> ylist, y_ptr, y_src, y_dst;
+   long ystage_size = 0;
+};
+struct PatchHostV // matrix-side maps, built with the pattern
+{
+   std::vector<unsigned short> pslot; // [NVD*NVD][stride]
+   std::vector<int> run_s, run_g, v_ptr, v_src, v_dst;
+   long vstage_size = 0;
+};
+void patch_order(Integrator &I);                 // fills I.perm (patch order) and I.pdesc[].ne / colours
+void patch_build_y(Integrator &I, PatchHostY &H); // needs maps in patch order (I.perm)
+void patch_build_v(Integrator &I, PatchHostV &H); // needs the CSR pattern
 
 } // namespace madb

@@ -461,12 +461,13 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
    }
 }
 
+/// Gather + quadrature loop of sorted element t: element vector r, upper triangle of the element matrix A.
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
-__global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs<Func, Cfg> a)
+__device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, const int t,
+                                                double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
+                                                double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1], double &energy)
 {
    constexpr int DIM = Cfg::DIM, NVD = Cfg::NVD;
-   const int t = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
-   if (t >= a.end) { return; }
 
    // ---- gather: vertices, dofs of all fields ---------------------------------------
    double X[Cfg::NGN][DIM];
@@ -506,9 +507,7 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs
    Func f;
    f.load(a.fparams);
 
-   double r[(MODE & (MODE_RES | MODE_ACT)) ? NVD : 1];
-   double A[(MODE & MODE_JAC) ? Cfg::NSYM : 1];
-   double energy = 0.0;
+   energy = 0.0;
    if constexpr ((MODE & (MODE_RES | MODE_ACT)) != 0)
    {
 #pragma unroll
@@ -530,6 +529,18 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs
 #pragma unroll 1
       for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE>(a, q, t, X, u, vdir, f, r, A, energy); }
    }
+}
+
+template <class Func, class Cfg, int MODE, bool UNROLLQ>
+__global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs<Func, Cfg> a)
+{
+   constexpr int NVD = Cfg::NVD;
+   const int t = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= a.end) { return; }
+   double r[(MODE & (MODE_RES | MODE_ACT)) ? NVD : 1];
+   double A[(MODE & MODE_JAC) ? Cfg::NSYM : 1];
+   double energy;
+   element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy);
 
    // ---- scatter --------------------------------------------------------------------
    // Map entries are read through the read-only path in row batches, ahead of the

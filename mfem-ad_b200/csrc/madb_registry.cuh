@@ -2,6 +2,7 @@
 #pragma once
 #include "madb_host.hpp"
 #include "madb_kernels.cuh"
+#include "madb_patch.cuh"
 
 #include <cstring>
 #include <string>
@@ -22,7 +23,7 @@ template <class Cfg> std::string config_key()
    return k;
 }
 
-template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &L, int mode)
+template <class Func, class Cfg> AsmArgs<Func, Cfg> &fill_args(const LaunchCtx &L)
 {
    using Args = AsmArgs<Func, Cfg>;
    static Args a; // ~tens of KB: keep off the stack; calls are single-threaded per context
@@ -49,6 +50,28 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
    std::memcpy(a.tab.dphi, L.dphi, sizeof(a.tab.dphi));
    std::memcpy(a.tab.gdphi, L.gdphi, sizeof(a.tab.gdphi));
    std::memcpy(a.tab.w, L.w, sizeof(a.tab.w));
+   return a;
+}
+
+template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &L, int mode)
+{
+   using Args = AsmArgs<Func, Cfg>;
+   Args &a = fill_args<Func, Cfg>(L);
+   if constexpr (patch_eligible(Cfg::NVD))
+   {
+      if (L.patch && mode != MODE_ENERGY && mode != MODE_COEF)
+      {
+         a.begin = 0;
+         a.end = L.ne;
+         switch (mode)
+         {
+            case MODE_RES: return launch_patch_mode<Func, Cfg, MODE_RES, UNROLLQ>(a, L);
+            case MODE_RES | MODE_JAC: return launch_patch_mode<Func, Cfg, MODE_RES | MODE_JAC, UNROLLQ>(a, L);
+            case MODE_ACT: return launch_patch_mode<Func, Cfg, MODE_ACT, UNROLLQ>(a, L);
+            default: return -1;
+         }
+      }
+   }
    const bool whole = (mode == MODE_ENERGY || mode == MODE_COEF);
    const int nlaunch = whole ? 1 : L.ncolors;
    for (int c = 0; c < nlaunch; c++)
@@ -76,6 +99,7 @@ template <class Func, class Cfg, bool UNROLLQ> KernelOps make_ops()
    KernelOps o;
    o.map_aos = 0;
    o.matrix_free_only = 0;
+   o.patch_ok = patch_eligible(Cfg::NVD) ? 1 : 0;
    o.launch = &launch_impl<Func, Cfg, UNROLLQ>;
    o.n_input = Cfg::N_INPUT;
    o.n_fparam = Func::N_PARAM;

@@ -89,6 +89,35 @@ def test_scalar_grad_2d(ctx, p, kind, perturb):
     _compare(of, gi, _state(mesh, s))
 
 
+@pytest.mark.parametrize("case", ["q2", "q2perm", "q1", "elast", "hex"])
+def test_patch_assembly_many_patches(ctx, case):
+    """Meshes of several patches (PATCH_PE = 128 elements per CTA): interior rows written by the patch,
+    interface rows through the staging buffer + fixed-order reduction; essential dofs on top."""
+    if case == "hex":
+        mesh = G.cartesian_mesh((9, 8, 7), perturb=0.12)
+        s = G.h1_space(mesh, 1, mode=O.GRAD)
+        fs = S.minsurf(3, 0.5)
+    elif case == "elast":
+        mesh = G.cartesian_mesh((23, 19), perturb=0.15)
+        s = G.h1_space(mesh, 1, vdim=2, ordering=1, mode=O.GRAD | O.VECTOR)
+        fs = S.elasticity(2, 1.0, 1.0)
+    else:
+        mesh = G.cartesian_mesh((31, 26), lengths=(1.0, 0.8), perturb=0.2)
+        s = G.h1_space(mesh, 1 if case == "q1" else 2, mode=O.GRAD)
+        if case == "q2perm":
+            s = G.permute_dofs(s, 3)
+        fs = S.minsurf(2, 0.5)
+    ess = G.boundary_dofs(mesh, s)[::2] if case == "q2" else ()
+    of, gi = S.make_pair(ctx, mesh, [s], fs, ess=ess, block=(1 if case == "elast" else None))
+    st = gi.patch_stats()
+    assert st["patches"] >= 4 and st["ifc_dofs"] > 0
+    if case == "elast":
+        _compare(of, gi, _block_state(mesh, [s]))
+    else:
+        _compare(of, gi, _state(mesh, s), energy=(len(ess) == 0))
+    assert gi.patch_stats()["ifc_entries"] > 0
+
+
 def test_essential_bc_and_parameter_update(ctx):
     mesh = G.cartesian_mesh((6, 6), perturb=0.1)
     s = G.h1_space(mesh, 2, mode=O.GRAD)
