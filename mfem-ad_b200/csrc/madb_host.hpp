@@ -19,43 +19,43 @@ enum { MODE_RES = 1, MODE_JAC = 2, MODE_ACT = 4, MODE_ENERGY = 8, MODE_COEF = 16
 //    "minsurf|d2q4|3.1.4.0"          (kind | DIM,NQ1D | nd1d.vdim.mode.role per field)
 // A missing key is a loud error naming the MADB_INSTANCE line to add.
 // ---- patch assembly (madb_patch.cpp / madb_patch.cuh) ------------------------------
-// Elements are grouped into compact patches of PATCH_PE elements = one CTA.  A CTA
-// assembles complete CSR rows of its patch in shared memory and writes them once,
-// coalesced; rows shared with other patches ("interface") go to a staging buffer and
-// are summed in a fixed order by a second small kernel.
+// Elements are grouped into compact patches of PATCH_PE elements = one CTA.  The threads of a
+// CTA stage their element vectors / matrices in shared memory; every row of the patch is then
+// summed from its sources in a fixed order and written once, coalesced, to y / the CSR values.
+// Rows shared with other patches ("interface") go to a staging buffer and are summed in
+// ascending patch order by a second small kernel.
 constexpr int PATCH_PE = 128;
-constexpr int PATCH_MAXCOL = 31;
-// Shared-memory index of slot s: the low 4 bits are hashed with higher bits so that the slots of the
-// elements of one colour (regularly strided on structured meshes) spread over the banks; a permutation
-// inside each aligned group of 16 doubles, so consecutive slots stay conflict-free.
-#if defined(__CUDACC__)
-__host__ __device__
-#endif
-inline int patch_swz(int s) { return s ^ (((s >> 4) ^ (s >> 8)) & 15); }
-// the rows of one patch (at most PATCH_PE * nvd^2 matrix slots) must fit in shared memory, two CTAs per SM
-constexpr bool patch_eligible(int nvd) { return (long)PATCH_PE * nvd * nvd * 8 <= 100L * 1024; }
+constexpr int PATCH_LD = PATCH_PE + 1; // leading dimension of the staged element data (bank spread)
+constexpr int PATCH_MAXEXTRA = 7;      // a slot has 1 + at most 7 sources (3-bit count)
+inline constexpr int patch_al16(int bytes) { return (bytes + 15) & ~15; }
+// the staged element matrices of one patch must fit in shared memory, two CTAs per SM
+constexpr bool patch_eligible(int nvd) { return nvd <= 10; }
 struct PatchDesc
 {
-   int ne;                // elements of this patch (all PATCH_PE except possibly the last patch)
-   int nrow_int, nrows;   // local rows: interior first, then interface
-   int y_off;             // ylist[y_off + lr] = global dof of interior local row lr
-   int ystage_off;        // ystage[ystage_off + (lr - nrow_int)] <- interface rows
-   int nint, nslots;      // matrix slots: interior [0,nint) in CSR order, interface [nint,nslots)
-   int run_off, nruns;    // runs of consecutive CSR positions covering [0,nint)
-   int reserved;
-   int stage_off;         // vstage[stage_off + (s - nint)] <- interface slots
-   int ncol;              // element colours inside the patch
-   unsigned char col_off[PATCH_MAXCOL + 1]; // thread ranges per colour
+   int ne;                    // elements of this patch (all PATCH_PE except possibly the last patch)
+   int nrow_int, nrows;       // local rows: interior first, then interface
+   int nyfold;                // words of the row fold list (8 phase counts + folds)
+   int ystage_off;            // ystage[ystage_off + (lr - nrow_int)] <- interface rows
+   int yblob_off, yblob_bytes; // residual-side maps of the patch: yblob + 16*yblob_off
+   int nint, nslots;          // matrix slots: interior [0,nint) in CSR order, interface [nint,nslots)
+   int nvfold;                // words of the slot fold list
+   int nruns;                 // runs of consecutive CSR positions covering [0,nint)
+   int stage_off;             // vstage[stage_off + (s - nint)] <- interface slots
+   int vblob_off, vblob_bytes; // matrix-side maps: vblob + 16*vblob_off
+   int pad[2];
 };
+// Blob layouts (sections padded to 16 bytes, copied to shared memory with one bulk copy each):
+//   y blob: ysrc u16[nrows]  | yfold u32[nyfold] | ylist i32[nrow_int]
+//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | run_s i32[nruns+1] | run_g i32[nruns+1]
+// ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
+// fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
+// phase k adds the k-th further source, so every row / slot is summed in ascending element order.
 struct PatchDev
 {
    int npatch;
-   int max_rows, max_slots, max_runs; // shared-memory sizing
+   int max_yblob, max_vblob; // bytes, shared-memory sizing
    const PatchDesc *desc;
-   const unsigned short *yslot; // [NVD][stride]
-   const unsigned short *pslot; // [NVD*NVD][stride]
-   const int *ylist;
-   const int *run_s, *run_g;
+   const unsigned char *yblob, *vblob;
    double *ystage, *vstage;
    // interface reductions: out[dst[i]] = sum_{k in ptr[i]..ptr[i+1]} stage[src[k]]
    int ny_ifc, nv_ifc;
@@ -203,12 +203,11 @@ struct Integrator
    std::vector<PatchDesc> pdesc;
    std::vector<int> prows;      // concatenated local row lists (global dof ids), per patch [nrows]
    std::vector<int> prow_off;   // [npatch+1]
-   int max_rows = 0, max_slots = 0, max_runs = 0;
+   int max_yblob = 0, max_vblob = 0;
    bool have_patch_vals = false;
    PatchDev pdev {};
    PatchDesc *d_pdesc = nullptr;
-   unsigned short *d_yslot = nullptr, *d_pslot = nullptr;
-   int *d_ylist = nullptr, *d_run_s = nullptr, *d_run_g = nullptr;
+   unsigned char *d_yblob = nullptr, *d_vblob = nullptr;
    double *d_ystage = nullptr, *d_vstage = nullptr;
    int *d_yptr = nullptr, *d_ysrc = nullptr, *d_ydst = nullptr, *d_vptr = nullptr, *d_vsrc = nullptr, *d_vdst = nullptr;
 
@@ -229,20 +228,14 @@ void build_pattern(Integrator &I);
 void build_e2csr(const Integrator &I, const std::vector<int> &color, std::vector<int> &e2csr);
 
 // patch assembly (madb_patch.cpp)
-struct PatchHostY // residual-side maps, built at setup
+struct PatchHost // maps of one side (residual or matrix)
 {
-   std::vector<unsigned short> yslot; // [NVD][stride]
-   std::vector<int> ylist, y_ptr, y_src, y_dst;
-   long ystage_size = 0;
+   std::vector<unsigned char> blob;
+   std::vector<int> ptr, src, dst; // interface reduction lists
+   long stage_size = 0;
 };
-struct PatchHostV // matrix-side maps, built with the pattern
-{
-   std::vector<unsigned short> pslot; // [NVD*NVD][stride]
-   std::vector<int> run_s, run_g, v_ptr, v_src, v_dst;
-   long vstage_size = 0;
-};
-void patch_order(Integrator &I);                 // fills I.perm (patch order) and I.pdesc[].ne / colours
-void patch_build_y(Integrator &I, PatchHostY &H); // needs maps in patch order (I.perm)
-void patch_build_v(Integrator &I, PatchHostV &H); // needs the CSR pattern
+void patch_order(Integrator &I);                      // fills I.perm (patch order) and I.pdesc[].ne
+bool patch_build_y(Integrator &I, PatchHost &H);       // needs I.perm; false: not representable
+bool patch_build_v(Integrator &I, PatchHost &H);       // needs the CSR pattern
 
 } // namespace madb

@@ -5,14 +5,13 @@
 // (SURVEY a32).  On the GPU a per-element scatter writes every 8-byte value into
 // its own 32-byte sector (profiles/r01_v1_k_element.md: 4x the algorithmic DRAM
 // traffic).  Here elements are grouped into compact patches (recursive coordinate
-// bisection, PATCH_PE elements = one CTA); a CTA accumulates complete CSR rows of
-// its patch in shared memory and writes each row once, coalesced.
+// bisection, PATCH_PE elements = one CTA).  The CTA stages its element matrices in
+// shared memory; every CSR entry ("slot") of the patch is then gathered from its
+// sources in ascending element order and written once, coalesced.
 //   interior row  : every element containing the dof is in the patch -> final value
 //   interface row : partial sums go to a staging buffer; a second kernel adds the
 //                   partials of each entry in ascending patch order (deterministic).
-// Inside a patch the elements are coloured (no two of a colour share a dof) and
-// sorted by colour, so the shared-memory accumulation needs no atomics and has a
-// fixed order.
+// No atomics, no colouring: the summation order of every entry is fixed by the maps.
 #include "madb_host.hpp"
 
 #include <algorithm>
@@ -85,7 +84,7 @@ static void rcb(std::vector<int> &idx, int lo, int hi, const std::vector<double>
    }
 }
 
-// Patch order: fills I.perm (sorted position -> element), I.pdesc[p].ne/ncol/col_off.
+// Patch order: fills I.perm (sorted position -> element) and I.pdesc[p].ne.
 void patch_order(Integrator &I)
 {
    const int ne = I.ne, dim = I.mesh->dim, ngn = 1 << dim, pe = PATCH_PE;
@@ -103,63 +102,78 @@ void patch_order(Integrator &I)
    rcb(idx, 0, ne, cen, dim, pe, 0);
    const int np = (ne + pe - 1) / pe;
    I.pdesc.assign(np, PatchDesc());
-   // colour and sort inside each patch
-   bool ok = true;
-   parallel_for_p(np, 64, [&](long b, long e)
+   for (int p = 0; p < np; p++)
    {
-      std::vector<int> vd, dofs, col(pe), ord(pe);
-      std::vector<unsigned> mask;
-      std::vector<std::vector<int>> evd(pe);
-      for (long p = b; p < e; p++)
-      {
-         const int lo = (int)p * pe, n = std::min(pe, ne - lo);
-         // keep a reproducible order inside the patch before colouring
-         std::sort(idx.begin() + lo, idx.begin() + lo + n);
-         dofs.clear();
-         for (int l = 0; l < n; l++)
-         {
-            build_vdofs(I, idx[lo + l], evd[l]);
-            dofs.insert(dofs.end(), evd[l].begin(), evd[l].end());
-         }
-         std::sort(dofs.begin(), dofs.end());
-         dofs.erase(std::unique(dofs.begin(), dofs.end()), dofs.end());
-         mask.assign(dofs.size(), 0u);
-         int ncol = 0;
-         for (int l = 0; l < n; l++)
-         {
-            unsigned used = 0;
-            for (int v : evd[l]) { used |= mask[std::lower_bound(dofs.begin(), dofs.end(), v) - dofs.begin()]; }
-            int c = 0;
-            while (c < 32 && (used >> c) & 1u) { c++; }
-            if (c >= PATCH_MAXCOL) { ok = false; c = PATCH_MAXCOL - 1; }
-            col[l] = c;
-            ncol = std::max(ncol, c + 1);
-            for (int v : evd[l]) { mask[std::lower_bound(dofs.begin(), dofs.end(), v) - dofs.begin()] |= 1u << c; }
-         }
-         PatchDesc &D = I.pdesc[p];
-         std::memset(&D, 0, sizeof(D));
-         D.ne = n;
-         D.ncol = ncol;
-         for (int l = 0; l < n; l++) { ord[l] = l; }
-         std::stable_sort(ord.begin(), ord.begin() + n, [&](int a, int bb) { return col[a] < col[bb]; });
-         std::vector<int> tmp(n);
-         for (int l = 0; l < n; l++) { tmp[l] = idx[lo + ord[l]]; }
-         int k = 0;
-         for (int c = 0; c <= PATCH_MAXCOL; c++)
-         {
-            while (k < n && col[ord[k]] < c) { k++; }
-            D.col_off[c] = (unsigned char)k;
-         }
-         for (int c = ncol; c <= PATCH_MAXCOL; c++) { D.col_off[c] = (unsigned char)n; }
-         std::copy(tmp.begin(), tmp.end(), idx.begin() + lo);
-      }
-   });
-   if (!ok) { I.pdesc.clear(); I.use_patches = false; return; }
+      std::memset(&I.pdesc[p], 0, sizeof(PatchDesc));
+      const int lo = p * pe, n = std::min(pe, ne - lo);
+      I.pdesc[p].ne = n;
+      std::sort(idx.begin() + lo, idx.begin() + lo + n); // ascending element id = summation order inside the patch
+   }
    I.perm = idx;
 }
 
-// Residual side: local rows per patch, interior/interface split, yslot map, interface reduction lists.
-void patch_build_y(Integrator &I, PatchHostY &H)
+namespace
+{
+struct BlobWriter
+{
+   std::vector<unsigned char> b;
+   template <class T> void section(const std::vector<T> &v, size_t n)
+   {
+      const size_t bytes = n * sizeof(T), off = b.size();
+      b.resize(off + (size_t)patch_al16((int)bytes), 0);
+      if (bytes) { std::memcpy(b.data() + off, v.data(), bytes); }
+   }
+};
+
+// Sources per destination (shared-memory locations, ascending element order) -> first source per destination
+// plus the fold list: in phase k (k >= 1) the k-th source of every destination is added onto its first source,
+// so afterwards the first source holds the complete sum.  Destinations with identical source lists (the (i,j)
+// and (j,i) entries of a symmetric element matrix) share their folds.  Layout of `fold`:
+// 8 counts (phases 1..8; u32) followed by the (dst | src << 16) words, phase by phase.
+bool pack_sources(const std::vector<std::vector<unsigned short>> &srcs, int ndst, std::vector<unsigned short> &first,
+                  std::vector<unsigned> &fold)
+{
+   first.assign(ndst, 0);
+   std::vector<std::vector<unsigned>> ph(PATCH_MAXEXTRA + 1);
+   for (int d = 0; d < ndst; d++)
+   {
+      const std::vector<unsigned short> &L = srcs[d];
+      if (L.empty() || (int)L.size() > 1 + PATCH_MAXEXTRA) { return false; }
+      first[d] = L[0];
+      for (size_t k = 1; k < L.size(); k++) { ph[k].push_back((unsigned)L[0] | ((unsigned)L[k] << 16)); }
+   }
+   fold.assign(8, 0u);
+   for (int k = 1; k <= PATCH_MAXEXTRA; k++)
+   {
+      std::sort(ph[k].begin(), ph[k].end());
+      ph[k].erase(std::unique(ph[k].begin(), ph[k].end()), ph[k].end());
+      fold[k - 1] = (unsigned)ph[k].size();
+      fold.insert(fold.end(), ph[k].begin(), ph[k].end());
+   }
+   return true;
+}
+
+// group (destination, staging index) pairs by destination; sources stay in ascending staging (= patch) order
+void group_by_dst(std::vector<std::pair<int, int>> &tup, PatchHost &H)
+{
+   std::stable_sort(tup.begin(), tup.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first < b.first; });
+   H.ptr.clear(); H.dst.clear();
+   H.src.resize(tup.size());
+   for (size_t k = 0; k < tup.size(); k++)
+   {
+      if (k == 0 || tup[k].first != tup[k - 1].first)
+      {
+         H.ptr.push_back((int)k);
+         H.dst.push_back(tup[k].first);
+      }
+      H.src[k] = tup[k].second;
+   }
+   H.ptr.push_back((int)tup.size());
+}
+} // namespace
+
+// Residual side: local rows per patch (interior / interface), row sources, interface reduction lists.
+bool patch_build_y(Integrator &I, PatchHost &H)
 {
    const int ne = I.ne, nvd = I.nvd, pe = PATCH_PE, np = (int)I.pdesc.size();
    // which patches touch a dof: first patch id, or -2 when more than one
@@ -179,10 +193,14 @@ void patch_build_y(Integrator &I, PatchHostY &H)
    }
    I.prow_off.assign(np + 1, 0);
    std::vector<std::vector<int>> rows(np);
-   H.yslot.assign((size_t)nvd * I.stride, 0);
+   std::vector<std::vector<unsigned char>> blobs(np);
+   bool ok = true;
    parallel_for_p(np, 64, [&](long b, long e)
    {
-      std::vector<int> vd, dofs, ifc;
+      std::vector<int> vd, dofs, ifc, ylist;
+      std::vector<std::vector<unsigned short>> srcs;
+      std::vector<unsigned short> first;
+      std::vector<unsigned> fold;
       for (long p = b; p < e; p++)
       {
          PatchDesc &D = I.pdesc[p];
@@ -202,6 +220,7 @@ void patch_build_y(Integrator &I, PatchHostY &H)
          D.nrow_int = (int)R.size();
          R.insert(R.end(), ifc.begin(), ifc.end());
          D.nrows = (int)R.size();
+         srcs.assign(D.nrows, std::vector<unsigned short>());
          for (int l = 0; l < D.ne; l++)
          {
             build_vdofs(I, I.perm[lo + l], vd);
@@ -211,26 +230,35 @@ void patch_build_y(Integrator &I, PatchHostY &H)
                int lr;
                if (owner[v] != -2) { lr = (int)(std::lower_bound(R.begin(), R.begin() + D.nrow_int, v) - R.begin()); }
                else { lr = (int)(std::lower_bound(R.begin() + D.nrow_int, R.end(), v) - R.begin()); }
-               H.yslot[(size_t)i * I.stride + lo + l] = (unsigned short)patch_swz(lr);
+               srcs[lr].push_back((unsigned short)(i * PATCH_LD + l));
             }
          }
+         if (!pack_sources(srcs, D.nrows, first, fold)) { ok = false; continue; }
+         D.nyfold = (int)fold.size();
+         ylist.assign(R.begin(), R.begin() + D.nrow_int);
+         BlobWriter W;
+         W.section(first, first.size());
+         W.section(fold, fold.size());
+         W.section(ylist, ylist.size());
+         blobs[p].swap(W.b);
       }
    });
-   // offsets, lists
-   I.max_rows = 0;
-   long yoff = 0, soff = 0;
+   if (!ok) { return false; }
+   long soff = 0, boff = 0;
+   I.max_yblob = 0;
    for (int p = 0; p < np; p++)
    {
       PatchDesc &D = I.pdesc[p];
-      D.y_off = (int)yoff;
       D.ystage_off = (int)soff;
-      yoff += D.nrow_int;
+      D.yblob_off = (int)(boff / 16);
+      D.yblob_bytes = (int)blobs[p].size();
       soff += D.nrows - D.nrow_int;
+      boff += (long)blobs[p].size();
       I.prow_off[p + 1] = I.prow_off[p] + D.nrows;
-      I.max_rows = std::max(I.max_rows, D.nrows);
+      I.max_yblob = std::max(I.max_yblob, D.yblob_bytes);
    }
-   H.ystage_size = soff;
-   H.ylist.resize(std::max<long>(yoff, 1));
+   H.stage_size = soff;
+   H.blob.resize(std::max<long>(boff, 16));
    I.prows.resize(I.prow_off[np]);
    std::vector<std::pair<int, int>> tup; // (dof, stage index) in ascending patch order
    tup.reserve(soff);
@@ -238,63 +266,48 @@ void patch_build_y(Integrator &I, PatchHostY &H)
    {
       const PatchDesc &D = I.pdesc[p];
       std::copy(rows[p].begin(), rows[p].end(), I.prows.begin() + I.prow_off[p]);
-      std::copy(rows[p].begin(), rows[p].begin() + D.nrow_int, H.ylist.begin() + D.y_off);
+      std::copy(blobs[p].begin(), blobs[p].end(), H.blob.begin() + (size_t)D.yblob_off * 16);
       for (int k = D.nrow_int; k < D.nrows; k++) { tup.emplace_back(rows[p][k], D.ystage_off + (k - D.nrow_int)); }
    }
-   std::stable_sort(tup.begin(), tup.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first < b.first; });
-   H.y_ptr.assign(1, 0);
-   H.y_dst.clear();
-   H.y_src.resize(tup.size());
-   for (size_t k = 0; k < tup.size(); k++)
-   {
-      if (k == 0 || tup[k].first != tup[k - 1].first)
-      {
-         if (k) { H.y_ptr.push_back((int)k); }
-         H.y_dst.push_back(tup[k].first);
-      }
-      H.y_src[k] = tup[k].second;
-   }
-   H.y_ptr.push_back((int)tup.size());
-   if (tup.empty()) { H.y_ptr.assign(1, 0); }
+   group_by_dst(tup, H);
+   return true;
 }
 
-// Matrix side: slot of every element-matrix entry, runs of interior slots, interface reduction lists.
-void patch_build_v(Integrator &I, PatchHostV &H)
+// Matrix side: slots of the patch (interior rows in CSR order, then interface entries), slot sources,
+// runs of consecutive CSR positions, interface reduction lists.
+bool patch_build_v(Integrator &I, PatchHost &H)
 {
    const int nvd = I.nvd, pe = PATCH_PE, np = (int)I.pdesc.size();
-   H.pslot.assign((size_t)nvd * nvd * I.stride, 0);
-   struct PerPatch
-   {
-      std::vector<int> run_s, run_g;
-      std::vector<int> ifc_gpos; // global CSR position of each interface slot
-   };
-   std::vector<PerPatch> PP(np);
+   std::vector<std::vector<unsigned char>> blobs(np);
+   std::vector<std::vector<int>> ifc_gpos(np);
    bool ok = true;
    parallel_for_p(np, 64, [&](long b, long e)
    {
-      std::vector<int> vd, base;
+      std::vector<int> vd, base, run_s, run_g;
       std::vector<long> keys;
+      std::vector<std::vector<unsigned short>> srcs;
+      std::vector<unsigned short> first;
+      std::vector<unsigned> fold;
       for (long p = b; p < e; p++)
       {
          PatchDesc &D = I.pdesc[p];
-         PerPatch &P = PP[p];
          const int lo = (int)p * pe;
          const int *R = I.prows.data() + I.prow_off[p];
-         // interior rows: slots follow the CSR rows; merge rows with consecutive dof ids into runs
+         // interior rows: slots follow the CSR rows; rows with consecutive dof ids merge into runs
          base.assign(D.nrows, 0);
          int s = 0;
-         P.run_s.clear(); P.run_g.clear();
+         run_s.clear(); run_g.clear();
          for (int lr = 0; lr < D.nrow_int; lr++)
          {
             const int r = R[lr];
-            if (lr == 0 || R[lr - 1] + 1 != r) { P.run_s.push_back(s); P.run_g.push_back(I.rowptr[r]); }
+            if (lr == 0 || R[lr - 1] + 1 != r) { run_s.push_back(s); run_g.push_back(I.rowptr[r]); }
             base[lr] = s;
             s += I.rowptr[r + 1] - I.rowptr[r];
          }
          D.nint = s;
-         D.nruns = (int)P.run_s.size();
-         P.run_s.push_back(s); // sentinel
-         P.run_g.push_back(0);
+         D.nruns = (int)run_s.size();
+         run_s.push_back(s); // sentinel
+         run_g.push_back(0);
          // interface rows: the columns present in this patch
          keys.clear();
          for (int l = 0; l < D.ne; l++)
@@ -303,7 +316,7 @@ void patch_build_v(Integrator &I, PatchHostV &H)
             for (int i = 0; i < nvd; i++)
             {
                const int lr = (int)(std::lower_bound(R + D.nrow_int, R + D.nrows, vd[i]) - R);
-               if (lr < D.nrows && R[lr] == vd[i] && lr >= D.nrow_int)
+               if (lr < D.nrows && R[lr] == vd[i])
                {
                   for (int j = 0; j < nvd; j++) { keys.push_back(((long)lr << 32) | (unsigned)vd[j]); }
                }
@@ -312,15 +325,15 @@ void patch_build_v(Integrator &I, PatchHostV &H)
          std::sort(keys.begin(), keys.end());
          keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
          D.nslots = D.nint + (int)keys.size();
-         if (D.nslots > 65520) { ok = false; }
-         P.ifc_gpos.resize(keys.size());
+         ifc_gpos[p].resize(keys.size());
          for (size_t k = 0; k < keys.size(); k++)
          {
             const int r = R[(int)(keys[k] >> 32)], c = (int)(keys[k] & 0xffffffff);
             const int *cb = I.colidx.data() + I.rowptr[r], *ce = I.colidx.data() + I.rowptr[r + 1];
-            P.ifc_gpos[k] = (int)(std::lower_bound(cb, ce, c) - I.colidx.data());
+            ifc_gpos[p][k] = (int)(std::lower_bound(cb, ce, c) - I.colidx.data());
          }
-         // element entries -> slots
+         // element entries -> slots; a slot lists its sources in ascending element order
+         srcs.assign(D.nslots, std::vector<unsigned short>());
          for (int l = 0; l < D.ne; l++)
          {
             build_vdofs(I, I.perm[lo + l], vd);
@@ -340,54 +353,51 @@ void patch_build_v(Integrator &I, PatchHostV &H)
                      const long key = ((long)lr << 32) | (unsigned)vd[j];
                      slot = D.nint + (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
                   }
-                  H.pslot[((size_t)i * nvd + j) * I.stride + lo + l] = (unsigned short)patch_swz(slot);
+                  const int lo_ = std::min(i, j), hi_ = std::max(i, j);
+                  const int k = hi_ * (hi_ + 1) / 2 + lo_; // symidx (madb_kernels.cuh)
+                  srcs[slot].push_back((unsigned short)(k * PATCH_LD + l));
                }
             }
          }
+         if (!pack_sources(srcs, D.nslots, first, fold)) { ok = false; continue; }
+         D.nvfold = (int)fold.size();
+         BlobWriter W;
+         W.section(first, first.size());
+         W.section(fold, fold.size());
+         W.section(run_s, run_s.size());
+         W.section(run_g, run_g.size());
+         blobs[p].swap(W.b);
       }
    });
-   if (!ok) { set_error("patch assembly: more than 65535 matrix slots in one patch"); I.have_patch_vals = false; return; }
-   long roff = 0, soff = 0;
-   I.max_slots = 0;
-   I.max_runs = 0;
+   if (!ok) { set_error("patch assembly: a matrix entry has more than 8 contributing elements in one patch"); return false; }
+   long soff = 0, boff = 0;
+   I.max_vblob = 0;
    for (int p = 0; p < np; p++)
    {
       PatchDesc &D = I.pdesc[p];
-      D.run_off = (int)roff;
       D.stage_off = (int)soff;
-      roff += D.nruns + 1;
+      D.vblob_off = (int)(boff / 16);
+      D.vblob_bytes = (int)blobs[p].size();
       soff += D.nslots - D.nint;
-      I.max_slots = std::max(I.max_slots, D.nslots);
-      I.max_runs = std::max(I.max_runs, D.nruns);
+      boff += (long)blobs[p].size();
+      I.max_vblob = std::max(I.max_vblob, D.vblob_bytes);
    }
-   H.vstage_size = soff;
-   H.run_s.resize(roff); H.run_g.resize(roff); 
+   if (boff / 16 >= 0x7fffffffL) { set_error("patch assembly: maps too large"); return false; }
+   H.stage_size = soff;
+   H.blob.resize(std::max<long>(boff, 16));
    std::vector<std::pair<int, int>> tup((size_t)soff);
    parallel_for_p(np, 64, [&](long b, long e)
    {
       for (long p = b; p < e; p++)
       {
          const PatchDesc &D = I.pdesc[p];
-         std::copy(PP[p].run_s.begin(), PP[p].run_s.end(), H.run_s.begin() + D.run_off);
-         std::copy(PP[p].run_g.begin(), PP[p].run_g.end(), H.run_g.begin() + D.run_off);
-         for (size_t k = 0; k < PP[p].ifc_gpos.size(); k++) { tup[(size_t)D.stage_off + k] = {PP[p].ifc_gpos[k], D.stage_off + (int)k}; }
+         std::copy(blobs[p].begin(), blobs[p].end(), H.blob.begin() + (size_t)D.vblob_off * 16);
+         for (size_t k = 0; k < ifc_gpos[p].size(); k++) { tup[(size_t)D.stage_off + k] = {ifc_gpos[p][k], D.stage_off + (int)k}; }
       }
    });
-   // group by CSR position, sources in ascending staging (= patch) order
-   std::stable_sort(tup.begin(), tup.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first < b.first; });
-   H.v_ptr.clear(); H.v_dst.clear();
-   H.v_src.resize(tup.size());
-   for (size_t k = 0; k < tup.size(); k++)
-   {
-      if (k == 0 || tup[k].first != tup[k - 1].first)
-      {
-         H.v_ptr.push_back((int)k);
-         H.v_dst.push_back(tup[k].first);
-      }
-      H.v_src[k] = tup[k].second;
-   }
-   H.v_ptr.push_back((int)tup.size());
+   group_by_dst(tup, H);
    I.have_patch_vals = true;
+   return true;
 }
 
 } // namespace madb

@@ -53,7 +53,7 @@ Integrator::~Integrator()
    cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_perm); cudaFree(d_cvalue); cudaFree(d_cgrad); cudaFree(d_energy); cudaFree(d_esum);
    cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
-   cudaFree(d_pdesc); cudaFree(d_yslot); cudaFree(d_pslot); cudaFree(d_ylist); cudaFree(d_run_s); cudaFree(d_run_g);
+   cudaFree(d_pdesc); cudaFree(d_yblob); cudaFree(d_vblob);
    cudaFree(d_ystage); cudaFree(d_vstage); cudaFree(d_yptr); cudaFree(d_ysrc); cudaFree(d_ydst);
    cudaFree(d_vptr); cudaFree(d_vsrc); cudaFree(d_vdst);
 }
@@ -173,19 +173,6 @@ template <class T> static int upload(const std::vector<T> &h, T **d)
    return 0;
 }
 
-// [n][stride] 16-bit slots -> [(n+1)/2][stride] words holding slots 2k (low half) and 2k+1 (high half)
-static void pack_slots(const std::vector<unsigned short> &in, int n, int stride, std::vector<unsigned short> &out)
-{
-   const int nw = (n + 1) / 2;
-   out.assign((size_t)nw * stride * 2, 0);
-   for (int k = 0; k < n; k++)
-   {
-      const unsigned short *src = in.data() + (size_t)k * stride;
-      unsigned short *dst = out.data() + (size_t)(k / 2) * stride * 2 + (k & 1);
-      for (int t = 0; t < stride; t++) { dst[(size_t)2 * t] = src[t]; }
-   }
-}
-
 static int setup_integrator(Integrator &I)
 {
    const int dim = I.mesh->dim;
@@ -273,26 +260,22 @@ static int setup_integrator(Integrator &I)
    if (upload(e2n, &I.d_e2n) || upload(vmap, &I.d_vmap) || upload(pmap, &I.d_pmap) || upload(I.perm, &I.d_perm)) { return 2; }
    if (I.use_patches)
    {
-      PatchHostY H;
-      patch_build_y(I, H);
-      std::vector<unsigned short> packed;
-      pack_slots(H.yslot, I.nvd, I.stride, packed);
-      if (upload(packed, &I.d_yslot) || upload(H.ylist, &I.d_ylist) || upload(H.y_ptr, &I.d_yptr) || upload(H.y_src, &I.d_ysrc) ||
-          upload(H.y_dst, &I.d_ydst) || upload(I.pdesc, &I.d_pdesc))
+      PatchHost H;
+      if (!patch_build_y(I, H)) { set_error("patch assembly: a dof has more than 8 contributing elements in one patch (set MADB_NO_PATCH=1)"); return 1; }
+      if (upload(H.blob, &I.d_yblob) || upload(H.ptr, &I.d_yptr) || upload(H.src, &I.d_ysrc) || upload(H.dst, &I.d_ydst) ||
+          upload(I.pdesc, &I.d_pdesc))
       {
          return 2;
       }
-      CUDA_OK(cudaMalloc((void **)&I.d_ystage, std::max<size_t>(H.ystage_size, 1) * sizeof(double)));
+      CUDA_OK(cudaMalloc((void **)&I.d_ystage, std::max<size_t>(H.stage_size, 1) * sizeof(double)));
       PatchDev &P = I.pdev;
       P.npatch = (int)I.pdesc.size();
-      P.max_rows = I.max_rows;
-      P.max_slots = 0;
-      P.max_runs = 0;
+      P.max_yblob = I.max_yblob;
+      P.max_vblob = 0;
       P.desc = I.d_pdesc;
-      P.yslot = I.d_yslot;
-      P.ylist = I.d_ylist;
+      P.yblob = I.d_yblob;
       P.ystage = I.d_ystage;
-      P.ny_ifc = (int)H.y_dst.size();
+      P.ny_ifc = (int)H.dst.size();
       P.y_ptr = I.d_yptr; P.y_src = I.d_ysrc; P.y_dst = I.d_ydst;
    }
 
@@ -364,32 +347,25 @@ static int setup_integrator(Integrator &I)
 
 static int ensure_pattern_device(Integrator &I)
 {
-   if (I.d_e2csr || I.d_pslot) { return 0; }
+   if (I.d_e2csr || I.d_vblob) { return 0; }
    build_pattern(I);
    if (!I.have_pattern) { return 1; }
    if (I.use_patches)
    {
-      PatchHostV H;
-      patch_build_v(I, H);
-      if (!I.have_patch_vals) { return 1; }
-      std::vector<unsigned short> packed;
-      pack_slots(H.pslot, I.nvd * I.nvd, I.stride, packed);
-      H.pslot.clear(); H.pslot.shrink_to_fit();
-      if (upload(packed, &I.d_pslot) || upload(H.run_s, &I.d_run_s) || upload(H.run_g, &I.d_run_g) ||
-          upload(H.v_ptr, &I.d_vptr) || upload(H.v_src, &I.d_vsrc) || upload(H.v_dst, &I.d_vdst) ||
+      PatchHost H;
+      if (!patch_build_v(I, H)) { return 1; }
+      if (upload(H.blob, &I.d_vblob) || upload(H.ptr, &I.d_vptr) || upload(H.src, &I.d_vsrc) || upload(H.dst, &I.d_vdst) ||
           upload(I.rowptr, &I.d_rowptr) || upload(I.colidx, &I.d_colidx))
       {
          return 2;
       }
-      CUDA_OK(cudaMalloc((void **)&I.d_vstage, std::max<size_t>(H.vstage_size, 1) * sizeof(double)));
+      CUDA_OK(cudaMalloc((void **)&I.d_vstage, std::max<size_t>(H.stage_size, 1) * sizeof(double)));
       CUDA_OK(cudaMemcpy(I.d_pdesc, I.pdesc.data(), I.pdesc.size() * sizeof(PatchDesc), cudaMemcpyHostToDevice));
       PatchDev &P = I.pdev;
-      P.max_slots = I.max_slots;
-      P.max_runs = I.max_runs;
-      P.pslot = I.d_pslot;
-      P.run_s = I.d_run_s; P.run_g = I.d_run_g;
+      P.max_vblob = I.max_vblob;
+      P.vblob = I.d_vblob;
       P.vstage = I.d_vstage;
-      P.nv_ifc = (int)H.v_dst.size();
+      P.nv_ifc = (int)H.dst.size();
       P.v_ptr = I.d_vptr; P.v_src = I.d_vsrc; P.v_dst = I.d_vdst;
       return 0;
    }
@@ -849,7 +825,6 @@ extern "C"
       if (ncolors)
       {
          *ncolors = (int)I->color_off.size() - 1;
-         if (I->use_patches) { for (const PatchDesc &D : I->pdesc) { *ncolors = std::max(*ncolors, D.ncol); } }
       }
       return 0;
    }
@@ -858,12 +833,12 @@ extern "C"
       for (int k = 0; k < 8; k++) { out[k] = 0; }
       if (!I->use_patches) { return 0; }
       out[0] = (int64_t)I->pdesc.size();
-      out[1] = I->max_rows;
-      out[2] = I->max_slots;
       out[3] = I->pdev.ny_ifc;
       out[4] = I->pdev.nv_ifc;
       for (const PatchDesc &D : I->pdesc)
       {
+         out[1] = std::max<int64_t>(out[1], D.nrows);
+         out[2] = std::max<int64_t>(out[2], D.nslots);
          out[5] += D.nrows - D.nrow_int;
          out[6] += D.nslots - D.nint;
          out[7] += D.nruns;

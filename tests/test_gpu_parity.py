@@ -238,7 +238,7 @@ def test_3d_trilinear_assembled(ctx, kind):
     s = G.permute_dofs(G.h1_space(mesh, 1, mode=O.GRAD), 5)
     fs = S.diffusion(3) if kind == "diffusion" else S.minsurf(3, 0.5)
     of, gi = S.make_pair(ctx, mesh, [s], fs)
-    assert gi.ncolors >= 8
+    assert gi.ncolors >= 8 or gi.patch_stats()["patches"] >= 1  # colour-scatter path or patch assembly
     _compare(of, gi, _state(mesh, s))
 
 
