@@ -37,16 +37,17 @@ struct PatchDesc
    int nyfold;                // words of the row fold list (8 phase counts + folds)
    int ystage_off;            // ystage[ystage_off + (lr - nrow_int)] <- interface rows
    int yblob_off, yblob_bytes; // residual-side maps of the patch: yblob + 16*yblob_off
-   int nint, nslots;          // matrix slots: interior [0,nint) in CSR order, interface [nint,nslots)
+   int nint, nexc, nslots;    // matrix slots: [0,nint) interior rows in CSR order, [nint,nexc) interface entries of
+                              // this patch alone, [nexc,nslots) interface entries shared with other patches
    int nvfold;                // words of the slot fold list
    int nruns;                 // runs of consecutive CSR positions covering [0,nint)
-   int stage_off;             // vstage[stage_off + (s - nint)] <- interface slots
+   int stage_off;             // vstage[stage_off + (s - nexc)] <- shared interface slots
    int vblob_off, vblob_bytes; // matrix-side maps: vblob + 16*vblob_off
-   int pad[2];
+   int pad[1];
 };
 // Blob layouts (sections padded to 16 bytes, copied to shared memory with one bulk copy each):
 //   y blob: ysrc u16[nrows]  | yfold u32[nyfold] | ylist i32[nrow_int]
-//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | run_s i32[nruns+1] | run_g i32[nruns+1]
+//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | run_s i32[nruns+1] | run_g i32[nruns+1] | xg i32[nexc-nint]
 // ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
 // fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
 // phase k adds the k-th further source, so every row / slot is summed in ascending element order.

@@ -273,42 +273,28 @@ bool patch_build_y(Integrator &I, PatchHost &H)
    return true;
 }
 
-// Matrix side: slots of the patch (interior rows in CSR order, then interface entries), slot sources,
-// runs of consecutive CSR positions, interface reduction lists.
+// Matrix side: slots of the patch, slot sources, runs of consecutive CSR positions, interface reduction lists.
+// Slot order of a patch: [0,nint) rows interior to the patch, CSR order (runs of consecutive positions);
+// [nint,nexc) entries of interface rows that only this patch contributes to (explicit CSR positions);
+// [nexc,nslots) entries of interface rows shared with other patches.  The first two groups are final values
+// and are written straight to the CSR array; only the third goes through staging.
 bool patch_build_v(Integrator &I, PatchHost &H)
 {
    const int nvd = I.nvd, pe = PATCH_PE, np = (int)I.pdesc.size();
    std::vector<std::vector<unsigned char>> blobs(np);
-   std::vector<std::vector<int>> ifc_gpos(np);
-   bool ok = true;
+   std::vector<std::vector<long>> ifc_keys(np);  // (local row << 32 | column dof), sorted
+   std::vector<std::vector<int>> ifc_gpos(np);   // CSR position of each key
+   std::vector<std::vector<int>> shared_gpos(np); // CSR positions of the staged slots, staging order
+   // pass A: interface entries of every patch
    parallel_for_p(np, 64, [&](long b, long e)
    {
-      std::vector<int> vd, base, run_s, run_g;
-      std::vector<long> keys;
-      std::vector<std::vector<unsigned short>> srcs;
-      std::vector<unsigned short> first;
-      std::vector<unsigned> fold;
+      std::vector<int> vd;
       for (long p = b; p < e; p++)
       {
-         PatchDesc &D = I.pdesc[p];
+         const PatchDesc &D = I.pdesc[p];
          const int lo = (int)p * pe;
          const int *R = I.prows.data() + I.prow_off[p];
-         // interior rows: slots follow the CSR rows; rows with consecutive dof ids merge into runs
-         base.assign(D.nrows, 0);
-         int s = 0;
-         run_s.clear(); run_g.clear();
-         for (int lr = 0; lr < D.nrow_int; lr++)
-         {
-            const int r = R[lr];
-            if (lr == 0 || R[lr - 1] + 1 != r) { run_s.push_back(s); run_g.push_back(I.rowptr[r]); }
-            base[lr] = s;
-            s += I.rowptr[r + 1] - I.rowptr[r];
-         }
-         D.nint = s;
-         D.nruns = (int)run_s.size();
-         run_s.push_back(s); // sentinel
-         run_g.push_back(0);
-         // interface rows: the columns present in this patch
+         std::vector<long> &keys = ifc_keys[p];
          keys.clear();
          for (int l = 0; l < D.ne; l++)
          {
@@ -324,7 +310,6 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          }
          std::sort(keys.begin(), keys.end());
          keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
-         D.nslots = D.nint + (int)keys.size();
          ifc_gpos[p].resize(keys.size());
          for (size_t k = 0; k < keys.size(); k++)
          {
@@ -332,6 +317,67 @@ bool patch_build_v(Integrator &I, PatchHost &H)
             const int *cb = I.colidx.data() + I.rowptr[r], *ce = I.colidx.data() + I.rowptr[r + 1];
             ifc_gpos[p][k] = (int)(std::lower_bound(cb, ce, c) - I.colidx.data());
          }
+      }
+   });
+   // number of patches contributing to every CSR position of an interface row
+   std::vector<unsigned char> cnt(I.colidx.size(), 0);
+   for (int p = 0; p < np; p++)
+   {
+      for (int g : ifc_gpos[p]) { if (cnt[g] < 255) { cnt[g]++; } }
+   }
+   // pass B: slots, sources, blobs
+   bool ok = true;
+   parallel_for_p(np, 64, [&](long b, long e)
+   {
+      std::vector<int> vd, base, run_s, run_g, keyslot, xg;
+      std::vector<std::pair<int, int>> excl; // (CSR position, key index)
+      std::vector<std::vector<unsigned short>> srcs;
+      std::vector<unsigned short> first;
+      std::vector<unsigned> fold;
+      for (long p = b; p < e; p++)
+      {
+         PatchDesc &D = I.pdesc[p];
+         const int lo = (int)p * pe;
+         const int *R = I.prows.data() + I.prow_off[p];
+         const std::vector<long> &keys = ifc_keys[p];
+         // interior rows: slots follow the CSR rows; consecutive CSR positions merge into runs
+         base.assign(D.nrows, 0);
+         int s = 0;
+         run_s.clear(); run_g.clear();
+         for (int lr = 0; lr < D.nrow_int; lr++)
+         {
+            const int r = R[lr];
+            if (lr == 0 || R[lr - 1] + 1 != r) { run_s.push_back(s); run_g.push_back(I.rowptr[r]); }
+            base[lr] = s;
+            s += I.rowptr[r + 1] - I.rowptr[r];
+         }
+         // interface entries only this patch contributes to: final values, by CSR position
+         excl.clear();
+         keyslot.assign(keys.size(), -1);
+         for (size_t k = 0; k < keys.size(); k++) { if (cnt[ifc_gpos[p][k]] == 1) { excl.emplace_back(ifc_gpos[p][k], (int)k); } }
+         std::sort(excl.begin(), excl.end());
+         D.nint = s;
+         D.nruns = (int)run_s.size();
+         run_s.push_back(s); // sentinel
+         run_g.push_back(0);
+         xg.clear();
+         for (size_t k = 0; k < excl.size(); k++)
+         {
+            keyslot[excl[k].second] = s++;
+            xg.push_back(excl[k].first);
+         }
+         D.nexc = s;
+         // shared interface entries: staged
+         shared_gpos[p].clear();
+         for (size_t k = 0; k < keys.size(); k++)
+         {
+            if (keyslot[k] < 0)
+            {
+               keyslot[k] = s++;
+               shared_gpos[p].push_back(ifc_gpos[p][k]);
+            }
+         }
+         D.nslots = s;
          // element entries -> slots; a slot lists its sources in ascending element order
          srcs.assign(D.nslots, std::vector<unsigned short>());
          for (int l = 0; l < D.ne; l++)
@@ -351,7 +397,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
                   else
                   {
                      const long key = ((long)lr << 32) | (unsigned)vd[j];
-                     slot = D.nint + (int)(std::lower_bound(keys.begin(), keys.end(), key) - keys.begin());
+                     slot = keyslot[std::lower_bound(keys.begin(), keys.end(), key) - keys.begin()];
                   }
                   const int lo_ = std::min(i, j), hi_ = std::max(i, j);
                   const int k = hi_ * (hi_ + 1) / 2 + lo_; // symidx (madb_kernels.cuh)
@@ -366,6 +412,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          W.section(fold, fold.size());
          W.section(run_s, run_s.size());
          W.section(run_g, run_g.size());
+         W.section(xg, xg.size());
          blobs[p].swap(W.b);
       }
    });
@@ -378,7 +425,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
       D.stage_off = (int)soff;
       D.vblob_off = (int)(boff / 16);
       D.vblob_bytes = (int)blobs[p].size();
-      soff += D.nslots - D.nint;
+      soff += D.nslots - D.nexc;
       boff += (long)blobs[p].size();
       I.max_vblob = std::max(I.max_vblob, D.vblob_bytes);
    }
@@ -392,7 +439,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
       {
          const PatchDesc &D = I.pdesc[p];
          std::copy(blobs[p].begin(), blobs[p].end(), H.blob.begin() + (size_t)D.vblob_off * 16);
-         for (size_t k = 0; k < ifc_gpos[p].size(); k++) { tup[(size_t)D.stage_off + k] = {ifc_gpos[p][k], D.stage_off + (int)k}; }
+         for (size_t k = 0; k < shared_gpos[p].size(); k++) { tup[(size_t)D.stage_off + k] = {shared_gpos[p][k], D.stage_off + (int)k}; }
       }
    });
    group_by_dst(tup, H);

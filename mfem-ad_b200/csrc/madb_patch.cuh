@@ -163,11 +163,12 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
       {
          const int o_runs = o_vfold + patch_al16(4 * D.nvfold);
          const int o_rung = o_runs + patch_al16(4 * (D.nruns + 1));
+         const int o_xg = o_rung + patch_al16(4 * (D.nruns + 1));
 #define MADB_RUN_S(r) (*(const int *)(smraw + o_runs + 4 * (r)))
 #define MADB_RUN_G(r) (*(const int *)(smraw + o_rung + 4 * (r)))
          // interior slots are numbered in CSR order: slot s of run r goes to position run_g[r] + (s - run_s[r])
          int rn = 0, rs = MADB_RUN_S(0), re = (D.nruns > 0) ? MADB_RUN_S(1) : 0, rg = MADB_RUN_G(0);
-         const int nint = D.nint, nslots = D.nslots;
+         const int nint = D.nint, nexc = D.nexc, nslots = D.nslots;
 #pragma unroll 4
          for (int s = tid; s < nint; s += PE)
          {
@@ -181,8 +182,12 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
             }
             a.vals[rg + (s - rs)] = v;
          }
-         double *stage = P.vstage + D.stage_off - nint;
-         for (int s = nint + tid; s < nslots; s += PE) { stage[s] = MADB_SA(*(const unsigned short *)(smraw + o_vb + 2 * s)); }
+         for (int s = nint + tid; s < nexc; s += PE)
+         {
+            a.vals[*(const int *)(smraw + o_xg + 4 * (s - nint))] = MADB_SA(*(const unsigned short *)(smraw + o_vb + 2 * s));
+         }
+         double *stage = P.vstage + D.stage_off - nexc;
+         for (int s = nexc + tid; s < nslots; s += PE) { stage[s] = MADB_SA(*(const unsigned short *)(smraw + o_vb + 2 * s)); }
 #undef MADB_RUN_S
 #undef MADB_RUN_G
       }

@@ -840,7 +840,7 @@ extern "C"
          out[1] = std::max<int64_t>(out[1], D.nrows);
          out[2] = std::max<int64_t>(out[2], D.nslots);
          out[5] += D.nrows - D.nrow_int;
-         out[6] += D.nslots - D.nint;
+         out[6] += D.nslots - D.nexc;
          out[7] += D.nruns;
       }
       return 0;
