@@ -51,6 +51,9 @@ MADB_HD ZD zfmac(ZD a, double b, ZD c)
    return {fma(a.v, b, c.v), false};
 }
 
+/// acc += a*b, skipped when a is structurally zero
+MADB_HD void zacc(double &acc, ZD a, double b) { if (!a.z) { acc = fma(a.v, b, acc); } }
+
 // packed upper-triangular index of (i,j), i<=j, row-major
 template <int N> MADB_HD constexpr int hidx(int i, int j) { return i * N - (i * (i - 1)) / 2 + (j - i); }
 

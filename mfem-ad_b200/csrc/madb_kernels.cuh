@@ -20,6 +20,7 @@
 #pragma once
 #include "madb_config.cuh"
 #include "madb_host.hpp"
+#include "madb_sf2d.cuh"
 #include <cuda_runtime.h>
 
 namespace madb
@@ -50,6 +51,7 @@ template <class Func, class Cfg> struct AsmArgs
    double *cvalue, *cgrad; // MODE_COEF: value [e][q] and gradient [e][q][N] at the points
    double fparams[Func::N_PARAM > 0 ? Func::N_PARAM : 1];
    Tables<Cfg> tab;
+   typename Sf2dTabFor<Cfg>::type sf; // 1-D tables of the sum-factorised 2-D path (empty otherwise)
 };
 
 template <int DIM> MADB_HD void invert(const double (&J)[DIM][DIM], double (&Ji)[DIM][DIM], double &det)
@@ -461,6 +463,273 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
    }
 }
 
+/// Sum-factorised gather + quadrature loop (madb_sf2d.cuh) for 2-D scalar H1 fields with ADEval::GRAD.
+template <class Func, class Cfg, int MODE>
+__device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a, const int t,
+                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
+                                                     double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1])
+{
+   constexpr int ND = Cfg::template field<0>::ND1D, NQ = Cfg::NQ1D, NVD = Cfg::NVD;
+   constexpr bool RES = (MODE & MODE_RES) != 0, JAC = (MODE & MODE_JAC) != 0, ACT = (MODE & MODE_ACT) != 0;
+   constexpr int ORDER = (JAC || ACT) ? 2 : 1;
+   static_assert(Func::N_INPUT == 2 && Func::N_QPRM == 0, "sum-factorised 2-D path: scalar field, GRAD, no per-point parameters");
+   const auto &T = a.sf;
+
+   // ---- gather ---------------------------------------------------------------------------
+   double X[4][2];
+#pragma unroll
+   for (int k = 0; k < 4; k++)
+   {
+      const int n = a.e2n[(size_t)k * a.stride + t];
+      X[k][0] = a.coords[(size_t)n * 2];
+      X[k][1] = a.coords[(size_t)n * 2 + 1];
+   }
+   double u[ND][ND], vd[ACT ? ND : 1][ACT ? ND : 1];
+#pragma unroll
+   for (int i = 0; i < NVD; i++)
+   {
+      const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
+      u[i / ND][i % ND] = a.x[idx];
+      if constexpr (ACT) { vd[i / ND][i % ND] = a.v[idx]; }
+   }
+   Func f;
+   f.load(a.fparams);
+
+   // ---- bilinear geometry: dx/dxi = a0 + d eta, dx/deta = c0 + d xi ---------------------------
+   double a0[2], c0[2], dd[2], Jc1[NQ][2];
+#pragma unroll
+   for (int i = 0; i < 2; i++)
+   {
+      a0[i] = X[1][i] - X[0][i];
+      c0[i] = X[2][i] - X[0][i];
+      dd[i] = (X[3][i] - X[2][i]) - a0[i];
+#pragma unroll
+      for (int q = 0; q < NQ; q++) { Jc1[q][i] = fma(dd[i], T.xq[q], c0[i]); }
+   }
+
+   // ---- x-step of the interpolation ----------------------------------------------------------
+   double ub[ND][NQ], ug[ND][NQ], vb[ACT ? ND : 1][ACT ? NQ : 1], vg[ACT ? ND : 1][ACT ? NQ : 1];
+#pragma unroll
+   for (int i2 = 0; i2 < ND; i2++)
+   {
+#pragma unroll
+      for (int q = 0; q < NQ; q++)
+      {
+         double sb = T.B[q][0] * u[i2][0], sg = T.G[q][0] * u[i2][0];
+#pragma unroll
+         for (int i1 = 1; i1 < ND; i1++)
+         {
+            sb = fma(T.B[q][i1], u[i2][i1], sb);
+            sg = fma(T.G[q][i1], u[i2][i1], sg);
+         }
+         ub[i2][q] = sb;
+         ug[i2][q] = sg;
+         if constexpr (ACT)
+         {
+            double tb = T.B[q][0] * vd[i2][0], tg = T.G[q][0] * vd[i2][0];
+#pragma unroll
+            for (int i1 = 1; i1 < ND; i1++)
+            {
+               tb = fma(T.B[q][i1], vd[i2][i1], tb);
+               tg = fma(T.G[q][i1], vd[i2][i1], tg);
+            }
+            vb[i2][q] = tb;
+            vg[i2][q] = tg;
+         }
+      }
+   }
+
+   if constexpr (RES || ACT)
+   {
+#pragma unroll
+      for (int i = 0; i < NVD; i++) { r[i] = 0.0; }
+   }
+   if constexpr (JAC)
+   {
+#pragma unroll
+      for (int i = 0; i < Cfg::NSYM; i++) { A[i] = 0.0; }
+   }
+
+#pragma unroll
+   for (int q2 = 0; q2 < NQ; q2++)
+   {
+      const double J00 = fma(dd[0], T.xq[q2], a0[0]), J10 = fma(dd[1], T.xq[q2], a0[1]);
+      ZD gh0[NQ], gh1[NQ];                    // reference-space gradient (RES) or H^ v^ (ACT), weighted
+      ZD H00[JAC ? NQ : 1], H01[JAC ? NQ : 1], H11[JAC ? NQ : 1];
+#pragma unroll
+      for (int q1 = 0; q1 < NQ; q1++)
+      {
+         // y-step of the interpolation: reference gradient at (q2, q1)
+         double rg0 = T.B[q2][0] * ug[0][q1], rg1 = T.G[q2][0] * ub[0][q1];
+#pragma unroll
+         for (int i2 = 1; i2 < ND; i2++)
+         {
+            rg0 = fma(T.B[q2][i2], ug[i2][q1], rg0);
+            rg1 = fma(T.G[q2][i2], ub[i2][q1], rg1);
+         }
+         const double J01 = Jc1[q1][0], J11 = Jc1[q1][1];
+         const double det = J00 * J11 - J01 * J10;
+         const double rdet = 1.0 / det;
+         // physical gradient = J^-T (ref grad) = adj^T (ref grad) / det,  adj = [[J11,-J01],[-J10,J00]]
+         double xin[2];
+         xin[0] = (J11 * rg0 - J10 * rg1) * rdet;
+         xin[1] = (J00 * rg1 - J01 * rg0) * rdet;
+         using TA = AD<2, ORDER>;
+         TA xs[2];
+         xs[0] = ad_seed<2, ORDER>(xin[0], 0);
+         xs[1] = ad_seed<2, ORDER>(xin[1], 1);
+         const TA res = f(xs, nullptr);
+         const double wq = T.wq[q2] * T.wq[q1];
+         ZD h00 {0.0, true}, h01 {0.0, true}, h11 {0.0, true};
+         if constexpr (ORDER >= 2)
+         {
+            // H^ = (w/det) adj H adj^T
+            const double sc = wq * rdet;
+            const ZD g00 = res.H(hidx<2>(0, 0)), g01 = res.H(hidx<2>(0, 1)), g11 = res.H(hidx<2>(1, 1));
+            const ZD M00 = zfmac(g01, -J01, zmulc(g00, J11)), M01 = zfmac(g11, -J01, zmulc(g01, J11));
+            const ZD M10 = zfmac(g01, J00, zmulc(g00, -J10)), M11 = zfmac(g11, J00, zmulc(g01, -J10));
+            h00 = zmulc(zfmac(M01, -J01, zmulc(M00, J11)), sc);
+            h01 = zmulc(zfmac(M01, J00, zmulc(M00, -J10)), sc);
+            h11 = zmulc(zfmac(M11, J00, zmulc(M10, -J10)), sc);
+         }
+         if constexpr (JAC)
+         {
+            H00[q1] = h00;
+            H01[q1] = h01;
+            H11[q1] = h11;
+         }
+         if constexpr (RES)
+         {
+            // g^ = w adj g
+            gh0[q1] = zmulc(zfmac(res.G(1), -J01, zmulc(res.G(0), J11)), wq);
+            gh1[q1] = zmulc(zfmac(res.G(1), J00, zmulc(res.G(0), -J10)), wq);
+         }
+         if constexpr (ACT)
+         {
+            // y^ = H^ v^ with v^ the reference gradient of the direction
+            double vr0 = T.B[q2][0] * vg[0][q1], vr1 = T.G[q2][0] * vb[0][q1];
+#pragma unroll
+            for (int i2 = 1; i2 < ND; i2++)
+            {
+               vr0 = fma(T.B[q2][i2], vg[i2][q1], vr0);
+               vr1 = fma(T.G[q2][i2], vb[i2][q1], vr1);
+            }
+            gh0[q1] = zfmac(h01, vr1, zmulc(h00, vr0));
+            gh1[q1] = zfmac(h11, vr1, zmulc(h01, vr0));
+         }
+      }
+
+      // ---- element vector: r[i2][i1] += B[q2][i2] t0[i1] + G[q2][i2] t1[i1] ------------------------
+      if constexpr (RES || ACT)
+      {
+         ZD t0[ND], t1[ND];
+#pragma unroll
+         for (int i1 = 0; i1 < ND; i1++)
+         {
+            ZD s0 {0.0, true}, s1 {0.0, true};
+#pragma unroll
+            for (int q1 = 0; q1 < NQ; q1++)
+            {
+               s0 = zfmac(gh0[q1], T.G[q1][i1], s0);
+               s1 = zfmac(gh1[q1], T.B[q1][i1], s1);
+            }
+            t0[i1] = s0;
+            t1[i1] = s1;
+         }
+#pragma unroll
+         for (int i2 = 0; i2 < ND; i2++)
+         {
+#pragma unroll
+            for (int i1 = 0; i1 < ND; i1++)
+            {
+               zacc(r[i2 * ND + i1], t0[i1], T.B[q2][i2]);
+               zacc(r[i2 * ND + i1], t1[i1], T.G[q2][i2]);
+            }
+         }
+      }
+
+      // ---- element matrix (upper triangle), one H^ component at a time to keep the live set small ----
+      if constexpr (JAC)
+      {
+         {
+            ZD T00[ND][ND];
+#pragma unroll
+            for (int i1 = 0; i1 < ND; i1++)
+            {
+#pragma unroll
+               for (int j1 = i1; j1 < ND; j1++)
+               {
+                  ZD s {0.0, true};
+#pragma unroll
+                  for (int q1 = 0; q1 < NQ; q1++) { s = zfmac(H00[q1], T.GG[q1][i1][j1], s); }
+                  T00[i1][j1] = s;
+                  T00[j1][i1] = s;
+               }
+            }
+#pragma unroll
+            for (int J = 0; J < NVD; J++)
+            {
+#pragma unroll
+               for (int I = 0; I <= J; I++)
+               {
+                  zacc(A[symidx(I, J)], T00[I % ND][J % ND], T.BB[q2][I / ND][J / ND]);
+               }
+            }
+         }
+         {
+            ZD T01[ND][ND]; // sum_q1 G[q1][i1] B[q1][j1] H^01
+#pragma unroll
+            for (int i1 = 0; i1 < ND; i1++)
+            {
+#pragma unroll
+               for (int j1 = 0; j1 < ND; j1++)
+               {
+                  ZD s {0.0, true};
+#pragma unroll
+                  for (int q1 = 0; q1 < NQ; q1++) { s = zfmac(H01[q1], T.BG[q1][j1][i1], s); }
+                  T01[i1][j1] = s;
+               }
+            }
+#pragma unroll
+            for (int J = 0; J < NVD; J++)
+            {
+#pragma unroll
+               for (int I = 0; I <= J; I++)
+               {
+                  zacc(A[symidx(I, J)], T01[I % ND][J % ND], T.BG[q2][I / ND][J / ND]);
+                  zacc(A[symidx(I, J)], T01[J % ND][I % ND], T.BG[q2][J / ND][I / ND]);
+               }
+            }
+         }
+         {
+            ZD T11[ND][ND];
+#pragma unroll
+            for (int i1 = 0; i1 < ND; i1++)
+            {
+#pragma unroll
+               for (int j1 = i1; j1 < ND; j1++)
+               {
+                  ZD s {0.0, true};
+#pragma unroll
+                  for (int q1 = 0; q1 < NQ; q1++) { s = zfmac(H11[q1], T.BB[q1][i1][j1], s); }
+                  T11[i1][j1] = s;
+                  T11[j1][i1] = s;
+               }
+            }
+#pragma unroll
+            for (int J = 0; J < NVD; J++)
+            {
+#pragma unroll
+               for (int I = 0; I <= J; I++)
+               {
+                  zacc(A[symidx(I, J)], T11[I % ND][J % ND], T.GG[q2][I / ND][J / ND]);
+               }
+            }
+         }
+      }
+   }
+}
+
 /// Gather + quadrature loop of sorted element t: element vector r, upper triangle of the element matrix A.
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
 __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, const int t,
@@ -468,6 +737,14 @@ __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, con
                                                 double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1], double &energy)
 {
    constexpr int DIM = Cfg::DIM, NVD = Cfg::NVD;
+#ifndef MADB_NO_SF2D
+   if constexpr (sf2d_cfg<Cfg>() && Func::N_QPRM == 0 && (MODE == MODE_RES || MODE == (MODE_RES | MODE_JAC) || MODE == MODE_ACT))
+   {
+      energy = 0.0;
+      element_compute_sf2d<Func, Cfg, MODE>(a, t, r, A);
+      return;
+   }
+#endif
 
    // ---- gather: vertices, dofs of all fields ---------------------------------------
    double X[Cfg::NGN][DIM];

@@ -50,6 +50,7 @@ template <class Func, class Cfg> AsmArgs<Func, Cfg> &fill_args(const LaunchCtx &
    std::memcpy(a.tab.dphi, L.dphi, sizeof(a.tab.dphi));
    std::memcpy(a.tab.gdphi, L.gdphi, sizeof(a.tab.gdphi));
    std::memcpy(a.tab.w, L.w, sizeof(a.tab.w));
+   fill_sf2d(a.sf, L.b1d[0], L.g1d[0], L.xq1d, L.w1d);
    return a;
 }
 
