@@ -30,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 EPS = 0.5
 P = 2
+FP64_INSTR = 2754  # DFMA+DMUL+DADD per element in the SASS of k_patch<minsurf,Q2,RES|JAC> (tools/sass_count.sh)
 
 
 def peaks():
@@ -220,7 +221,13 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    launches_per_step = gi.ncolors
+    gi.assemble(x, y, vals)
+    stats = gi.patch_stats()
+    patch = stats["patches"] > 0
+    # patch path: k_patch + the two interface reductions (residual rows, CSR entries); colour path: one launch per colour
+    launches_per_step = 3 if patch else gi.ncolors
+    kernel_launches = 1 if patch else gi.ncolors
+    gi.set_timing(True)
     with torch.cuda.stream(stream):
         for _ in range(max(args.warmup, 3)):
             step_device()
@@ -229,18 +236,21 @@ def run_gpu(args):
         if rank == 0:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         barrier()
         ev0.record(stream)
         for k in range(args.steps):
-            kev[k][0].record(stream)
             gi.assemble(x, y, vals)
-            kev[k][1].record(stream)
             exchange()
         ev1.record(stream)
         barrier()
         ms_total = ev0.elapsed_time(ev1)
-        ms_kernel = float(np.mean([a.elapsed_time(b) for a, b in kev]))  # the ncolors launches of k_element<RES|JAC>
+        # dominant kernel alone: CUDA events recorded by the library on its stream around the element kernel(s)
+        kms = []
+        for k in range(min(args.steps, 10)):
+            gi.assemble(x, y, vals)
+            kms.append(gi.last_kernel_ms())
+        ms_kernel = float(np.mean(kms))
+        gi.set_timing(False)
         # keep the GPU busy a little longer so the clock sampler sees load
         t_end = time.perf_counter() + 1.0
         while time.perf_counter() < t_end:
@@ -280,11 +290,14 @@ def run_gpu(args):
             "dofs_per_gpu": ndof, "nnz_per_gpu": int(nnz), "setup_s": setup_s,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "kernel": "k_element<MinimalSurfaceEnergy<2>,Q2,RES|JAC>",
-                         "launches_per_step": launches_per_step, "avg_launch_ms": ms_kernel / launches_per_step,
+                         "kernel": ("k_patch" if patch else "k_element") + "<MinimalSurfaceEnergy<2>,Q2,RES|JAC>",
+                         "launches_per_step": kernel_launches, "avg_launch_ms": ms_kernel / kernel_launches,
                          "algorithmic_bytes_per_step": alg_bytes,
-                         "fp64": {"flop_est_per_element": 5400, "peak_tflops_measured": 37.1,
-                                  "frac": 5400.0 * nx * nx / (ms_kernel * 1e-3) / 37.1e12}},
+                         "note": "achieved = algorithmic bytes of one assembly / device time of the element kernel "
+                                 "(events on the library stream); the interface reductions add ms_per_step - kernel time",
+                         "fp64": {"fp64_instr_per_element": FP64_INSTR, "peak_tflops_measured": 37.1,
+                                  "frac": 2.0 * FP64_INSTR * nx * nx / (ms_kernel * 1e-3) / 37.1e12}},
+            "patch_stats": stats,
             "e2e": {"value": world * ndof / (e2e_ms * 1e-3), "unit": "DOF/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof + 8 * int(nnz)},
             "gpu_launches": launches_per_step * args.steps,

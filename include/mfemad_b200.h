@@ -146,6 +146,10 @@ int madb_integrator_sizes(madb_integrator *I, int64_t *ntotal, int *nq_el, int *
  * and max matrix slots per patch, interface dofs, interface matrix entries, staged residual and matrix
  * partials, CSR runs.  Matrix-side figures are 0 until the sparsity pattern has been built. */
 int madb_integrator_patch_stats(madb_integrator *I, int64_t *out);
+/* Device timing of the element kernel(s) of the last mult / assemble / grad_mult call: CUDA events on the
+ * context stream around the dominant kernel (the interface reduction and essential-dof kernels excluded). */
+int madb_integrator_set_timing(madb_integrator *I, int on);
+int madb_integrator_last_kernel_ms(madb_integrator *I, double *ms);
 
 /* Evaluator sources that vary in space (src/ad_native.hpp:56-61):
  * GridFunction parameter of field `field` (dof vector of that space), and

@@ -64,6 +64,8 @@ def lib():
         L.madb_integrator_destroy.argtypes = [vp]
         L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.madb_integrator_patch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.madb_integrator_set_timing.argtypes = [vp, C.c_int]
+        L.madb_integrator_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
         L.madb_integrator_set_param_field.argtypes = [vp, C.c_int, dp]
         L.madb_integrator_set_param_qf.argtypes = [vp, C.c_int, dp]
         L.madb_integrator_set_essential.argtypes = [vp, C.c_int, ip]
@@ -207,6 +209,15 @@ class Integrator:
         self.ntotal, self.nq_el, self.ncolors = nt.value, nq.value, nc.value
         self._pattern = None
         self._keep = []
+
+    def set_timing(self, on=True):
+        _check(lib().madb_integrator_set_timing(self.h, 1 if on else 0))
+
+    def last_kernel_ms(self):
+        """Device time of the element kernel(s) of the last call (set_timing(True) first)."""
+        ms = C.c_double()
+        _check(lib().madb_integrator_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def patch_stats(self):
         """Patch-assembly diagnostics (madb_integrator_patch_stats)."""

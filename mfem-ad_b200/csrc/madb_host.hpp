@@ -85,6 +85,7 @@ struct LaunchCtx
    const double *b1d[8], *g1d[8];
    const double *xq1d, *w1d;
    const PatchDev *patch; // non-null: patch assembly (elements in patch order)
+   cudaEvent_t ev0, ev1;  // non-null: recorded around the element kernel(s) (madb_integrator_set_timing)
 };
 
 struct KernelOps
@@ -211,6 +212,10 @@ struct Integrator
    unsigned char *d_yblob = nullptr, *d_vblob = nullptr;
    double *d_ystage = nullptr, *d_vstage = nullptr;
    int *d_yptr = nullptr, *d_ysrc = nullptr, *d_ydst = nullptr, *d_vptr = nullptr, *d_vsrc = nullptr, *d_vdst = nullptr;
+
+   // optional device timing of the element kernel(s)
+   bool timing = false;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
    // essential dofs
    int ness = 0;

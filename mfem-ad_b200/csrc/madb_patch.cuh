@@ -224,7 +224,9 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       if (e != cudaSuccess) { return (int)e; }
       smem_set = smem_bytes;
    }
+   if (L.ev0) { cudaEventRecord(L.ev0, L.stream); }
    kern<<<P.npatch, PATCH_PE, smem_bytes, L.stream>>>(a, P);
+   if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
    if (wy && P.ny_ifc > 0)
    {
       k_ifc_reduce<<<(P.ny_ifc + 255) / 256, 256, 0, L.stream>>>(P.ny_ifc, P.y_ptr, P.y_src, P.y_dst, P.ystage, L.y);

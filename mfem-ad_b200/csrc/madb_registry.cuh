@@ -75,6 +75,7 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
    }
    const bool whole = (mode == MODE_ENERGY || mode == MODE_COEF);
    const int nlaunch = whole ? 1 : L.ncolors;
+   if (L.ev0) { cudaEventRecord(L.ev0, L.stream); }
    for (int c = 0; c < nlaunch; c++)
    {
       a.begin = whole ? 0 : L.color_off[c];
@@ -92,6 +93,7 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
          default: return -1;
       }
    }
+   if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
    return (int)cudaGetLastError();
 }
 

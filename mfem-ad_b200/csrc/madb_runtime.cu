@@ -53,6 +53,7 @@ Integrator::~Integrator()
    cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_perm); cudaFree(d_cvalue); cudaFree(d_cgrad); cudaFree(d_energy); cudaFree(d_esum);
    cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
+   if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
    cudaFree(d_pdesc); cudaFree(d_yblob); cudaFree(d_vblob);
    cudaFree(d_ystage); cudaFree(d_vstage); cudaFree(d_yptr); cudaFree(d_ysrc); cudaFree(d_ydst);
    cudaFree(d_vptr); cudaFree(d_vsrc); cudaFree(d_vdst);
@@ -428,6 +429,8 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    for (size_t f = 0; f < I.fields.size(); f++) { L.b1d[f] = I.b1d[f].data(); L.g1d[f] = I.g1d[f].data(); }
    L.xq1d = I.xq1d.data(); L.w1d = I.w1d.data();
    L.patch = I.use_patches ? &I.pdev : nullptr;
+   L.ev0 = I.timing ? I.ev0 : nullptr;
+   L.ev1 = I.timing ? I.ev1 : nullptr;
 
    if (stage_in(I, x, N, &I.d_x, &L.x)) { return 2; }
    const double *v_orig = nullptr; // device copy of the caller's direction
@@ -826,6 +829,26 @@ extern "C"
       {
          *ncolors = (int)I->color_off.size() - 1;
       }
+      return 0;
+   }
+   int madb_integrator_set_timing(madb_integrator *I, int on)
+   {
+      CUDA_OK(cudaSetDevice(I->ctx->device));
+      if (on && !I->ev0)
+      {
+         CUDA_OK(cudaEventCreate(&I->ev0));
+         CUDA_OK(cudaEventCreate(&I->ev1));
+      }
+      I->timing = on != 0;
+      return 0;
+   }
+   int madb_integrator_last_kernel_ms(madb_integrator *I, double *ms)
+   {
+      if (!I->timing || !I->ev0) { set_error("madb_integrator_last_kernel_ms: timing is off (madb_integrator_set_timing)"); return 1; }
+      CUDA_OK(cudaEventSynchronize(I->ev1));
+      float t = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&t, I->ev0, I->ev1));
+      *ms = t;
       return 0;
    }
    int madb_integrator_patch_stats(madb_integrator *I, int64_t *out)
