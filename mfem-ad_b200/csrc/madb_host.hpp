@@ -43,11 +43,15 @@ struct PatchDesc
    int nruns;                 // runs of consecutive CSR positions covering [0,nint)
    int stage_off;             // vstage[stage_off + (s - nexc)] <- shared interface slots
    int vblob_off, vblob_bytes; // matrix-side maps: vblob + 16*vblob_off
-   int pad[1];
+   int nchunk, nover;         // chunk descriptors / explicit positions of the directly written slots [0,nexc)
+   int pad[3];
 };
 // Blob layouts (sections padded to 16 bytes, copied to shared memory with one bulk copy each):
 //   y blob: ysrc u16[nrows]  | yfold u32[nyfold] | ylist i32[nrow_int]
-//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | run_s i32[nruns+1] | run_g i32[nruns+1] | xg i32[nexc-nint]
+//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | chunk i32[4*nchunk] | over i32[nover]
+//           chunk c covers slots [32c, 32c+32) of the directly written slots [0,nexc):
+//           {g0, g1, split, -1}: lane < split -> CSR position g0 + lane, else g1 + (lane - split);
+//           {.., .., .., off >= 0}: explicit positions over[off + lane]
 // ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
 // fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
 // phase k adds the k-th further source, so every row / slot is summed in ascending element order.

@@ -329,7 +329,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
    bool ok = true;
    parallel_for_p(np, 64, [&](long b, long e)
    {
-      std::vector<int> vd, base, run_s, run_g, keyslot, xg;
+      std::vector<int> vd, base, run_s, run_g, keyslot, xg, gpos, chunks, over;
       std::vector<std::pair<int, int>> excl; // (CSR position, key index)
       std::vector<std::vector<unsigned short>> srcs;
       std::vector<unsigned short> first;
@@ -410,9 +410,46 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          BlobWriter W;
          W.section(first, first.size());
          W.section(fold, fold.size());
-         W.section(run_s, run_s.size());
-         W.section(run_g, run_g.size());
-         W.section(xg, xg.size());
+         // CSR position of every directly written slot, packed per chunk of 32 slots:
+         // {g0, g1, split, -1}: slots [0,split) of the chunk go to g0 + lane, the rest to g1 + (lane - split);
+         // {0, 0, 0, off}:      irregular chunk, explicit positions over[off + lane]
+         {
+            gpos.assign(D.nexc, 0);
+            for (int r = 0; r < D.nruns; r++)
+            {
+               for (int q = run_s[r]; q < run_s[r + 1]; q++) { gpos[q] = run_g[r] + (q - run_s[r]); }
+            }
+            for (int q = D.nint; q < D.nexc; q++) { gpos[q] = xg[q - D.nint]; }
+            const int nchunk = (D.nexc + 31) / 32;
+            chunks.assign((size_t)4 * nchunk, 0);
+            over.clear();
+            for (int c = 0; c < nchunk; c++)
+            {
+               const int b0 = c * 32, n = std::min(32, D.nexc - b0);
+               int split = n, breaks = 0;
+               for (int q = 1; q < n; q++)
+               {
+                  if (gpos[b0 + q] != gpos[b0 + q - 1] + 1) { breaks++; if (breaks == 1) { split = q; } }
+               }
+               int *d = &chunks[(size_t)4 * c];
+               if (breaks <= 1)
+               {
+                  d[0] = gpos[b0];
+                  d[1] = (split < n) ? gpos[b0 + split] : 0;
+                  d[2] = split;
+                  d[3] = -1;
+               }
+               else
+               {
+                  d[3] = (int)over.size();
+                  for (int q = 0; q < 32; q++) { over.push_back(q < n ? gpos[b0 + q] : 0); }
+               }
+            }
+            D.nchunk = nchunk;
+            D.nover = (int)over.size();
+         }
+         W.section(chunks, chunks.size());
+         W.section(over, over.size());
          blobs[p].swap(W.b);
       }
    });

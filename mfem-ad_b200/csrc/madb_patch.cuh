@@ -14,6 +14,8 @@
 //  without atomics and without order dependence.
 #pragma once
 #include "madb_kernels.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace madb
 {
@@ -48,6 +50,88 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                    : "r"(smem_u32(bar)), "r"(parity)
                    : "memory");
    }
+}
+
+/// barrier of the PATCH_PE threads working on one patch: the whole CTA (BAR = 0) or one warpgroup (named barrier BAR)
+template <int BAR> __device__ __forceinline__ void patch_bar()
+{
+   if constexpr (BAR == 0) { __syncthreads(); }
+   else { asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory"); }
+}
+
+/// Fold + gather + write-out of one staged patch by PATCH_PE threads (tid = 0..PATCH_PE-1).
+/// base: shared memory of the patch: element vectors at 0, element matrices at o_sa, y maps at o_yb, matrix maps at o_vb.
+template <int BAR>
+__device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
+                                            const bool wy, const bool wv, const int tid, double *__restrict__ y,
+                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage)
+{
+   constexpr int PE = PATCH_PE;
+#define MADB_SR(i) (*(double *)(base + 8 * (i)))
+#define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
+   const int nrows = D.nrows, nrow_int = D.nrow_int, nexc = D.nexc, nslots = D.nslots;
+   const int o_yfold = o_yb + patch_al16(2 * nrows);
+   const int o_vfold = o_vb + patch_al16(2 * nslots);
+   // ---- fold: add the further sources of every row / slot onto its first source, phase by phase -------
+   {
+      int ybase = 8, vbase = 8;
+      for (int ph = 0; ph < 8; ph++)
+      {
+         const int ny = wy ? *(const int *)(base + o_yfold + 4 * ph) : 0;
+         const int nv = wv ? *(const int *)(base + o_vfold + 4 * ph) : 0;
+         if (ny == 0 && nv == 0) { break; }
+         for (int i = tid; i < ny; i += PE)
+         {
+            const unsigned w = *(const unsigned *)(base + o_yfold + 4 * (ybase + i));
+            MADB_SR(w & 0xffffu) += MADB_SR(w >> 16);
+         }
+         for (int i = tid; i < nv; i += PE)
+         {
+            const unsigned w = *(const unsigned *)(base + o_vfold + 4 * (vbase + i));
+            MADB_SA(w & 0xffffu) += MADB_SA(w >> 16);
+         }
+         ybase += ny;
+         vbase += nv;
+         patch_bar<BAR>();
+      }
+   }
+   // ---- rows of the residual -----------------------------------------------------------
+   if (wy)
+   {
+      const int o_ylist = o_yfold + patch_al16(4 * D.nyfold);
+      for (int lr = tid; lr < nrows; lr += PE)
+      {
+         const double v = MADB_SR(*(const unsigned short *)(base + o_yb + 2 * lr));
+         if (lr < nrow_int) { y[*(const int *)(base + o_ylist + 4 * lr)] = v; }
+         else { ystage[D.ystage_off + (lr - nrow_int)] = v; }
+      }
+   }
+   // ---- CSR entries ------------------------------------------------------------------------
+   if (wv)
+   {
+      const int o_chunk = o_vfold + patch_al16(4 * D.nvfold);
+      const int o_over = o_chunk + patch_al16(16 * D.nchunk);
+      const unsigned short *vsrc = (const unsigned short *)(base + o_vb);
+      const int4 *chunks = (const int4 *)(base + o_chunk);
+      const int *over = (const int *)(base + o_over);
+      const int lane = tid & 31, nchunk = D.nchunk;
+      // directly written slots: CSR positions from the chunk descriptors (consecutive lanes -> consecutive positions)
+#pragma unroll 4
+      for (int c = tid >> 5; c < nchunk; c += PE / 32)
+      {
+         const int4 d = chunks[c];
+         const int s = c * 32 + lane;
+         if (s < nexc)
+         {
+            const int g = (d.w >= 0) ? over[d.w + lane] : ((lane < d.z) ? d.x + lane : d.y + (lane - d.z));
+            vals[g] = MADB_SA(vsrc[s]);
+         }
+      }
+      double *stage = vstage + D.stage_off - nexc;
+      for (int s = nexc + tid; s < nslots; s += PE) { stage[s] = MADB_SA(vsrc[s]); }
+   }
+#undef MADB_SR
+#undef MADB_SA
 }
 
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
@@ -110,90 +194,113 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
    __syncthreads();
    mbar_wait(&mbar, 0);
 
-   // ---- fold: add the further sources of every row / slot onto its first source, phase by phase -------
-   const int o_yfold = o_yb + patch_al16(2 * D.nrows);
-   const int o_vfold = o_vb + patch_al16(2 * D.nslots);
-   {
-      int ybase = 8, vbase = 8;
-      for (int ph = 0; ph < 8; ph++)
-      {
-         const int ny = wy ? *(const int *)(smraw + o_yfold + 4 * ph) : 0;
-         const int nv = wv ? *(const int *)(smraw + o_vfold + 4 * ph) : 0;
-         if (ny == 0 && nv == 0) { break; }
-         if constexpr (HAS_Y)
-         {
-            for (int i = tid; i < ny; i += PE)
-            {
-               const unsigned w = *(const unsigned *)(smraw + o_yfold + 4 * (ybase + i));
-               MADB_SR(w & 0xffffu) += MADB_SR(w >> 16);
-            }
-         }
-         if constexpr (HAS_V)
-         {
-            for (int i = tid; i < nv; i += PE)
-            {
-               const unsigned w = *(const unsigned *)(smraw + o_vfold + 4 * (vbase + i));
-               MADB_SA(w & 0xffffu) += MADB_SA(w >> 16);
-            }
-         }
-         ybase += ny;
-         vbase += nv;
-         __syncthreads();
-      }
-   }
-
-   // ---- rows of the residual -----------------------------------------------------------
-   if constexpr (HAS_Y)
-   {
-      if (wy)
-      {
-         const int o_ylist = o_yfold + patch_al16(4 * D.nyfold);
-         for (int lr = tid; lr < D.nrows; lr += PE)
-         {
-            const double v = MADB_SR(*(const unsigned short *)(smraw + o_yb + 2 * lr));
-            if (lr < D.nrow_int) { a.y[*(const int *)(smraw + o_ylist + 4 * lr)] = v; }
-            else { P.ystage[D.ystage_off + (lr - D.nrow_int)] = v; }
-         }
-      }
-   }
-   // ---- CSR entries ------------------------------------------------------------------------
-   if constexpr (HAS_V)
-   {
-      if (wv)
-      {
-         const int o_runs = o_vfold + patch_al16(4 * D.nvfold);
-         const int o_rung = o_runs + patch_al16(4 * (D.nruns + 1));
-         const int o_xg = o_rung + patch_al16(4 * (D.nruns + 1));
-#define MADB_RUN_S(r) (*(const int *)(smraw + o_runs + 4 * (r)))
-#define MADB_RUN_G(r) (*(const int *)(smraw + o_rung + 4 * (r)))
-         // interior slots are numbered in CSR order: slot s of run r goes to position run_g[r] + (s - run_s[r])
-         int rn = 0, rs = MADB_RUN_S(0), re = (D.nruns > 0) ? MADB_RUN_S(1) : 0, rg = MADB_RUN_G(0);
-         const int nint = D.nint, nexc = D.nexc, nslots = D.nslots;
-#pragma unroll 4
-         for (int s = tid; s < nint; s += PE)
-         {
-            const double v = MADB_SA(*(const unsigned short *)(smraw + o_vb + 2 * s));
-            while (s >= re)
-            {
-               rn++;
-               rs = re;
-               re = MADB_RUN_S(rn + 1);
-               rg = MADB_RUN_G(rn);
-            }
-            a.vals[rg + (s - rs)] = v;
-         }
-         for (int s = nint + tid; s < nexc; s += PE)
-         {
-            a.vals[*(const int *)(smraw + o_xg + 4 * (s - nint))] = MADB_SA(*(const unsigned short *)(smraw + o_vb + 2 * s));
-         }
-         double *stage = P.vstage + D.stage_off - nexc;
-         for (int s = nexc + tid; s < nslots; s += PE) { stage[s] = MADB_SA(*(const unsigned short *)(smraw + o_vb + 2 * s)); }
-#undef MADB_RUN_S
-#undef MADB_RUN_G
-      }
-   }
+   patch_drain<0>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
 #undef MADB_SR
 #undef MADB_SA
+}
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised persistent variant (fused residual + Jacobian): one CTA per SM, four warpgroups.
+//   warpgroups 2,3 (216 registers/thread after setmaxnreg): element computation, patch after patch;
+//                  each stages its element vectors / matrices in its own shared-memory buffer
+//   warpgroups 0,1 (40 registers/thread): writer w folds, gathers and writes the rows of the patches
+//                  finished by compute warpgroup w while that one is already working on its next
+//                  patch; it also prefetches the gather maps of the next patch with cp.async.bulk.
+// Hand-off through mbarriers: full[w] (compute -> writer), empty[w] (writer -> compute),
+// blob[w] (bulk-copy completion).  Patches are dealt round-robin: p = (it * gridDim + cta) * 2 + w.
+// ---------------------------------------------------------------------------------------------
+template <class Func, class Cfg, bool UNROLLQ>
+__global__ void __launch_bounds__(4 * PATCH_PE, 1) k_patch_ws(const __grid_constant__ AsmArgs<Func, Cfg> a,
+                                                              const __grid_constant__ PatchDev P)
+{
+   constexpr int MODE = MODE_RES | MODE_JAC;
+   constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = PATCH_PE, LD = PATCH_LD;
+   constexpr int SR_BYTES = patch_al16(NVD * LD * 8), SA_BYTES = patch_al16(NSYM * LD * 8);
+   extern __shared__ __align__(16) unsigned char smraw[];
+   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blob[2];
+   __shared__ PatchDesc Dd[2];
+   const int wg = threadIdx.x >> 7, tid = threadIdx.x & (PE - 1);
+   const int w = wg & 1;
+   const bool wy = a.write_y != 0;
+   const int wg_bytes = SR_BYTES + SA_BYTES + P.max_yblob + P.max_vblob;
+   unsigned char *base = smraw + (size_t)w * wg_bytes;
+   if (threadIdx.x == 0)
+   {
+      for (int k = 0; k < 2; k++)
+      {
+         mbar_init(&bar_full[k], PE);
+         mbar_init(&bar_empty[k], PE);
+         mbar_init(&bar_blob[k], 1);
+      }
+   }
+   __syncthreads();
+
+   if (wg >= 2)
+   {
+      // ================= compute warpgroups =================
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+      for (int it = 0;; it++)
+      {
+         const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+         if (p >= P.npatch) { break; }
+         const int t = p * PE + tid;
+         const bool valid = t < a.end;
+         double r[NVD], A[NSYM], energy;
+         if (valid) { element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy); }
+         mbar_wait(&bar_empty[w], (it & 1) ^ 1); // the writer has drained the previous patch of this buffer
+         if (valid)
+         {
+#pragma unroll
+            for (int i = 0; i < NVD; i++) { *(double *)(base + 8 * (i * LD + tid)) = r[i]; }
+#pragma unroll
+            for (int k = 0; k < NSYM; k++) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = A[k]; }
+         }
+         mbar_arrive(&bar_full[w]);
+      }
+   }
+   else
+   {
+      // ================= writer warpgroups =================
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      auto prefetch = [&](int p)
+      {
+         // one thread: descriptor to shared memory, then the bulk copies of the patch's maps
+         const PatchDesc *src = P.desc + p;
+         for (int k = 0; k < (int)(sizeof(PatchDesc) / sizeof(int)); k++) { ((int *)&Dd[w])[k] = __ldg((const int *)src + k); }
+         unsigned char *mb = base + SR_BYTES + SA_BYTES;
+         const int yb = wy ? Dd[w].yblob_bytes : 0, vb = Dd[w].vblob_bytes;
+         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+         mbar_expect_tx(&bar_blob[w], (unsigned)(yb + vb));
+         if (yb) { bulk_g2s(mb, P.yblob + (size_t)Dd[w].yblob_off * 16, yb, &bar_blob[w]); }
+         if (vb) { bulk_g2s(mb + P.max_yblob, P.vblob + (size_t)Dd[w].vblob_off * 16, vb, &bar_blob[w]); }
+      };
+      {
+         const int p0 = (int)blockIdx.x * 2 + w;
+         if (tid == 0 && p0 < P.npatch) { prefetch(p0); }
+      }
+      const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_vb = o_yb + P.max_yblob;
+      for (int it = 0;; it++)
+      {
+         const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+         if (p >= P.npatch) { break; }
+         mbar_wait(&bar_blob[w], it & 1);
+         const PatchDesc D = Dd[w];
+         mbar_wait(&bar_full[w], it & 1);
+         if (w == 0) { patch_drain<1>(base, o_sa, o_yb, o_vb, D, wy, true, tid, a.y, a.vals, P.ystage, P.vstage); }
+         else { patch_drain<2>(base, o_sa, o_yb, o_vb, D, wy, true, tid, a.y, a.vals, P.ystage, P.vstage); }
+         mbar_arrive(&bar_empty[w]);
+         // all threads of this writer are done with the maps: fetch those of the next patch
+         if (w == 0) { patch_bar<1>(); }
+         else { patch_bar<2>(); }
+         const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+         if (tid == 0 && pn < P.npatch) { prefetch(pn); }
+      }
+   }
 }
 
 // out[dst[i]] = sum of the staged partials of entry i, in ascending patch order
@@ -225,7 +332,36 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       smem_set = smem_bytes;
    }
    if (L.ev0) { cudaEventRecord(L.ev0, L.stream); }
-   kern<<<P.npatch, PATCH_PE, smem_bytes, L.stream>>>(a, P);
+   bool done = false;
+   if constexpr (MODE == (MODE_RES | MODE_JAC))
+   {
+      static const bool use_ws = getenv("MADB_PATCH_WS") ? atoi(getenv("MADB_PATCH_WS")) != 0 : true;
+      if (wv && use_ws)
+      {
+         static int ws_smem_set = 0, nsm = 0;
+         auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
+         const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yblob + P.max_vblob) + 16;
+         if (nsm == 0)
+         {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+         }
+         if (ws_bytes <= 220 * 1024)
+         {
+            if (ws_bytes > ws_smem_set)
+            {
+               const cudaError_t e = cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_bytes);
+               if (e != cudaSuccess) { return (int)e; }
+               ws_smem_set = ws_bytes;
+            }
+            const int grid = std::min(nsm, (P.npatch + 1) / 2);
+            kws<<<grid, 4 * PATCH_PE, ws_bytes, L.stream>>>(a, P);
+            done = true;
+         }
+      }
+   }
+   if (!done) { kern<<<P.npatch, PATCH_PE, smem_bytes, L.stream>>>(a, P); }
    if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
    if (wy && P.ny_ifc > 0)
    {
