@@ -43,21 +43,23 @@ struct PatchDesc
    int nruns;                 // runs of consecutive CSR positions covering [0,nint)
    int stage_off;             // vstage[stage_off + (s - nexc)] <- shared interface slots
    int vblob_off, vblob_bytes; // matrix-side maps: vblob + 16*vblob_off
-   int nchunk, nover;         // chunk descriptors / explicit positions of the directly written slots [0,nexc)
+   int nchunk, nirr;          // chunk descriptors / irregular chunks of the directly written slots [0,nexc)
    int pad[3];
 };
 // Blob layouts (sections padded to 16 bytes, copied to shared memory with one bulk copy each):
 //   y blob: ysrc u16[nrows]  | yfold u32[nyfold] | ylist i32[nrow_int]
-//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | chunk i32[4*nchunk] | over i32[nover]
+//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | chunk i32[4*nchunk] | irr u16[nirr] | over i32[32*nirr]
 //           chunk c covers slots [32c, 32c+32) of the directly written slots [0,nexc):
-//           {g0, g1, split, -1}: lane < split -> CSR position g0 + lane, else g1 + (lane - split);
-//           {.., .., .., off >= 0}: explicit positions over[off + lane]
+//           {g0, g1 - split, split, -1}: lane < split -> CSR position g0 + lane, else g1 + (lane - split);
+//           {.., .., .., k >= 0}: irregular, chunk irr[k]: explicit positions over[32 k + lane]
 // ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
 // fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
 // phase k adds the k-th further source, so every row / slot is summed in ascending element order.
 struct PatchDev
 {
    int npatch;
+   unsigned long long *dbg;  // MADB_PATCH_DEBUG & 8: cycle counters of the writer warpgroup (diagnostics)
+   int debug;                // MADB_PATCH_DEBUG: 1 = skip the CSR write-out, 2 = skip the element computation (timing experiments)
    int max_yblob, max_vblob; // bytes, shared-memory sizing
    const PatchDesc *desc;
    const unsigned char *yblob, *vblob;
@@ -213,6 +215,7 @@ struct Integrator
    bool have_patch_vals = false;
    PatchDev pdev {};
    PatchDesc *d_pdesc = nullptr;
+   unsigned long long *d_dbg = nullptr;
    unsigned char *d_yblob = nullptr, *d_vblob = nullptr;
    double *d_ystage = nullptr, *d_vstage = nullptr;
    int *d_yptr = nullptr, *d_ysrc = nullptr, *d_ydst = nullptr, *d_vptr = nullptr, *d_vsrc = nullptr, *d_vdst = nullptr;

@@ -464,10 +464,12 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
 }
 
 /// Sum-factorised gather + quadrature loop (madb_sf2d.cuh) for 2-D scalar H1 fields with ADEval::GRAD.
-template <class Func, class Cfg, int MODE>
+/// The element vector is returned in r; the entries of the upper triangle of the element matrix are handed
+/// to sink(k, value), k = symidx(I, J), one by one at the end (they never all live in registers: the
+/// pulled-back Hessians of the NQ x NQ points are kept instead, 3 doubles per point).
+template <class Func, class Cfg, int MODE, class Sink>
 __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a, const int t,
-                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
-                                                     double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1])
+                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink)
 {
    constexpr int ND = Cfg::template field<0>::ND1D, NQ = Cfg::NQ1D, NVD = Cfg::NVD;
    constexpr bool RES = (MODE & MODE_RES) != 0, JAC = (MODE & MODE_JAC) != 0, ACT = (MODE & MODE_ACT) != 0;
@@ -544,18 +546,13 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
 #pragma unroll
       for (int i = 0; i < NVD; i++) { r[i] = 0.0; }
    }
-   if constexpr (JAC)
-   {
-#pragma unroll
-      for (int i = 0; i < Cfg::NSYM; i++) { A[i] = 0.0; }
-   }
+   ZD H00[JAC ? NQ : 1][JAC ? NQ : 1], H01[JAC ? NQ : 1][JAC ? NQ : 1], H11[JAC ? NQ : 1][JAC ? NQ : 1]; // [q2][q1]
 
 #pragma unroll
    for (int q2 = 0; q2 < NQ; q2++)
    {
       const double J00 = fma(dd[0], T.xq[q2], a0[0]), J10 = fma(dd[1], T.xq[q2], a0[1]);
       ZD gh0[NQ], gh1[NQ];                    // reference-space gradient (RES) or H^ v^ (ACT), weighted
-      ZD H00[JAC ? NQ : 1], H01[JAC ? NQ : 1], H11[JAC ? NQ : 1];
 #pragma unroll
       for (int q1 = 0; q1 < NQ; q1++)
       {
@@ -594,9 +591,9 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
          }
          if constexpr (JAC)
          {
-            H00[q1] = h00;
-            H01[q1] = h01;
-            H11[q1] = h11;
+            H00[q2][q1] = h00;
+            H01[q2][q1] = h01;
+            H11[q2][q1] = h11;
          }
          if constexpr (RES)
          {
@@ -648,86 +645,69 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
          }
       }
 
-      // ---- element matrix (upper triangle), one H^ component at a time to keep the live set small ----
-      if constexpr (JAC)
+   }
+
+   // ---- element matrix: for every pair (i1 <= j1) of 1-D x-indices contract over q1, then emit the (i2, j2) block ----
+   if constexpr (JAC)
+   {
+#pragma unroll
+      for (int j1 = 0; j1 < ND; j1++)
       {
+#pragma unroll
+         for (int i1 = 0; i1 <= j1; i1++)
          {
-            ZD T00[ND][ND];
+            ZD T00[NQ], T01[NQ], T10[NQ], T11[NQ]; // per q2: sum_q1 (1-D products)[q1][i1][j1] H^ab(q2,q1)
 #pragma unroll
-            for (int i1 = 0; i1 < ND; i1++)
+            for (int q2 = 0; q2 < NQ; q2++)
             {
+               ZD s00 {0.0, true}, s01 {0.0, true}, s10 {0.0, true}, s11 {0.0, true};
 #pragma unroll
-               for (int j1 = i1; j1 < ND; j1++)
+               for (int q1 = 0; q1 < NQ; q1++)
                {
-                  ZD s {0.0, true};
-#pragma unroll
-                  for (int q1 = 0; q1 < NQ; q1++) { s = zfmac(H00[q1], T.GG[q1][i1][j1], s); }
-                  T00[i1][j1] = s;
-                  T00[j1][i1] = s;
+                  s00 = zfmac(H00[q2][q1], T.GG[q1][i1][j1], s00);
+                  s01 = zfmac(H01[q2][q1], T.BG[q1][j1][i1], s01); // G[q1][i1] B[q1][j1]
+                  if (i1 != j1) { s10 = zfmac(H01[q2][q1], T.BG[q1][i1][j1], s10); } // G[q1][j1] B[q1][i1]
+                  s11 = zfmac(H11[q2][q1], T.BB[q1][i1][j1], s11);
                }
+               T00[q2] = s00;
+               T01[q2] = s01;
+               T10[q2] = (i1 != j1) ? s10 : s01;
+               T11[q2] = s11;
             }
 #pragma unroll
-            for (int J = 0; J < NVD; J++)
+            for (int i2 = 0; i2 < ND; i2++)
             {
 #pragma unroll
-               for (int I = 0; I <= J; I++)
+               for (int j2 = 0; j2 < ND; j2++)
                {
-                  zacc(A[symidx(I, J)], T00[I % ND][J % ND], T.BB[q2][I / ND][J / ND]);
-               }
-            }
-         }
-         {
-            ZD T01[ND][ND]; // sum_q1 G[q1][i1] B[q1][j1] H^01
+                  if (i1 == j1 && i2 > j2) { continue; }
+                  // entry (I, J), I = (i2, i1), J = (j2, j1)
+                  double v = 0.0;
 #pragma unroll
-            for (int i1 = 0; i1 < ND; i1++)
-            {
-#pragma unroll
-               for (int j1 = 0; j1 < ND; j1++)
-               {
-                  ZD s {0.0, true};
-#pragma unroll
-                  for (int q1 = 0; q1 < NQ; q1++) { s = zfmac(H01[q1], T.BG[q1][j1][i1], s); }
-                  T01[i1][j1] = s;
-               }
-            }
-#pragma unroll
-            for (int J = 0; J < NVD; J++)
-            {
-#pragma unroll
-               for (int I = 0; I <= J; I++)
-               {
-                  zacc(A[symidx(I, J)], T01[I % ND][J % ND], T.BG[q2][I / ND][J / ND]);
-                  zacc(A[symidx(I, J)], T01[J % ND][I % ND], T.BG[q2][J / ND][I / ND]);
-               }
-            }
-         }
-         {
-            ZD T11[ND][ND];
-#pragma unroll
-            for (int i1 = 0; i1 < ND; i1++)
-            {
-#pragma unroll
-               for (int j1 = i1; j1 < ND; j1++)
-               {
-                  ZD s {0.0, true};
-#pragma unroll
-                  for (int q1 = 0; q1 < NQ; q1++) { s = zfmac(H11[q1], T.BB[q1][i1][j1], s); }
-                  T11[i1][j1] = s;
-                  T11[j1][i1] = s;
-               }
-            }
-#pragma unroll
-            for (int J = 0; J < NVD; J++)
-            {
-#pragma unroll
-               for (int I = 0; I <= J; I++)
-               {
-                  zacc(A[symidx(I, J)], T11[I % ND][J % ND], T.GG[q2][I / ND][J / ND]);
+                  for (int q2 = 0; q2 < NQ; q2++)
+                  {
+                     zacc(v, T00[q2], T.BB[q2][i2][j2]);
+                     zacc(v, T01[q2], T.BG[q2][i2][j2]);
+                     zacc(v, T10[q2], T.BG[q2][j2][i2]);
+                     zacc(v, T11[q2], T.GG[q2][i2][j2]);
+                  }
+                  const int I = i2 * ND + i1, J = j2 * ND + j1;
+                  sink(symidx(I, J), v);
                }
             }
          }
       }
    }
+}
+
+/// does <functional, configuration, mode> take the sum-factorised 2-D path?
+template <class Func, class Cfg, int MODE> constexpr bool use_sf2d()
+{
+#ifdef MADB_NO_SF2D
+   return false;
+#else
+   return sf2d_cfg<Cfg>() && Func::N_QPRM == 0 && (MODE == MODE_RES || MODE == (MODE_RES | MODE_JAC) || MODE == MODE_ACT);
+#endif
 }
 
 /// Gather + quadrature loop of sorted element t: element vector r, upper triangle of the element matrix A.
@@ -737,14 +717,12 @@ __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, con
                                                 double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1], double &energy)
 {
    constexpr int DIM = Cfg::DIM, NVD = Cfg::NVD;
-#ifndef MADB_NO_SF2D
-   if constexpr (sf2d_cfg<Cfg>() && Func::N_QPRM == 0 && (MODE == MODE_RES || MODE == (MODE_RES | MODE_JAC) || MODE == MODE_ACT))
+   if constexpr (use_sf2d<Func, Cfg, MODE>())
    {
       energy = 0.0;
-      element_compute_sf2d<Func, Cfg, MODE>(a, t, r, A);
+      element_compute_sf2d<Func, Cfg, MODE>(a, t, r, [&](int k, double v) { if constexpr ((MODE & MODE_JAC) != 0) { A[k] = v; } });
       return;
    }
-#endif
 
    // ---- gather: vertices, dofs of all fields ---------------------------------------
    double X[Cfg::NGN][DIM];

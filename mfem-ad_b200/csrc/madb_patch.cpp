@@ -330,6 +330,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
    parallel_for_p(np, 64, [&](long b, long e)
    {
       std::vector<int> vd, base, run_s, run_g, keyslot, xg, gpos, chunks, over;
+      std::vector<unsigned short> irr;
       std::vector<std::pair<int, int>> excl; // (CSR position, key index)
       std::vector<std::vector<unsigned short>> srcs;
       std::vector<unsigned short> first;
@@ -411,8 +412,8 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          W.section(first, first.size());
          W.section(fold, fold.size());
          // CSR position of every directly written slot, packed per chunk of 32 slots:
-         // {g0, g1, split, -1}: slots [0,split) of the chunk go to g0 + lane, the rest to g1 + (lane - split);
-         // {0, 0, 0, off}:      irregular chunk, explicit positions over[off + lane]
+         // {g0, g1 - split, split, -1}: slots [0,split) of the chunk go to g0 + lane, the rest to g1 + (lane - split);
+         // {0, 0, 0, k >= 0}:   irregular chunk, the k-th of the list irr[]: explicit positions over[32 k + lane]
          {
             gpos.assign(D.nexc, 0);
             for (int r = 0; r < D.nruns; r++)
@@ -423,6 +424,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
             const int nchunk = (D.nexc + 31) / 32;
             chunks.assign((size_t)4 * nchunk, 0);
             over.clear();
+            irr.clear();
             for (int c = 0; c < nchunk; c++)
             {
                const int b0 = c * 32, n = std::min(32, D.nexc - b0);
@@ -435,20 +437,22 @@ bool patch_build_v(Integrator &I, PatchHost &H)
                if (breaks <= 1)
                {
                   d[0] = gpos[b0];
-                  d[1] = (split < n) ? gpos[b0 + split] : 0;
+                  d[1] = (split < n) ? gpos[b0 + split] - split : 0;
                   d[2] = split;
                   d[3] = -1;
                }
                else
                {
-                  d[3] = (int)over.size();
+                  d[3] = (int)irr.size();
+                  irr.push_back((unsigned short)c);
                   for (int q = 0; q < 32; q++) { over.push_back(q < n ? gpos[b0 + q] : 0); }
                }
             }
             D.nchunk = nchunk;
-            D.nover = (int)over.size();
+            D.nirr = (int)irr.size();
          }
          W.section(chunks, chunks.size());
+         W.section(irr, irr.size());
          W.section(over, over.size());
          blobs[p].swap(W.b);
       }

@@ -61,18 +61,24 @@ template <int BAR> __device__ __forceinline__ void patch_bar()
 
 /// Fold + gather + write-out of one staged patch by PATCH_PE threads (tid = 0..PATCH_PE-1).
 /// base: shared memory of the patch: element vectors at 0, element matrices at o_sa, y maps at o_yb, matrix maps at o_vb.
-template <int BAR>
+/// Every loop is written in batches of U independent iterations (all index loads, then all value loads, then
+/// all stores): the chains are shared-memory-latency bound, and only a few warps work on a patch.
+template <int BAR, int U>
 __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
                                             const bool wy, const bool wv, const int tid, double *__restrict__ y,
-                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage)
+                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage,
+                                            long long *tm = nullptr)
 {
    constexpr int PE = PATCH_PE;
+   long long t0 = tm ? clock64() : 0;
+#define MADB_TICK(k) if (tm) { const long long t1 = clock64(); tm[k] += t1 - t0; t0 = t1; }
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
 #define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
    const int nrows = D.nrows, nrow_int = D.nrow_int, nexc = D.nexc, nslots = D.nslots;
    const int o_yfold = o_yb + patch_al16(2 * nrows);
    const int o_vfold = o_vb + patch_al16(2 * nslots);
    // ---- fold: add the further sources of every row / slot onto its first source, phase by phase -------
+   // (inside one phase every location occurs at most once, as a destination or as a source)
    {
       int ybase = 8, vbase = 8;
       for (int ph = 0; ph < 8; ph++)
@@ -85,16 +91,31 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
             const unsigned w = *(const unsigned *)(base + o_yfold + 4 * (ybase + i));
             MADB_SR(w & 0xffffu) += MADB_SR(w >> 16);
          }
-         for (int i = tid; i < nv; i += PE)
+         for (int i0 = tid; i0 < nv; i0 += PE * U)
          {
-            const unsigned w = *(const unsigned *)(base + o_vfold + 4 * (vbase + i));
-            MADB_SA(w & 0xffffu) += MADB_SA(w >> 16);
+            unsigned w[U];
+            double d0[U], d1[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+               const int i = i0 + u * PE;
+               w[u] = *(const unsigned *)(base + o_vfold + 4 * (vbase + (i < nv ? i : i0)));
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+               d0[u] = MADB_SA(w[u] & 0xffffu);
+               d1[u] = MADB_SA(w[u] >> 16);
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) { if (i0 + u * PE < nv) { MADB_SA(w[u] & 0xffffu) = d0[u] + d1[u]; } }
          }
          ybase += ny;
          vbase += nv;
          patch_bar<BAR>();
       }
    }
+   MADB_TICK(2)
    // ---- rows of the residual -----------------------------------------------------------
    if (wy)
    {
@@ -106,30 +127,53 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
          else { ystage[D.ystage_off + (lr - nrow_int)] = v; }
       }
    }
+   MADB_TICK(3)
    // ---- CSR entries ------------------------------------------------------------------------
    if (wv)
    {
       const int o_chunk = o_vfold + patch_al16(4 * D.nvfold);
-      const int o_over = o_chunk + patch_al16(16 * D.nchunk);
+      const int o_irr = o_chunk + patch_al16(16 * D.nchunk);
+      const int o_over = o_irr + patch_al16(2 * D.nirr);
       const unsigned short *vsrc = (const unsigned short *)(base + o_vb);
       const int4 *chunks = (const int4 *)(base + o_chunk);
+      const unsigned short *irr = (const unsigned short *)(base + o_irr);
       const int *over = (const int *)(base + o_over);
-      const int lane = tid & 31, nchunk = D.nchunk;
-      // directly written slots: CSR positions from the chunk descriptors (consecutive lanes -> consecutive positions)
-#pragma unroll 4
-      for (int c = tid >> 5; c < nchunk; c += PE / 32)
+      const int lane = tid & 31, nchunk = D.nchunk, nirr = D.nirr;
+      constexpr int NW = PE / 32;
+      // directly written slots: CSR positions from the chunk descriptors {g0, g1 - split, split, flag}
+      // (consecutive lanes -> consecutive positions)
+      for (int c0 = tid >> 5; c0 < nchunk; c0 += NW * U)
       {
-         const int4 d = chunks[c];
-         const int s = c * 32 + lane;
-         if (s < nexc)
+         int g[U];
+         unsigned idx[U];
+         double v[U];
+#pragma unroll
+         for (int u = 0; u < U; u++)
          {
-            const int g = (d.w >= 0) ? over[d.w + lane] : ((lane < d.z) ? d.x + lane : d.y + (lane - d.z));
-            vals[g] = MADB_SA(vsrc[s]);
+            const int c = c0 + u * NW, cc = (c < nchunk) ? c : c0;
+            const int4 d = chunks[cc];
+            const int s = cc * 32 + lane;
+            idx[u] = vsrc[(s < nexc) ? s : nexc - 1];
+            const int gg = ((lane < d.z) ? d.x : d.y) + lane;
+            g[u] = (c < nchunk && d.w < 0 && s < nexc) ? gg : -1;
          }
+#pragma unroll
+         for (int u = 0; u < U; u++) { v[u] = MADB_SA(idx[u]); }
+#pragma unroll
+         for (int u = 0; u < U; u++) { if (g[u] >= 0) { vals[g[u]] = v[u]; } }
+      }
+      MADB_TICK(4)
+      // irregular chunks: explicit positions
+      for (int k = tid >> 5; k < nirr; k += NW)
+      {
+         const int s = irr[k] * 32 + lane;
+         if (s < nexc) { vals[over[32 * k + lane]] = MADB_SA(vsrc[s]); }
       }
       double *stage = vstage + D.stage_off - nexc;
       for (int s = nexc + tid; s < nslots; s += PE) { stage[s] = MADB_SA(vsrc[s]); }
    }
+   MADB_TICK(5)
+#undef MADB_TICK
 #undef MADB_SR
 #undef MADB_SA
 }
@@ -166,21 +210,19 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
 
    const int t = p * PE + tid;
    const bool valid = tid < D.ne;
+   if (valid)
    {
       double r[HAS_Y ? NVD : 1];
-      double A[HAS_V ? NSYM : 1];
-      double energy;
-      if (valid)
+      if constexpr (use_sf2d<Func, Cfg, MODE>() && HAS_V)
       {
+         // matrix entries stream from the computation straight into the staging buffer
+         element_compute_sf2d<Func, Cfg, MODE>(a, t, r, [&](int k, double v) { if (wv) { MADB_SA(k * LD + tid) = v; } });
+      }
+      else
+      {
+         double A[HAS_V ? NSYM : 1];
+         double energy;
          element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy);
-         if constexpr (HAS_Y)
-         {
-            if (wy)
-            {
-#pragma unroll
-               for (int i = 0; i < NVD; i++) { MADB_SR(i * LD + tid) = r[i]; }
-            }
-         }
          if constexpr (HAS_V)
          {
             if (wv)
@@ -190,11 +232,19 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
             }
          }
       }
+      if constexpr (HAS_Y)
+      {
+         if (wy)
+         {
+#pragma unroll
+            for (int i = 0; i < NVD; i++) { MADB_SR(i * LD + tid) = r[i]; }
+         }
+      }
    }
    __syncthreads();
    mbar_wait(&mbar, 0);
 
-   patch_drain<0>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
+   patch_drain<0, 4>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
 #undef MADB_SR
 #undef MADB_SA
 }
@@ -205,17 +255,17 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised persistent variant (fused residual + Jacobian): one CTA per SM, four warpgroups.
-//   warpgroups 2,3 (216 registers/thread after setmaxnreg): element computation, patch after patch;
-//                  each stages its element vectors / matrices in its own shared-memory buffer
-//   warpgroups 0,1 (40 registers/thread): writer w folds, gathers and writes the rows of the patches
-//                  finished by compute warpgroup w while that one is already working on its next
-//                  patch; it also prefetches the gather maps of the next patch with cp.async.bulk.
+// Warp-specialised persistent variant (fused residual + Jacobian): one CTA per SM, three warpgroups.
+//   warpgroups 1,2 (224 registers/thread after setmaxnreg): element computation, patch after patch;
+//                  each streams its element vectors / matrices into its own shared-memory buffer
+//   warpgroup 0    (64 registers/thread): folds, gathers and writes the rows of the finished patches
+//                  of both compute warpgroups while those are already working on their next patch;
+//                  it also prefetches the gather maps of the next patch with cp.async.bulk.
 // Hand-off through mbarriers: full[w] (compute -> writer), empty[w] (writer -> compute),
 // blob[w] (bulk-copy completion).  Patches are dealt round-robin: p = (it * gridDim + cta) * 2 + w.
 // ---------------------------------------------------------------------------------------------
 template <class Func, class Cfg, bool UNROLLQ>
-__global__ void __launch_bounds__(4 * PATCH_PE, 1) k_patch_ws(const __grid_constant__ AsmArgs<Func, Cfg> a,
+__global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_constant__ AsmArgs<Func, Cfg> a,
                                                               const __grid_constant__ PatchDev P)
 {
    constexpr int MODE = MODE_RES | MODE_JAC;
@@ -225,10 +275,8 @@ __global__ void __launch_bounds__(4 * PATCH_PE, 1) k_patch_ws(const __grid_const
    __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blob[2];
    __shared__ PatchDesc Dd[2];
    const int wg = threadIdx.x >> 7, tid = threadIdx.x & (PE - 1);
-   const int w = wg & 1;
    const bool wy = a.write_y != 0;
    const int wg_bytes = SR_BYTES + SA_BYTES + P.max_yblob + P.max_vblob;
-   unsigned char *base = smraw + (size_t)w * wg_bytes;
    if (threadIdx.x == 0)
    {
       for (int k = 0; k < 2; k++)
@@ -240,66 +288,108 @@ __global__ void __launch_bounds__(4 * PATCH_PE, 1) k_patch_ws(const __grid_const
    }
    __syncthreads();
 
-   if (wg >= 2)
+   if (wg != 0)
    {
       // ================= compute warpgroups =================
       asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+      const int w = wg - 1;
+      unsigned char *base = smraw + (size_t)w * wg_bytes;
       for (int it = 0;; it++)
       {
          const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
          if (p >= P.npatch) { break; }
          const int t = p * PE + tid;
-         const bool valid = t < a.end;
-         double r[NVD], A[NSYM], energy;
-         if (valid) { element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy); }
-         mbar_wait(&bar_empty[w], (it & 1) ^ 1); // the writer has drained the previous patch of this buffer
+         const bool valid = t < a.end && !(P.debug & 2);
+         double r[NVD];
+         const unsigned par = (it & 1) ^ 1; // parity of "the writer has drained the previous patch of this buffer"
+         if constexpr (use_sf2d<Func, Cfg, MODE>())
+         {
+            bool waited = false;
+            if (valid)
+            {
+               element_compute_sf2d<Func, Cfg, MODE>(a, t, r, [&](int k, double v)
+               {
+                  if (!waited) { mbar_wait(&bar_empty[w], par); waited = true; }
+                  *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = v;
+               });
+            }
+            if (!waited) { mbar_wait(&bar_empty[w], par); }
+         }
+         else
+         {
+            double A[NSYM], energy;
+            if (valid) { element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy); }
+            mbar_wait(&bar_empty[w], par);
+            if (valid)
+            {
+#pragma unroll
+               for (int k = 0; k < NSYM; k++) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = A[k]; }
+            }
+         }
          if (valid)
          {
 #pragma unroll
             for (int i = 0; i < NVD; i++) { *(double *)(base + 8 * (i * LD + tid)) = r[i]; }
-#pragma unroll
-            for (int k = 0; k < NSYM; k++) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = A[k]; }
          }
          mbar_arrive(&bar_full[w]);
       }
    }
    else
    {
-      // ================= writer warpgroups =================
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-      auto prefetch = [&](int p)
+      // ================= writer warpgroup =================
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      auto prefetch = [&](int w, int p)
       {
          // one thread: descriptor to shared memory, then the bulk copies of the patch's maps
          const PatchDesc *src = P.desc + p;
          for (int k = 0; k < (int)(sizeof(PatchDesc) / sizeof(int)); k++) { ((int *)&Dd[w])[k] = __ldg((const int *)src + k); }
-         unsigned char *mb = base + SR_BYTES + SA_BYTES;
+         unsigned char *mb = smraw + (size_t)w * wg_bytes + SR_BYTES + SA_BYTES;
          const int yb = wy ? Dd[w].yblob_bytes : 0, vb = Dd[w].vblob_bytes;
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
          mbar_expect_tx(&bar_blob[w], (unsigned)(yb + vb));
          if (yb) { bulk_g2s(mb, P.yblob + (size_t)Dd[w].yblob_off * 16, yb, &bar_blob[w]); }
          if (vb) { bulk_g2s(mb + P.max_yblob, P.vblob + (size_t)Dd[w].vblob_off * 16, vb, &bar_blob[w]); }
       };
+      if (tid == 0)
       {
-         const int p0 = (int)blockIdx.x * 2 + w;
-         if (tid == 0 && p0 < P.npatch) { prefetch(p0); }
+         for (int w = 0; w < 2; w++)
+         {
+            const int p0 = (int)blockIdx.x * 2 + w;
+            if (p0 < P.npatch) { prefetch(w, p0); }
+         }
       }
       const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_vb = o_yb + P.max_yblob;
+      const bool wvd = !(P.debug & 1);
+      long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const bool timing = P.dbg != nullptr && tid == 0;
       for (int it = 0;; it++)
       {
-         const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
-         if (p >= P.npatch) { break; }
-         mbar_wait(&bar_blob[w], it & 1);
-         const PatchDesc D = Dd[w];
-         mbar_wait(&bar_full[w], it & 1);
-         if (w == 0) { patch_drain<1>(base, o_sa, o_yb, o_vb, D, wy, true, tid, a.y, a.vals, P.ystage, P.vstage); }
-         else { patch_drain<2>(base, o_sa, o_yb, o_vb, D, wy, true, tid, a.y, a.vals, P.ystage, P.vstage); }
-         mbar_arrive(&bar_empty[w]);
-         // all threads of this writer are done with the maps: fetch those of the next patch
-         if (w == 0) { patch_bar<1>(); }
-         else { patch_bar<2>(); }
-         const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
-         if (tid == 0 && pn < P.npatch) { prefetch(pn); }
+         bool any = false;
+#pragma unroll 1
+         for (int w = 0; w < 2; w++)
+         {
+            const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+            if (p >= P.npatch) { continue; }
+            any = true;
+            unsigned char *base = smraw + (size_t)w * wg_bytes;
+            long long c0 = timing ? clock64() : 0;
+            mbar_wait(&bar_blob[w], it & 1);
+            const PatchDesc D = Dd[w];
+            if (timing) { const long long c1 = clock64(); tm[0] += c1 - c0; c0 = c1; }
+            mbar_wait(&bar_full[w], it & 1);
+            if (timing) { const long long c1 = clock64(); tm[1] += c1 - c0; c0 = c1; }
+            patch_drain<1, 8>(base, o_sa, o_yb, o_vb, D, wy, wvd, tid, a.y, a.vals, P.ystage, P.vstage, timing ? tm : nullptr);
+            if (timing) { c0 = clock64(); }
+            mbar_arrive(&bar_empty[w]);
+            // all writer threads are done with the maps of this buffer: fetch those of its next patch
+            patch_bar<1>();
+            const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+            if (tid == 0 && pn < P.npatch) { prefetch(w, pn); }
+            if (timing) { tm[6] += clock64() - c0; tm[7] += 1; }
+         }
+         if (!any) { break; }
       }
+      if (timing) { for (int k = 0; k < 8; k++) { atomicAdd(P.dbg + k, (unsigned long long)tm[k]); } }
    }
 }
 
@@ -356,7 +446,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
                ws_smem_set = ws_bytes;
             }
             const int grid = std::min(nsm, (P.npatch + 1) / 2);
-            kws<<<grid, 4 * PATCH_PE, ws_bytes, L.stream>>>(a, P);
+            kws<<<grid, 3 * PATCH_PE, ws_bytes, L.stream>>>(a, P);
             done = true;
          }
       }

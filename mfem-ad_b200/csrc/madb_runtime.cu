@@ -271,6 +271,14 @@ static int setup_integrator(Integrator &I)
       CUDA_OK(cudaMalloc((void **)&I.d_ystage, std::max<size_t>(H.stage_size, 1) * sizeof(double)));
       PatchDev &P = I.pdev;
       P.npatch = (int)I.pdesc.size();
+      P.debug = getenv("MADB_PATCH_DEBUG") ? atoi(getenv("MADB_PATCH_DEBUG")) : 0;
+      P.dbg = nullptr;
+      if (P.debug & 8)
+      {
+         CUDA_OK(cudaMalloc((void **)&I.d_dbg, 16 * sizeof(unsigned long long)));
+         CUDA_OK(cudaMemset(I.d_dbg, 0, 16 * sizeof(unsigned long long)));
+         P.dbg = I.d_dbg;
+      }
       P.max_yblob = I.max_yblob;
       P.max_vblob = 0;
       P.desc = I.d_pdesc;
@@ -853,6 +861,13 @@ extern "C"
    }
    int madb_integrator_patch_stats(madb_integrator *I, int64_t *out)
    {
+      if (I->d_dbg)
+      {
+         unsigned long long h[16];
+         cudaMemcpy(h, I->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+         fprintf(stderr, "writer cycles: wait_blob %llu wait_full %llu fold %llu rows %llu main %llu rest %llu tail %llu patches %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+         cudaMemset(I->d_dbg, 0, sizeof(h));
+      }
       for (int k = 0; k < 8; k++) { out[k] = 0; }
       if (!I->use_patches) { return 0; }
       out[0] = (int64_t)I->pdesc.size();
