@@ -43,15 +43,16 @@ struct PatchDesc
    int nruns;                 // runs of consecutive CSR positions covering [0,nint)
    int stage_off;             // vstage[stage_off + (s - nexc)] <- shared interface slots
    int vblob_off, vblob_bytes; // matrix-side maps: vblob + 16*vblob_off
-   int nchunk, nirr;          // chunk descriptors / irregular chunks of the directly written slots [0,nexc)
-   int pad[3];
+   int nchunk, nirr;          // chunk descriptors (padded to a multiple of 32) / irregular chunks (multiple of 8)
+   int nvsrc;                 // entries of vsrc (>= nslots, padded to 32*nchunk)
+   int pad[2];
 };
 // Blob layouts (sections padded to 16 bytes, copied to shared memory with one bulk copy each):
 //   y blob: ysrc u16[nrows]  | yfold u32[nyfold] | ylist i32[nrow_int]
-//   v blob: vsrc u16[nslots] | vfold u32[nvfold] | chunk i32[4*nchunk] | irr u16[nirr] | over i32[32*nirr]
+//   v blob: vsrc u16[nvsrc] | vfold u32[nvfold] | chunk i32[4*nchunk] | isrc u16[32*nirr] | over i32[32*nirr]
 //           chunk c covers slots [32c, 32c+32) of the directly written slots [0,nexc):
-//           {g0, g1 - split, split, -1}: lane < split -> CSR position g0 + lane, else g1 + (lane - split);
-//           {.., .., .., k >= 0}: irregular, chunk irr[k]: explicit positions over[32 k + lane]
+//           {g0, g1 - split, split, n}: lanes < n store; lane < split -> CSR position g0 + lane, else g1 + (lane - split);
+//           n = 0: nothing (padding, or an irregular chunk: its sources / explicit positions are isrc / over, -1 = none)
 // ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
 // fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
 // phase k adds the k-th further source, so every row / slot is summed in ascending element order.

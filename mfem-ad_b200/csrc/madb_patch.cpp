@@ -330,7 +330,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
    parallel_for_p(np, 64, [&](long b, long e)
    {
       std::vector<int> vd, base, run_s, run_g, keyslot, xg, gpos, chunks, over;
-      std::vector<unsigned short> irr;
+      std::vector<unsigned short> isrc;
       std::vector<std::pair<int, int>> excl; // (CSR position, key index)
       std::vector<std::vector<unsigned short>> srcs;
       std::vector<unsigned short> first;
@@ -408,9 +408,6 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          }
          if (!pack_sources(srcs, D.nslots, first, fold)) { ok = false; continue; }
          D.nvfold = (int)fold.size();
-         BlobWriter W;
-         W.section(first, first.size());
-         W.section(fold, fold.size());
          // CSR position of every directly written slot, packed per chunk of 32 slots:
          // {g0, g1 - split, split, -1}: slots [0,split) of the chunk go to g0 + lane, the rest to g1 + (lane - split);
          // {0, 0, 0, k >= 0}:   irregular chunk, the k-th of the list irr[]: explicit positions over[32 k + lane]
@@ -421,38 +418,52 @@ bool patch_build_v(Integrator &I, PatchHost &H)
                for (int q = run_s[r]; q < run_s[r + 1]; q++) { gpos[q] = run_g[r] + (q - run_s[r]); }
             }
             for (int q = D.nint; q < D.nexc; q++) { gpos[q] = xg[q - D.nint]; }
-            const int nchunk = (D.nexc + 31) / 32;
+            // chunk table padded to a multiple of 32 chunks (dummy chunks write nothing) so that the
+            // device loop needs no bounds checks; d[3] = number of lanes of the chunk that store
+            const int nchunk = ((D.nexc + 31) / 32 + 31) / 32 * 32;
             chunks.assign((size_t)4 * nchunk, 0);
             over.clear();
-            irr.clear();
+            isrc.clear();
             for (int c = 0; c < nchunk; c++)
             {
-               const int b0 = c * 32, n = std::min(32, D.nexc - b0);
+               const int b0 = c * 32, n = std::max(0, std::min(32, D.nexc - b0));
                int split = n, breaks = 0;
                for (int q = 1; q < n; q++)
                {
                   if (gpos[b0 + q] != gpos[b0 + q - 1] + 1) { breaks++; if (breaks == 1) { split = q; } }
                }
                int *d = &chunks[(size_t)4 * c];
+               if (n == 0) { continue; }
                if (breaks <= 1)
                {
                   d[0] = gpos[b0];
                   d[1] = (split < n) ? gpos[b0 + split] - split : 0;
                   d[2] = split;
-                  d[3] = -1;
+                  d[3] = n;
                }
                else
                {
-                  d[3] = (int)irr.size();
-                  irr.push_back((unsigned short)c);
-                  for (int q = 0; q < 32; q++) { over.push_back(q < n ? gpos[b0 + q] : 0); }
+                  for (int q = 0; q < 32; q++)
+                  {
+                     over.push_back(q < n ? gpos[b0 + q] : -1);
+                     isrc.push_back(q < n ? first[b0 + q] : 0);
+                  }
                }
             }
+            while ((over.size() / 32) % 8 != 0) // pad the irregular list to a multiple of 8 chunks
+            {
+               for (int q = 0; q < 32; q++) { over.push_back(-1); isrc.push_back(0); }
+            }
             D.nchunk = nchunk;
-            D.nirr = (int)irr.size();
+            D.nirr = (int)over.size() / 32;
+            first.resize(std::max<size_t>(first.size(), (size_t)32 * nchunk), 0); // padded so that chunk loads stay in bounds
          }
+         D.nvsrc = (int)first.size();
+         BlobWriter W;
+         W.section(first, first.size());
+         W.section(fold, fold.size());
          W.section(chunks, chunks.size());
-         W.section(irr, irr.size());
+         W.section(isrc, isrc.size());
          W.section(over, over.size());
          blobs[p].swap(W.b);
       }

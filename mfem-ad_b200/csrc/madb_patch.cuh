@@ -52,31 +52,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
    }
 }
 
-/// barrier of the PATCH_PE threads working on one patch: the whole CTA (BAR = 0) or one warpgroup (named barrier BAR)
-template <int BAR> __device__ __forceinline__ void patch_bar()
+/// barrier of the NT threads draining one patch: the whole CTA (BAR = 0) or the writer warps (named barrier BAR)
+template <int BAR, int NT> __device__ __forceinline__ void patch_bar()
 {
    if constexpr (BAR == 0) { __syncthreads(); }
-   else { asm volatile("bar.sync %0, 128;" ::"n"(BAR) : "memory"); }
+   else { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory"); }
 }
 
-/// Fold + gather + write-out of one staged patch by PATCH_PE threads (tid = 0..PATCH_PE-1).
+/// Fold + gather + write-out of one staged patch by NT threads (tid = 0..NT-1).
 /// base: shared memory of the patch: element vectors at 0, element matrices at o_sa, y maps at o_yb, matrix maps at o_vb.
 /// Every loop is written in batches of U independent iterations (all index loads, then all value loads, then
 /// all stores): the chains are shared-memory-latency bound, and only a few warps work on a patch.
-template <int BAR, int U>
+template <int BAR, int NT, int U>
 __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
                                             const bool wy, const bool wv, const int tid, double *__restrict__ y,
                                             double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage,
-                                            long long *tm = nullptr)
+                                            const int dbg = 0)
 {
-   constexpr int PE = PATCH_PE;
-   long long t0 = tm ? clock64() : 0;
-#define MADB_TICK(k) if (tm) { const long long t1 = clock64(); tm[k] += t1 - t0; t0 = t1; }
+   (void)dbg;
+   static_assert(32 % ((NT / 32) * U) == 0 || ((NT / 32) * U) % 32 == 0, "chunk tables are padded to multiples of 32 chunks");
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
 #define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
    const int nrows = D.nrows, nrow_int = D.nrow_int, nexc = D.nexc, nslots = D.nslots;
    const int o_yfold = o_yb + patch_al16(2 * nrows);
-   const int o_vfold = o_vb + patch_al16(2 * nslots);
+   const int o_vfold = o_vb + patch_al16(2 * D.nvsrc);
    // ---- fold: add the further sources of every row / slot onto its first source, phase by phase -------
    // (inside one phase every location occurs at most once, as a destination or as a source)
    {
@@ -86,19 +85,19 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
          const int ny = wy ? *(const int *)(base + o_yfold + 4 * ph) : 0;
          const int nv = wv ? *(const int *)(base + o_vfold + 4 * ph) : 0;
          if (ny == 0 && nv == 0) { break; }
-         for (int i = tid; i < ny; i += PE)
+         for (int i = tid; i < ny; i += NT)
          {
             const unsigned w = *(const unsigned *)(base + o_yfold + 4 * (ybase + i));
             MADB_SR(w & 0xffffu) += MADB_SR(w >> 16);
          }
-         for (int i0 = tid; i0 < nv; i0 += PE * U)
+         for (int i0 = tid; i0 < nv; i0 += NT * U)
          {
             unsigned w[U];
             double d0[U], d1[U];
 #pragma unroll
             for (int u = 0; u < U; u++)
             {
-               const int i = i0 + u * PE;
+               const int i = i0 + u * NT;
                w[u] = *(const unsigned *)(base + o_vfold + 4 * (vbase + (i < nv ? i : i0)));
             }
 #pragma unroll
@@ -108,72 +107,90 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
                d1[u] = MADB_SA(w[u] >> 16);
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) { if (i0 + u * PE < nv) { MADB_SA(w[u] & 0xffffu) = d0[u] + d1[u]; } }
+            for (int u = 0; u < U; u++) { if (i0 + u * NT < nv) { MADB_SA(w[u] & 0xffffu) = d0[u] + d1[u]; } }
          }
          ybase += ny;
          vbase += nv;
-         patch_bar<BAR>();
+         patch_bar<BAR, NT>();
       }
    }
-   MADB_TICK(2)
    // ---- rows of the residual -----------------------------------------------------------
    if (wy)
    {
       const int o_ylist = o_yfold + patch_al16(4 * D.nyfold);
-      for (int lr = tid; lr < nrows; lr += PE)
+      for (int lr = tid; lr < nrows; lr += NT)
       {
          const double v = MADB_SR(*(const unsigned short *)(base + o_yb + 2 * lr));
          if (lr < nrow_int) { y[*(const int *)(base + o_ylist + 4 * lr)] = v; }
          else { ystage[D.ystage_off + (lr - nrow_int)] = v; }
       }
    }
-   MADB_TICK(3)
    // ---- CSR entries ------------------------------------------------------------------------
    if (wv)
    {
+      constexpr int NW = NT / 32;
       const int o_chunk = o_vfold + patch_al16(4 * D.nvfold);
-      const int o_irr = o_chunk + patch_al16(16 * D.nchunk);
-      const int o_over = o_irr + patch_al16(2 * D.nirr);
+      const int o_isrc = o_chunk + patch_al16(16 * D.nchunk);
+      const int o_over = o_isrc + patch_al16(64 * D.nirr);
       const unsigned short *vsrc = (const unsigned short *)(base + o_vb);
-      const int4 *chunks = (const int4 *)(base + o_chunk);
-      const unsigned short *irr = (const unsigned short *)(base + o_irr);
-      const int *over = (const int *)(base + o_over);
-      const int lane = tid & 31, nchunk = D.nchunk, nirr = D.nirr;
-      constexpr int NW = PE / 32;
-      // directly written slots: CSR positions from the chunk descriptors {g0, g1 - split, split, flag}
-      // (consecutive lanes -> consecutive positions)
-      for (int c0 = tid >> 5; c0 < nchunk; c0 += NW * U)
+      const int lane = tid & 31, warp = tid >> 5;
+      // directly written slots: CSR positions from the chunk descriptors {g0, g1 - split, split, n}
+      // (consecutive lanes -> consecutive positions); the tables are padded, no bounds checks
       {
-         int g[U];
-         unsigned idx[U];
-         double v[U];
-#pragma unroll
-         for (int u = 0; u < U; u++)
+         const int4 *cp = (const int4 *)(base + o_chunk) + warp;
+         const unsigned short *vp = vsrc + warp * 32 + lane;
+         for (int c0 = 0; c0 < D.nchunk; c0 += NW * U)
          {
-            const int c = c0 + u * NW, cc = (c < nchunk) ? c : c0;
-            const int4 d = chunks[cc];
-            const int s = cc * 32 + lane;
-            idx[u] = vsrc[(s < nexc) ? s : nexc - 1];
-            const int gg = ((lane < d.z) ? d.x : d.y) + lane;
-            g[u] = (c < nchunk && d.w < 0 && s < nexc) ? gg : -1;
+            int g[U];
+            unsigned idx[U];
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+               const int4 d = cp[u * NW];
+               idx[u] = vp[u * NW * 32];
+               g[u] = (lane < d.w) ? ((lane < d.z) ? d.x : d.y) + lane : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) { v[u] = MADB_SA(idx[u]); }
+#pragma unroll
+            for (int u = 0; u < U; u++) { if (g[u] >= 0) { vals[g[u]] = v[u]; } }
+            cp += NW * U;
+            vp += NW * U * 32;
          }
-#pragma unroll
-         for (int u = 0; u < U; u++) { v[u] = MADB_SA(idx[u]); }
-#pragma unroll
-         for (int u = 0; u < U; u++) { if (g[u] >= 0) { vals[g[u]] = v[u]; } }
       }
-      MADB_TICK(4)
-      // irregular chunks: explicit positions
-      for (int k = tid >> 5; k < nirr; k += NW)
+         // irregular chunks: explicit positions (-1: none)
       {
-         const int s = irr[k] * 32 + lane;
-         if (s < nexc) { vals[over[32 * k + lane]] = MADB_SA(vsrc[s]); }
+         constexpr int UI = (NW >= 8) ? 1 : 8 / NW;
+         const unsigned short *ip = (const unsigned short *)(base + o_isrc) + warp * 32 + lane;
+         const int *op = (const int *)(base + o_over) + warp * 32 + lane;
+         for (int k0 = 0; k0 < D.nirr; k0 += NW * UI)
+         {
+            int g[UI];
+            double v[UI];
+#pragma unroll
+            for (int u = 0; u < UI; u++)
+            {
+               g[u] = op[u * NW * 32];
+               v[u] = MADB_SA(ip[u * NW * 32]);
+            }
+#pragma unroll
+            for (int u = 0; u < UI; u++) { if (g[u] >= 0) { vals[g[u]] = v[u]; } }
+            ip += NW * UI * 32;
+            op += NW * UI * 32;
+         }
       }
+      // entries shared with other patches: staged, contiguous
       double *stage = vstage + D.stage_off - nexc;
-      for (int s = nexc + tid; s < nslots; s += PE) { stage[s] = MADB_SA(vsrc[s]); }
+      for (int s0 = nexc + tid; s0 < nslots; s0 += NT * 4)
+      {
+         double v[4];
+#pragma unroll
+         for (int u = 0; u < 4; u++) { const int s = s0 + u * NT; v[u] = MADB_SA(vsrc[s < nslots ? s : s0]); }
+#pragma unroll
+         for (int u = 0; u < 4; u++) { const int s = s0 + u * NT; if (s < nslots) { stage[s] = v[u]; } }
+      }
    }
-   MADB_TICK(5)
-#undef MADB_TICK
 #undef MADB_SR
 #undef MADB_SA
 }
@@ -244,7 +261,7 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
    __syncthreads();
    mbar_wait(&mbar, 0);
 
-   patch_drain<0, 4>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
+   patch_drain<0, PATCH_PE, 4>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
 #undef MADB_SR
 #undef MADB_SA
 }
@@ -264,8 +281,15 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 // Hand-off through mbarriers: full[w] (compute -> writer), empty[w] (writer -> compute),
 // blob[w] (bulk-copy completion).  Patches are dealt round-robin: p = (it * gridDim + cta) * 2 + w.
 // ---------------------------------------------------------------------------------------------
+constexpr int WS_WRITER_WG = 2;                              // writer warpgroups (all drain the same patch together)
+constexpr int WS_NT = WS_WRITER_WG * PATCH_PE;               // writer threads
+constexpr int WS_THREADS = (WS_WRITER_WG + 2) * PATCH_PE;
+// register split after setmaxnreg (sum over the CTA must stay BELOW 64 K: an exact fit deadlocks the increase)
+constexpr int WS_REG_COMPUTE = (WS_WRITER_WG == 1) ? 216 : 208, WS_REG_WRITER = (WS_WRITER_WG == 1) ? 64 : 40;
+static_assert(2 * PATCH_PE * WS_REG_COMPUTE + WS_NT * WS_REG_WRITER <= 65536 - 1024, "setmaxnreg budget");
+
 template <class Func, class Cfg, bool UNROLLQ>
-__global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_constant__ AsmArgs<Func, Cfg> a,
+__global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constant__ AsmArgs<Func, Cfg> a,
                                                               const __grid_constant__ PatchDev P)
 {
    constexpr int MODE = MODE_RES | MODE_JAC;
@@ -282,17 +306,17 @@ __global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_const
       for (int k = 0; k < 2; k++)
       {
          mbar_init(&bar_full[k], PE);
-         mbar_init(&bar_empty[k], PE);
+         mbar_init(&bar_empty[k], WS_NT);
          mbar_init(&bar_blob[k], 1);
       }
    }
    __syncthreads();
 
-   if (wg != 0)
+   if (wg >= WS_WRITER_WG)
    {
       // ================= compute warpgroups =================
-      asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-      const int w = wg - 1;
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_COMPUTE));
+      const int w = wg - WS_WRITER_WG;
       unsigned char *base = smraw + (size_t)w * wg_bytes;
       for (int it = 0;; it++)
       {
@@ -337,7 +361,8 @@ __global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_const
    else
    {
       // ================= writer warpgroup =================
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_WRITER));
+      const int wtid = threadIdx.x; // 0..WS_NT-1
       auto prefetch = [&](int w, int p)
       {
          // one thread: descriptor to shared memory, then the bulk copies of the patch's maps
@@ -350,7 +375,7 @@ __global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_const
          if (yb) { bulk_g2s(mb, P.yblob + (size_t)Dd[w].yblob_off * 16, yb, &bar_blob[w]); }
          if (vb) { bulk_g2s(mb + P.max_yblob, P.vblob + (size_t)Dd[w].vblob_off * 16, vb, &bar_blob[w]); }
       };
-      if (tid == 0)
+      if (wtid == 0)
       {
          for (int w = 0; w < 2; w++)
          {
@@ -360,8 +385,6 @@ __global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_const
       }
       const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_vb = o_yb + P.max_yblob;
       const bool wvd = !(P.debug & 1);
-      long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      const bool timing = P.dbg != nullptr && tid == 0;
       for (int it = 0;; it++)
       {
          bool any = false;
@@ -372,24 +395,17 @@ __global__ void __launch_bounds__(3 * PATCH_PE, 1) k_patch_ws(const __grid_const
             if (p >= P.npatch) { continue; }
             any = true;
             unsigned char *base = smraw + (size_t)w * wg_bytes;
-            long long c0 = timing ? clock64() : 0;
-            mbar_wait(&bar_blob[w], it & 1);
-            const PatchDesc D = Dd[w];
-            if (timing) { const long long c1 = clock64(); tm[0] += c1 - c0; c0 = c1; }
-            mbar_wait(&bar_full[w], it & 1);
-            if (timing) { const long long c1 = clock64(); tm[1] += c1 - c0; c0 = c1; }
-            patch_drain<1, 8>(base, o_sa, o_yb, o_vb, D, wy, wvd, tid, a.y, a.vals, P.ystage, P.vstage, timing ? tm : nullptr);
-            if (timing) { c0 = clock64(); }
+            mbar_wait(&bar_blob[w], it & 1); // maps and descriptor (Dd[w], stable until the next prefetch) have landed
+            mbar_wait(&bar_full[w], it & 1); // the compute warpgroup has staged the patch
+            patch_drain<1, WS_NT, 32 / (WS_NT / 32)>(base, o_sa, o_yb, o_vb, Dd[w], wy, wvd, wtid, a.y, a.vals, P.ystage, P.vstage);
             mbar_arrive(&bar_empty[w]);
             // all writer threads are done with the maps of this buffer: fetch those of its next patch
-            patch_bar<1>();
+            patch_bar<1, WS_NT>();
             const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
-            if (tid == 0 && pn < P.npatch) { prefetch(w, pn); }
-            if (timing) { tm[6] += clock64() - c0; tm[7] += 1; }
+            if (wtid == 0 && pn < P.npatch) { prefetch(w, pn); }
          }
          if (!any) { break; }
       }
-      if (timing) { for (int k = 0; k < 8; k++) { atomicAdd(P.dbg + k, (unsigned long long)tm[k]); } }
    }
 }
 
@@ -446,7 +462,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
                ws_smem_set = ws_bytes;
             }
             const int grid = std::min(nsm, (P.npatch + 1) / 2);
-            kws<<<grid, 3 * PATCH_PE, ws_bytes, L.stream>>>(a, P);
+            kws<<<grid, WS_THREADS, ws_bytes, L.stream>>>(a, P);
             done = true;
          }
       }

@@ -866,6 +866,7 @@ extern "C"
          unsigned long long h[16];
          cudaMemcpy(h, I->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
          fprintf(stderr, "writer cycles: wait_blob %llu wait_full %llu fold %llu rows %llu main %llu rest %llu tail %llu patches %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+         fprintf(stderr, "  fold phases (work, barrier): ph0 %llu %llu  ph1 %llu %llu  ph2+ %llu %llu\n", h[8], h[9], h[10], h[11], h[12], h[13]);
          cudaMemset(I->d_dbg, 0, sizeof(h));
       }
       for (int k = 0; k < 8; k++) { out[k] = 0; }
