@@ -409,17 +409,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
    }
 }
 
-// out[dst[i]] = sum of the staged partials of entry i, in ascending patch order
-static __global__ void __launch_bounds__(256) k_ifc_reduce(int n, const int *__restrict__ ptr, const int *__restrict__ src,
-                                                           const int *__restrict__ dst, const double *__restrict__ stage,
-                                                           double *__restrict__ out)
+// Interface reduction: out[dst[i]] = sum of the staged partials of entry i, in ascending patch order.
+// One launch covers both lists (residual rows: blocks [0, nby), CSR entries: the remaining blocks).
+struct IfcList
 {
-   const int i = blockIdx.x * 256 + threadIdx.x;
-   if (i >= n) { return; }
-   const int b = ptr[i], e = ptr[i + 1];
-   double s = stage[src[b]];
-   for (int k = b + 1; k < e; k++) { s += stage[src[k]]; }
-   out[dst[i]] = s;
+   int n;
+   const int *ptr, *src, *dst;
+   const double *stage;
+   double *out;
+};
+static __global__ void __launch_bounds__(256) k_ifc_reduce(const IfcList A, const IfcList B, const int nba)
+{
+   const bool first = (int)blockIdx.x < nba;
+   const IfcList &L = first ? A : B;
+   const int i = ((int)blockIdx.x - (first ? 0 : nba)) * 256 + threadIdx.x;
+   if (i >= L.n) { return; }
+   const int b = L.ptr[i], e = L.ptr[i + 1];
+   double s = L.stage[L.src[b]];
+   for (int k = b + 1; k < e; k++) { s += L.stage[L.src[k]]; }
+   L.out[L.dst[i]] = s;
 }
 
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
@@ -469,13 +477,11 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    }
    if (!done) { kern<<<P.npatch, PATCH_PE, smem_bytes, L.stream>>>(a, P); }
    if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
-   if (wy && P.ny_ifc > 0)
    {
-      k_ifc_reduce<<<(P.ny_ifc + 255) / 256, 256, 0, L.stream>>>(P.ny_ifc, P.y_ptr, P.y_src, P.y_dst, P.ystage, L.y);
-   }
-   if (wv && P.nv_ifc > 0)
-   {
-      k_ifc_reduce<<<(P.nv_ifc + 255) / 256, 256, 0, L.stream>>>(P.nv_ifc, P.v_ptr, P.v_src, P.v_dst, P.vstage, L.vals);
+      const IfcList ly = {wy ? P.ny_ifc : 0, P.y_ptr, P.y_src, P.y_dst, P.ystage, L.y};
+      const IfcList lv = {wv ? P.nv_ifc : 0, P.v_ptr, P.v_src, P.v_dst, P.vstage, L.vals};
+      const int nba = (ly.n + 255) / 256, nbb = (lv.n + 255) / 256;
+      if (nba + nbb > 0) { k_ifc_reduce<<<nba + nbb, 256, 0, L.stream>>>(ly, lv, nba); }
    }
    return (int)cudaGetLastError();
 }
