@@ -31,6 +31,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 EPS = 0.5
 P = 2
 FP64_INSTR = 2754  # DFMA+DMUL+DADD per element in the SASS of k_patch<minsurf,Q2,RES|JAC> (tools/sass_count.sh)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_patch_ws launch of this workload (1000x1000),
+# ncu --set full capture summarised in profiles/r01_v2_k_patch_ws.md
+NCU_TRAFFIC_BYTES = {1000: 957066240}
 
 
 def peaks():
@@ -289,7 +292,8 @@ def run_gpu(args):
             "qpts_per_s": world * nq / (ms_step * 1e-3),
             "dofs_per_gpu": ndof, "nnz_per_gpu": int(nnz), "setup_s": setup_s,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES.get(nx) if patch else None, "traffic_unit": "bytes per launch (ncu)",
+                         "peak_source": peak_src,
                          "kernel": ("k_patch_ws" if patch else "k_element") + "<MinimalSurfaceEnergy<2>,Q2,RES|JAC>",
                          "launches_per_step": kernel_launches, "avg_launch_ms": ms_kernel / kernel_launches,
                          "algorithmic_bytes_per_step": alg_bytes,
