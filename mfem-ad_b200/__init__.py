@@ -181,6 +181,11 @@ class Functional:
                                           g.ctypes.data, h.ctypes.data))
         return v, g, h
 
+    def eval_device(self, x, value=None, grad=None, hess=None, qprm=None):
+        """Same on buffers that already live on the device (torch tensors): x[npts, n]; outputs may be None."""
+        npts, n = x.shape
+        _check(lib().madb_functional_eval(self.ctx.h, self.h, n, npts, _ptr(x), _ptr(qprm), _ptr(value), _ptr(grad), _ptr(hess)))
+
     def __del__(self):
         try:
             lib().madb_functional_destroy(self.h)
@@ -292,6 +297,10 @@ class Integrator:
         grd = np.empty((ne, self.nq_el, n_in)) if want_grad else None
         _check(lib().madb_integrator_coefficient(self.h, _ptr(x), _ptr(val), _ptr(grd)))
         return val, grd
+
+    def coefficient_device(self, x, value=None, grad=None):
+        """Same on device buffers (torch tensors); value [ne*nq], grad [ne*nq*n] or None."""
+        _check(lib().madb_integrator_coefficient(self.h, _ptr(x), _ptr(value), _ptr(grad)))
 
     def grad_mult(self, x, v, y=None):
         if isinstance(x, np.ndarray):

@@ -122,6 +122,7 @@ struct Ctx
 {
    int device = 0;
    cudaStream_t stream = nullptr;
+   double *scratch = nullptr, *scratch_host = nullptr; // reduction partials (device) and result (pinned host)
 };
 
 struct Mesh

@@ -552,6 +552,8 @@ extern "C"
    {
       if (!c) { return 0; }
       cudaStreamDestroy(c->stream);
+      cudaFree(c->scratch);
+      cudaFreeHost(c->scratch_host);
       delete c;
       return 0;
    }
@@ -747,14 +749,18 @@ extern "C"
       Staged sp, sk, sl, sw;
       if (sp.in(psi, n) || sk.out(psik, n) || sl.out(lambda_prev, n) || sw.in(w, n)) { set_error("madb_lvpp_update: device staging failed"); return 2; }
       const int nb = std::min(1024, (n + 255) / 256);
-      double *partial = nullptr, *dsum = nullptr;
-      CUDA_OK(cudaMalloc((void **)&partial, (size_t)(nb + 1) * sizeof(double)));
-      dsum = partial + nb;
+      // block partials + the sum live in a per-context scratch buffer (no allocation per call)
+      if (!ctx->scratch)
+      {
+         CUDA_OK(cudaMalloc((void **)&ctx->scratch, 1025 * sizeof(double)));
+         CUDA_OK(cudaMallocHost((void **)&ctx->scratch_host, sizeof(double)));
+      }
+      double *partial = ctx->scratch, *dsum = ctx->scratch + 1024;
       k_lvpp_update<<<nb, 256, 0, ctx->stream>>>(n, alpha, sp.d, sk.d, sl.d, sw.d, partial);
       k_reduce_sum<<<1, 1024, 0, ctx->stream>>>(partial, nb, dsum);
-      CUDA_OK(cudaMemcpyAsync(lambda_diff, dsum, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      CUDA_OK(cudaMemcpyAsync(ctx->scratch_host, dsum, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
       CUDA_OK(cudaStreamSynchronize(ctx->stream));
-      cudaFree(partial);
+      *lambda_diff = *ctx->scratch_host;
       sp.finish(); sw.finish();
       if (sk.finish() || sl.finish()) { set_error("madb_lvpp_update: copy back failed"); return 2; }
       return 0;
