@@ -251,6 +251,18 @@ MADB_CMP(!=)
 // ---- elementary functions ---------------------------------------------------
 template <int N, int O> MADB_HD AD<N, O> sqrt(const AD<N, O> &a)
 {
+#if defined(__CUDA_ARCH__)
+   // one reciprocal square root instead of a square root and two divisions:
+   //   r = a^-1/2,  f = a r (one Newton correction),  f' = r/2,  f'' = -r^3/4
+   if (a.v > 0.0)
+   {
+      const double r = ::rsqrt(a.v);
+      double s = a.v * r;
+      s = fma(0.5 * r, fma(-s, s, a.v), s);
+      const double f1 = 0.5 * r;
+      return ad_chain(a, s, f1, -0.5 * f1 * (r * r));
+   }
+#endif
    const double s = ::sqrt(a.v);
    const double f1 = 0.5 / s;
    return ad_chain(a, s, f1, -0.5 * f1 / a.v);
@@ -277,12 +289,37 @@ template <int N, int O> MADB_HD AD<N, O> cos(const AD<N, O> &a)
    ::sincos(a.v, &s, &c);
    return ad_chain(a, c, -s, -c);
 }
+/// a^p for a real exponent; small integer exponents (the SIMP penalisation p = 3, src/mmto.hpp:24) by multiplication
+MADB_HD double rpow(double a, double p)
+{
+   if (p == 1.0) { return a; }
+   if (p == 2.0) { return a * a; }
+   if (p == 3.0) { return a * a * a; }
+   if (p == 0.0) { return 1.0; }
+   return ::pow(a, p);
+}
+template <int N, int O> MADB_HD AD<N, O> pow(const AD<N, O> &a, double p);
+template <int N, int O> MADB_HD AD<N, O> rpow(const AD<N, O> &a, double p) { return pow(a, p); }
+
 template <int N, int O> MADB_HD AD<N, O> pow(const AD<N, O> &a, double p)
 {
-   const double f = ::pow(a.v, p);
-   const double f1 = p * ::pow(a.v, p - 1.0);
-   const double f2 = (O >= 2) ? p * (p - 1.0) * ::pow(a.v, p - 2.0) : 0.0;
-   return ad_chain(a, f, f1, f2);
+   // one transcendental instead of three: a^(p-2) (or a^(p-1) for first order), the rest by multiplication.
+   // a == 0 keeps the reference's values pow(0, p), p pow(0, p-1), p (p-1) pow(0, p-2) (src/mmto.hpp:24 uses p = 3).
+   if (a.v == 0.0)
+   {
+      const double f2 = (O >= 2) ? p * (p - 1.0) * ::pow(a.v, p - 2.0) : 0.0;
+      return ad_chain(a, ::pow(a.v, p), p * ::pow(a.v, p - 1.0), f2);
+   }
+   if constexpr (O >= 2)
+   {
+      const double pm2 = rpow(a.v, p - 2.0), pm1 = pm2 * a.v;
+      return ad_chain(a, pm1 * a.v, p * pm1, p * (p - 1.0) * pm2);
+   }
+   else
+   {
+      const double pm1 = rpow(a.v, p - 1.0);
+      return ad_chain(a, pm1 * a.v, p * pm1, 0.0);
+   }
 }
 using ::cos;
 using ::exp;

@@ -330,9 +330,9 @@ template <int N> struct SIMPFunction
    }
    template <class T> MADB_HD T operator()(const T *x, const double *) const
    {
-      T result = E[0] * pow(x[0], p);
+      T result = E[0] * rpow(x[0], p);
 #pragma unroll
-      for (int i = 1; i < N; i++) { result += E[i] * pow(x[i], p); }
+      for (int i = 1; i < N; i++) { result += E[i] * rpow(x[i], p); }
       return result;
    }
 };
