@@ -56,19 +56,26 @@ struct PatchDesc
 // ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
 // fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
 // phase k adds the k-th further source, so every row / slot is summed in ascending element order.
+struct IfcListDev // interface reduction lists of one side (see k_ifc_reduce)
+{
+   int n4, ng;
+   const int4 *src4;
+   const int *dst4;
+   const int *ptr, *src, *dst;
+   const double *stage;
+   double *out;
+};
 struct PatchDev
 {
    int npatch;
-   unsigned long long *dbg;  // MADB_PATCH_DEBUG & 8: cycle counters of the writer warpgroup (diagnostics)
    int debug;                // MADB_PATCH_DEBUG: 1 = skip the CSR write-out, 2 = skip the element computation (timing experiments)
    int max_yblob, max_vblob; // bytes, shared-memory sizing
    const PatchDesc *desc;
    const unsigned char *yblob, *vblob;
    double *ystage, *vstage;
-   // interface reductions: out[dst[i]] = sum_{k in ptr[i]..ptr[i+1]} stage[src[k]]
-   int ny_ifc, nv_ifc;
-   const int *y_ptr, *y_src, *y_dst;
-   const int *v_ptr, *v_src, *v_dst;
+   // interface reductions: out[dst] = sum of the staged partials, ascending patch order
+   int ny_ifc, nv_ifc; // entries (statistics)
+   IfcListDev ylist, vlist;
 };
 
 struct LaunchCtx
@@ -217,10 +224,9 @@ struct Integrator
    bool have_patch_vals = false;
    PatchDev pdev {};
    PatchDesc *d_pdesc = nullptr;
-   unsigned long long *d_dbg = nullptr;
    unsigned char *d_yblob = nullptr, *d_vblob = nullptr;
    double *d_ystage = nullptr, *d_vstage = nullptr;
-   int *d_yptr = nullptr, *d_ysrc = nullptr, *d_ydst = nullptr, *d_vptr = nullptr, *d_vsrc = nullptr, *d_vdst = nullptr;
+   int *d_ifc[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}}; // [side][src4, dst4, ptr, src, dst]
 
    // optional device timing of the element kernel(s)
    bool timing = false;
@@ -246,7 +252,8 @@ void build_e2csr(const Integrator &I, const std::vector<int> &color, std::vector
 struct PatchHost // maps of one side (residual or matrix)
 {
    std::vector<unsigned char> blob;
-   std::vector<int> ptr, src, dst; // interface reduction lists
+   std::vector<int> ptr, src, dst; // interface reduction lists: entries with more than 4 sources
+   std::vector<int> src4, dst4;    // packed entries: 4 sources (-1: none) each
    long stage_size = 0;
 };
 void patch_order(Integrator &I);                      // fills I.perm (patch order) and I.pdesc[].ne

@@ -153,22 +153,31 @@ bool pack_sources(const std::vector<std::vector<unsigned short>> &srcs, int ndst
    return true;
 }
 
-// group (destination, staging index) pairs by destination; sources stay in ascending staging (= patch) order
+// group (destination, staging index) pairs by destination; sources stay in ascending staging (= patch) order.
+// Destinations with at most 4 sources go to the packed lists, the others to the CSR-like lists.
 void group_by_dst(std::vector<std::pair<int, int>> &tup, PatchHost &H)
 {
    std::stable_sort(tup.begin(), tup.end(), [](const std::pair<int, int> &a, const std::pair<int, int> &b) { return a.first < b.first; });
-   H.ptr.clear(); H.dst.clear();
-   H.src.resize(tup.size());
-   for (size_t k = 0; k < tup.size(); k++)
+   H.ptr.assign(1, 0);
+   H.src.clear(); H.dst.clear(); H.src4.clear(); H.dst4.clear();
+   size_t k = 0;
+   while (k < tup.size())
    {
-      if (k == 0 || tup[k].first != tup[k - 1].first)
+      size_t e = k;
+      while (e < tup.size() && tup[e].first == tup[k].first) { e++; }
+      if (e - k <= 4)
       {
-         H.ptr.push_back((int)k);
+         for (size_t q = 0; q < 4; q++) { H.src4.push_back(k + q < e ? tup[k + q].second : -1); }
+         H.dst4.push_back(tup[k].first);
+      }
+      else
+      {
+         for (size_t q = k; q < e; q++) { H.src.push_back(tup[q].second); }
+         H.ptr.push_back((int)H.src.size());
          H.dst.push_back(tup[k].first);
       }
-      H.src[k] = tup[k].second;
+      k = e;
    }
-   H.ptr.push_back((int)tup.size());
 }
 } // namespace
 

@@ -410,24 +410,40 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
 }
 
 // Interface reduction: out[dst[i]] = sum of the staged partials of entry i, in ascending patch order.
-// One launch covers both lists (residual rows: blocks [0, nby), CSR entries: the remaining blocks).
-struct IfcList
+// Entries with at most 4 sources (nearly all: 2 for an edge between two patches) are stored packed
+// {src0..src3 (-1: none), dst} so that all loads of an entry are independent; the rest as (ptr, src, dst) lists.
+// One launch covers the residual rows and the CSR entries: blocks [0,nb0) list A packed, [nb0,nb1) A general,
+// [nb1,nb2) B packed, [nb2,nb3) B general.
+using IfcList = IfcListDev;
+__device__ __forceinline__ void ifc_reduce_packed(const IfcList &L, const int i)
 {
-   int n;
-   const int *ptr, *src, *dst;
-   const double *stage;
-   double *out;
-};
-static __global__ void __launch_bounds__(256) k_ifc_reduce(const IfcList A, const IfcList B, const int nba)
+   if (i >= L.n4) { return; }
+   const int4 s = L.src4[i];
+   const int d = L.dst4[i];
+   const double a0 = L.stage[s.x], a1 = (s.y >= 0) ? L.stage[s.y] : 0.0, a2 = (s.z >= 0) ? L.stage[s.z] : 0.0,
+                a3 = (s.w >= 0) ? L.stage[s.w] : 0.0;
+   double v = a0;
+   if (s.y >= 0) { v += a1; }
+   if (s.z >= 0) { v += a2; }
+   if (s.w >= 0) { v += a3; }
+   L.out[d] = v;
+}
+__device__ __forceinline__ void ifc_reduce_general(const IfcList &L, const int i)
 {
-   const bool first = (int)blockIdx.x < nba;
-   const IfcList &L = first ? A : B;
-   const int i = ((int)blockIdx.x - (first ? 0 : nba)) * 256 + threadIdx.x;
-   if (i >= L.n) { return; }
+   if (i >= L.ng) { return; }
    const int b = L.ptr[i], e = L.ptr[i + 1];
    double s = L.stage[L.src[b]];
    for (int k = b + 1; k < e; k++) { s += L.stage[L.src[k]]; }
    L.out[L.dst[i]] = s;
+}
+static __global__ void __launch_bounds__(256) k_ifc_reduce(const IfcList A, const IfcList B, const int nb0, const int nb1,
+                                                           const int nb2)
+{
+   const int blk = blockIdx.x, t = threadIdx.x;
+   if (blk < nb0) { ifc_reduce_packed(A, blk * 256 + t); }
+   else if (blk < nb1) { ifc_reduce_general(A, (blk - nb0) * 256 + t); }
+   else if (blk < nb2) { ifc_reduce_packed(B, (blk - nb1) * 256 + t); }
+   else { ifc_reduce_general(B, (blk - nb2) * 256 + t); }
 }
 
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
@@ -478,10 +494,14 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    if (!done) { kern<<<P.npatch, PATCH_PE, smem_bytes, L.stream>>>(a, P); }
    if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
    {
-      const IfcList ly = {wy ? P.ny_ifc : 0, P.y_ptr, P.y_src, P.y_dst, P.ystage, L.y};
-      const IfcList lv = {wv ? P.nv_ifc : 0, P.v_ptr, P.v_src, P.v_dst, P.vstage, L.vals};
-      const int nba = (ly.n + 255) / 256, nbb = (lv.n + 255) / 256;
-      if (nba + nbb > 0) { k_ifc_reduce<<<nba + nbb, 256, 0, L.stream>>>(ly, lv, nba); }
+      IfcList ly = P.ylist, lv = P.vlist;
+      ly.stage = P.ystage; ly.out = L.y;
+      lv.stage = P.vstage; lv.out = L.vals;
+      if (!wy) { ly.n4 = ly.ng = 0; }
+      if (!wv) { lv.n4 = lv.ng = 0; }
+      const int nb0 = (ly.n4 + 255) / 256, nb1 = nb0 + (ly.ng + 255) / 256, nb2 = nb1 + (lv.n4 + 255) / 256,
+                nb3 = nb2 + (lv.ng + 255) / 256;
+      if (nb3 > 0) { k_ifc_reduce<<<nb3, 256, 0, L.stream>>>(ly, lv, nb0, nb1, nb2); }
    }
    return (int)cudaGetLastError();
 }

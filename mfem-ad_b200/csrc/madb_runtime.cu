@@ -55,8 +55,8 @@ Integrator::~Integrator()
    for (double *p : d_pstage) { cudaFree(p); }
    if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
    cudaFree(d_pdesc); cudaFree(d_yblob); cudaFree(d_vblob);
-   cudaFree(d_ystage); cudaFree(d_vstage); cudaFree(d_yptr); cudaFree(d_ysrc); cudaFree(d_ydst);
-   cudaFree(d_vptr); cudaFree(d_vsrc); cudaFree(d_vdst);
+   cudaFree(d_ystage); cudaFree(d_vstage);
+   for (int a = 0; a < 2; a++) { for (int b = 0; b < 5; b++) { cudaFree(d_ifc[a][b]); } }
 }
 
 #define CUDA_OK(call)                                                                                 \
@@ -174,6 +174,18 @@ template <class T> static int upload(const std::vector<T> &h, T **d)
    return 0;
 }
 
+static int upload_ifc(const PatchHost &H, int *(&d)[5], IfcListDev &L)
+{
+   if (upload(H.src4, &d[0]) || upload(H.dst4, &d[1]) || upload(H.ptr, &d[2]) || upload(H.src, &d[3]) || upload(H.dst, &d[4])) { return 2; }
+   L.n4 = (int)H.dst4.size();
+   L.ng = (int)H.dst.size();
+   L.src4 = (const int4 *)d[0];
+   L.dst4 = d[1];
+   L.ptr = d[2]; L.src = d[3]; L.dst = d[4];
+   L.stage = nullptr; L.out = nullptr;
+   return 0;
+}
+
 static int setup_integrator(Integrator &I)
 {
    const int dim = I.mesh->dim;
@@ -263,29 +275,17 @@ static int setup_integrator(Integrator &I)
    {
       PatchHost H;
       if (!patch_build_y(I, H)) { set_error("patch assembly: a dof has more than 8 contributing elements in one patch (set MADB_NO_PATCH=1)"); return 1; }
-      if (upload(H.blob, &I.d_yblob) || upload(H.ptr, &I.d_yptr) || upload(H.src, &I.d_ysrc) || upload(H.dst, &I.d_ydst) ||
-          upload(I.pdesc, &I.d_pdesc))
-      {
-         return 2;
-      }
+      if (upload(H.blob, &I.d_yblob) || upload(I.pdesc, &I.d_pdesc) || upload_ifc(H, I.d_ifc[0], I.pdev.ylist)) { return 2; }
       CUDA_OK(cudaMalloc((void **)&I.d_ystage, std::max<size_t>(H.stage_size, 1) * sizeof(double)));
       PatchDev &P = I.pdev;
       P.npatch = (int)I.pdesc.size();
       P.debug = getenv("MADB_PATCH_DEBUG") ? atoi(getenv("MADB_PATCH_DEBUG")) : 0;
-      P.dbg = nullptr;
-      if (P.debug & 8)
-      {
-         CUDA_OK(cudaMalloc((void **)&I.d_dbg, 16 * sizeof(unsigned long long)));
-         CUDA_OK(cudaMemset(I.d_dbg, 0, 16 * sizeof(unsigned long long)));
-         P.dbg = I.d_dbg;
-      }
       P.max_yblob = I.max_yblob;
       P.max_vblob = 0;
       P.desc = I.d_pdesc;
       P.yblob = I.d_yblob;
       P.ystage = I.d_ystage;
-      P.ny_ifc = (int)H.dst.size();
-      P.y_ptr = I.d_yptr; P.y_src = I.d_ysrc; P.y_dst = I.d_ydst;
+      P.ny_ifc = (int)(H.dst.size() + H.dst4.size());
    }
 
    // basis tables at the quadrature points: [q][toff_f + i], x fastest in q and i
@@ -363,8 +363,8 @@ static int ensure_pattern_device(Integrator &I)
    {
       PatchHost H;
       if (!patch_build_v(I, H)) { return 1; }
-      if (upload(H.blob, &I.d_vblob) || upload(H.ptr, &I.d_vptr) || upload(H.src, &I.d_vsrc) || upload(H.dst, &I.d_vdst) ||
-          upload(I.rowptr, &I.d_rowptr) || upload(I.colidx, &I.d_colidx))
+      if (upload(H.blob, &I.d_vblob) || upload_ifc(H, I.d_ifc[1], I.pdev.vlist) || upload(I.rowptr, &I.d_rowptr) ||
+          upload(I.colidx, &I.d_colidx))
       {
          return 2;
       }
@@ -374,8 +374,7 @@ static int ensure_pattern_device(Integrator &I)
       P.max_vblob = I.max_vblob;
       P.vblob = I.d_vblob;
       P.vstage = I.d_vstage;
-      P.nv_ifc = (int)H.dst.size();
-      P.v_ptr = I.d_vptr; P.v_src = I.d_vsrc; P.v_dst = I.d_vdst;
+      P.nv_ifc = (int)(H.dst.size() + H.dst4.size());
       return 0;
    }
    std::vector<int> e2csr;
@@ -867,14 +866,6 @@ extern "C"
    }
    int madb_integrator_patch_stats(madb_integrator *I, int64_t *out)
    {
-      if (I->d_dbg)
-      {
-         unsigned long long h[16];
-         cudaMemcpy(h, I->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
-         fprintf(stderr, "writer cycles: wait_blob %llu wait_full %llu fold %llu rows %llu main %llu rest %llu tail %llu patches %llu\n", h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
-         fprintf(stderr, "  fold phases (work, barrier): ph0 %llu %llu  ph1 %llu %llu  ph2+ %llu %llu\n", h[8], h[9], h[10], h[11], h[12], h[13]);
-         cudaMemset(I->d_dbg, 0, sizeof(h));
-      }
       for (int k = 0; k < 8; k++) { out[k] = 0; }
       if (!I->use_patches) { return 0; }
       out[0] = (int64_t)I->pdesc.size();

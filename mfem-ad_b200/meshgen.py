@@ -100,6 +100,19 @@ def permute_dofs(space, seed):
     return out
 
 
+def shuffle_mesh(mesh, spaces, seed):
+    """Same mesh with the elements and the vertices renumbered at random (and the element rows of the
+    dof maps permuted alike): nothing in the assembly may depend on a structured numbering."""
+    rng = np.random.default_rng(seed)
+    ne, nv = mesh["e2n"].shape[0], mesh["coords"].shape[0]
+    pe = rng.permutation(ne)
+    pv = rng.permutation(nv).astype(np.int32)  # old vertex id -> new id
+    coords = np.empty_like(mesh["coords"])
+    coords[pv] = mesh["coords"]
+    out = dict(mesh, e2n=pv[mesh["e2n"][pe]].astype(np.int32), coords=coords)
+    return out, [dict(s, e2l=np.ascontiguousarray(s["e2l"][pe])) for s in spaces]
+
+
 def _lagrange(nodes, t):
     t = np.atleast_1d(t)
     B = np.ones((len(t), len(nodes)))

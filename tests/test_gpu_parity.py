@@ -89,7 +89,7 @@ def test_scalar_grad_2d(ctx, p, kind, perturb):
     _compare(of, gi, _state(mesh, s))
 
 
-@pytest.mark.parametrize("case", ["q2", "q2perm", "q1", "elast", "hex"])
+@pytest.mark.parametrize("case", ["q2", "q2perm", "q2shuffled", "q1", "elast", "hex"])
 def test_patch_assembly_many_patches(ctx, case):
     """Meshes of several patches (PATCH_PE = 128 elements per CTA): interior rows written by the patch,
     interface rows through the staging buffer + fixed-order reduction; essential dofs on top."""
@@ -106,6 +106,9 @@ def test_patch_assembly_many_patches(ctx, case):
         s = G.h1_space(mesh, 1 if case == "q1" else 2, mode=O.GRAD)
         if case == "q2perm":
             s = G.permute_dofs(s, 3)
+        if case == "q2shuffled":  # random element order and vertex numbering, random dof numbering
+            s = G.permute_dofs(s, 4)
+            mesh, (s,) = G.shuffle_mesh(mesh, [s], 8)
         fs = S.minsurf(2, 0.5)
     ess = G.boundary_dofs(mesh, s)[::2] if case == "q2" else ()
     of, gi = S.make_pair(ctx, mesh, [s], fs, ess=ess, block=(1 if case == "elast" else None))
