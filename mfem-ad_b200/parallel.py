@@ -116,23 +116,33 @@ class SharedDofExchange:
             vec.index_copy_(0, idx_t.long(), src)
 
     def _exchange(self, vec, send, recv, add, tag):
-        ops, rbufs = [], []
-        for r in self.peers:
-            if r in send:
-                it = self._idx(("s", tag, r), send[r])
-                sb = self._buf(("s", tag, r), it.numel())
-                self._pack(vec, it, sb)
-                ops.append(dist.P2POp(dist.isend, sb, r, self.group))
-            if r in recv:
-                it = self._idx(("r", tag, r), recv[r])
-                rb = self._buf(("r", tag, r), it.numel())
-                ops.append(dist.P2POp(dist.irecv, rb, r, self.group))
-                rbufs.append((it, rb))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        for it, rb in rbufs:  # ascending peer rank: fixed summation order
-            self._unpack(vec, it, rb, add)
+        """One all-to-all-v (ncclGroup of send/recv pairs in which EVERY rank takes part, empty messages for
+        non-neighbours) instead of hand-built point-to-point batches: the same traffic, but the collective is
+        symmetric across ranks, which NCCL's lazy connection set-up requires at more than two ranks."""
+        key = ("a2a", tag)
+        if key not in self._bufs:
+            scount = [len(send[r]) if r in send else 0 for r in range(self.world)]
+            rcount = [len(recv[r]) if r in recv else 0 for r in range(self.world)]
+            sidx = np.concatenate([send[r] for r in range(self.world) if r in send]) if sum(scount) else np.zeros(0, np.int64)
+            ridx = np.concatenate([recv[r] for r in range(self.world) if r in recv]) if sum(rcount) else np.zeros(0, np.int64)
+            self._bufs[key] = (scount, rcount,
+                               torch.from_numpy(np.ascontiguousarray(sidx, dtype=np.int32)).to(self.device),
+                               torch.from_numpy(np.ascontiguousarray(ridx, dtype=np.int32)).to(self.device),
+                               torch.empty(max(sum(scount), 1), dtype=torch.float64, device=self.device),
+                               torch.empty(max(sum(rcount), 1), dtype=torch.float64, device=self.device))
+        scount, rcount, sidx, ridx, sbuf, rbuf = self._bufs[key]
+        ns, nr = sum(scount), sum(rcount)
+        if ns:
+            self._pack(vec, sidx, sbuf[:ns])
+        dist.all_to_all_single(rbuf[:nr], sbuf[:ns], rcount, scount, group=self.group)
+        if nr:
+            # received segments are ordered by ascending peer rank: fixed summation order.  A dof received from
+            # several sharers (a corner) appears once per peer; unpack peer by peer so that no two threads collide.
+            off = 0
+            for r in range(self.world):
+                if rcount[r]:
+                    self._unpack(vec, ridx[off:off + rcount[r]], rbuf[off:off + rcount[r]], add)
+                    off += rcount[r]
 
     def reduce_to_owner(self, y):
         """P^T: the owner's copy becomes the sum over all sharers (own value first, then ascending rank)."""
