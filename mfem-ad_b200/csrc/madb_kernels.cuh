@@ -173,7 +173,9 @@ __device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const
 }
 
 /// Contribution of one quadrature point to the element vector / matrix / energy.
-template <class Func, class Cfg, int MODE>
+/// B0, B1: only the matrix entries (a, b), a <= b, with b in [B0, B1) are accumulated (a thread may own a
+/// slice of the upper triangle: large element matrices are split over several threads, see k_element).
+template <class Func, class Cfg, int MODE, int B0 = 0, int B1 = Cfg::NVD>
 __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q, const int t,
                                        const double (&X)[Cfg::NGN][Cfg::DIM],
                                        const double (&u)[Cfg::NDOF_ALL],
@@ -413,6 +415,7 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
                   }
                   if constexpr ((MODE & MODE_JAC) != 0)
                   {
+                     if (b < B0 || b >= B1) { continue; }
                      // tcol[m] = sum_k H^[m][sb+k] bv[k]
                      ZD tcol[N];
 #pragma unroll
@@ -710,8 +713,9 @@ template <class Func, class Cfg, int MODE> constexpr bool use_sf2d()
 #endif
 }
 
-/// Gather + quadrature loop of sorted element t: element vector r, upper triangle of the element matrix A.
-template <class Func, class Cfg, int MODE, bool UNROLLQ>
+/// Gather + quadrature loop of sorted element t: element vector r, upper triangle of the element matrix A
+/// (columns b in [B0, B1) only).
+template <class Func, class Cfg, int MODE, bool UNROLLQ, int B0 = 0, int B1 = Cfg::NVD>
 __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, const int t,
                                                 double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
                                                 double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1], double &energy)
@@ -777,33 +781,46 @@ __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, con
    if constexpr (UNROLLQ)
    {
 #pragma unroll
-      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE>(a, q, t, X, u, vdir, f, r, A, energy); }
+      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, q, t, X, u, vdir, f, r, A, energy); }
    }
    else
    {
 #pragma unroll 1
-      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE>(a, q, t, X, u, vdir, f, r, A, energy); }
+      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, q, t, X, u, vdir, f, r, A, energy); }
    }
 }
 
-template <class Func, class Cfg, int MODE, bool UNROLLQ>
-__global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs<Func, Cfg> a)
+/// first column of slice k when the upper triangle of an n x n matrix is cut into nparts slices of about equal size
+MADB_HD constexpr int tri_split(int n, int nparts, int k)
+{
+   int b = 0;
+   while (b < n && b * (b + 1) / 2 * nparts < k * (n * (n + 1) / 2)) { b++; }
+   return k >= nparts ? n : b;
+}
+/// threads per element in the colour-scatter kernel: large element matrices (ex4 / ex5 blocks, order-2
+/// elasticity) are split so that a thread's slice of the upper triangle stays in registers
+template <class Cfg, int MODE> constexpr int element_parts() { return ((MODE & MODE_JAC) != 0 && Cfg::NVD > 12) ? 4 : 1; }
+
+/// compute + colour scatter of slice PART of NPART of sorted element t
+template <class Func, class Cfg, int MODE, bool UNROLLQ, int PART, int NPART>
+__device__ __forceinline__ void element_body(const AsmArgs<Func, Cfg> &a, const int t)
 {
    constexpr int NVD = Cfg::NVD;
-   const int t = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
-   if (t >= a.end) { return; }
-   double r[(MODE & (MODE_RES | MODE_ACT)) ? NVD : 1];
-   double A[(MODE & MODE_JAC) ? Cfg::NSYM : 1];
+   constexpr int B0 = tri_split(NVD, NPART, PART), B1 = tri_split(NVD, NPART, PART + 1);
+   // slices other than the first do not touch the element vector
+   constexpr int PMODE = (PART == 0) ? MODE : (MODE & ~(MODE_RES | MODE_ACT));
+   double r[(PMODE & (MODE_RES | MODE_ACT)) ? NVD : 1];
+   double A[(PMODE & MODE_JAC) ? Cfg::NSYM : 1];
    double energy;
-   element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy);
+   element_compute<Func, Cfg, PMODE, UNROLLQ, B0, B1>(a, t, r, A, energy);
 
    // ---- scatter --------------------------------------------------------------------
    // Map entries are read through the read-only path in row batches, ahead of the
    // dependent loads/stores, so that a warp keeps NVD independent requests in flight
    // (the first version serialised 81 map-load -> store round trips: 75 % of all
    // stall samples, profiles/r01_v1_k_element.md).
-   if constexpr (MODE == MODE_ENERGY) { a.energy[t] = energy; }
-   if constexpr ((MODE & (MODE_RES | MODE_ACT)) != 0)
+   if constexpr (PMODE == MODE_ENERGY) { a.energy[t] = energy; }
+   if constexpr ((PMODE & (MODE_RES | MODE_ACT)) != 0)
    {
       if (a.write_y)
       {
@@ -818,29 +835,47 @@ __global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs
          for (int i = 0; i < NVD; i++) { y[m[i] & 0x7fffffff] = old[i] + r[i]; }
       }
    }
-   if constexpr ((MODE & MODE_JAC) != 0)
+   if constexpr ((PMODE & MODE_JAC) != 0)
    {
       if (a.write_vals)
       {
          double *__restrict__ vals = a.vals;
          const int *__restrict__ e2csr = a.e2csr + t;
-         int m[2][NVD];
-#pragma unroll
-         for (int j = 0; j < NVD; j++) { m[0][j] = __ldg(e2csr + (size_t)j * a.stride); }
+         // entries (i, j) of this slice: max(i, j) in [B0, B1)
 #pragma unroll
          for (int i = 0; i < NVD; i++)
          {
-            if (i + 1 < NVD)
-            {
-#pragma unroll
-               for (int j = 0; j < NVD; j++) { m[(i + 1) & 1][j] = __ldg(e2csr + (size_t)((i + 1) * NVD + j) * a.stride); }
-            }
+            const int j0 = (i >= B0) ? 0 : B0, j1 = (i >= B1) ? 0 : B1;
+            int m[NVD];
             double old[NVD];
 #pragma unroll
-            for (int j = 0; j < NVD; j++) { old[j] = (m[i & 1][j] < 0) ? 0.0 : vals[m[i & 1][j] & 0x7fffffff]; }
+            for (int j = 0; j < NVD; j++) { if (j >= j0 && j < j1) { m[j] = __ldg(e2csr + (size_t)(i * NVD + j) * a.stride); } }
 #pragma unroll
-            for (int j = 0; j < NVD; j++) { vals[m[i & 1][j] & 0x7fffffff] = old[j] + A[symidx(i, j)]; }
+            for (int j = 0; j < NVD; j++) { if (j >= j0 && j < j1) { old[j] = (m[j] < 0) ? 0.0 : vals[m[j] & 0x7fffffff]; } }
+#pragma unroll
+            for (int j = 0; j < NVD; j++) { if (j >= j0 && j < j1) { vals[m[j] & 0x7fffffff] = old[j] + A[symidx(i, j)]; } }
          }
+      }
+   }
+}
+
+/// Colour-scatter kernel: one launch per colour, blockIdx.y = slice of the element matrix (element_parts).
+template <class Func, class Cfg, int MODE, bool UNROLLQ>
+__global__ void __launch_bounds__(128) k_element(const __grid_constant__ AsmArgs<Func, Cfg> a)
+{
+   constexpr int NPART = element_parts<Cfg, MODE>();
+   const int t = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+   if (t >= a.end) { return; }
+   if constexpr (NPART == 1) { element_body<Func, Cfg, MODE, UNROLLQ, 0, 1>(a, t); }
+   else
+   {
+      static_assert(NPART == 4, "slices are dispatched on blockIdx.y");
+      switch (blockIdx.y)
+      {
+         case 0: element_body<Func, Cfg, MODE, UNROLLQ, 0, 4>(a, t); break;
+         case 1: element_body<Func, Cfg, MODE, UNROLLQ, 1, 4>(a, t); break;
+         case 2: element_body<Func, Cfg, MODE, UNROLLQ, 2, 4>(a, t); break;
+         default: element_body<Func, Cfg, MODE, UNROLLQ, 3, 4>(a, t); break;
       }
    }
 }

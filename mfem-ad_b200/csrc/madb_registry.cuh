@@ -86,7 +86,9 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
       switch (mode)
       {
          case MODE_RES: k_element<Func, Cfg, MODE_RES, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
-         case MODE_RES | MODE_JAC: k_element<Func, Cfg, MODE_RES | MODE_JAC, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
+         case MODE_RES | MODE_JAC:
+            k_element<Func, Cfg, MODE_RES | MODE_JAC, UNROLLQ><<<dim3(grid, element_parts<Cfg, MODE_RES | MODE_JAC>()), 128, 0, L.stream>>>(a);
+            break;
          case MODE_ACT: k_element<Func, Cfg, MODE_ACT, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
          case MODE_ENERGY: k_element<Func, Cfg, MODE_ENERGY, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
          case MODE_COEF: k_element<Func, Cfg, MODE_COEF, UNROLLQ><<<grid, 128, 0, L.stream>>>(a); break;
