@@ -24,12 +24,16 @@ enum { MODE_RES = 1, MODE_JAC = 2, MODE_ACT = 4, MODE_ENERGY = 8, MODE_COEF = 16
 // summed from its sources in a fixed order and written once, coalesced, to y / the CSR values.
 // Rows shared with other patches ("interface") go to a staging buffer and are summed in
 // ascending patch order by a second small kernel.
-constexpr int PATCH_PE = 128;
+constexpr int PATCH_PE = 128;          // elements per patch (small element matrices, one thread per element)
 constexpr int PATCH_LD = PATCH_PE + 1; // leading dimension of the staged element data (bank spread)
+constexpr int PATCH_PE_LARGE = 64;     // element matrices with more than 10 dofs: smaller patches, 4 threads per element
+/// elements per patch / staging leading dimension for an element matrix of nvd dofs
+constexpr int patch_pe(int nvd) { return nvd <= 10 ? PATCH_PE : PATCH_PE_LARGE; }
+constexpr int patch_ld(int nvd) { return patch_pe(nvd) + 1; }
 constexpr int PATCH_MAXEXTRA = 7;      // a slot has 1 + at most 7 sources (3-bit count)
 inline constexpr int patch_al16(int bytes) { return (bytes + 15) & ~15; }
 // the staged element matrices of one patch must fit in shared memory, two CTAs per SM
-constexpr bool patch_eligible(int nvd) { return nvd <= 10; }
+constexpr bool patch_eligible(int nvd) { return nvd <= 20; }
 struct PatchDesc
 {
    int ne;                    // elements of this patch (all PATCH_PE except possibly the last patch)
@@ -217,6 +221,7 @@ struct Integrator
 
    // patch assembly
    bool use_patches = false;
+   int pe = PATCH_PE;           // elements per patch (patch_pe(nvd))
    std::vector<PatchDesc> pdesc;
    std::vector<int> prows;      // concatenated local row lists (global dof ids), per patch [nrows]
    std::vector<int> prow_off;   // [npatch+1]

@@ -87,7 +87,7 @@ static void rcb(std::vector<int> &idx, int lo, int hi, const std::vector<double>
 // Patch order: fills I.perm (sorted position -> element) and I.pdesc[p].ne.
 void patch_order(Integrator &I)
 {
-   const int ne = I.ne, dim = I.mesh->dim, ngn = 1 << dim, pe = PATCH_PE;
+   const int ne = I.ne, dim = I.mesh->dim, ngn = 1 << dim, pe = I.pe;
    std::vector<double> cen((size_t)ne * 3, 0.0);
    for (int e = 0; e < ne; e++)
    {
@@ -184,7 +184,7 @@ void group_by_dst(std::vector<std::pair<int, int>> &tup, PatchHost &H)
 // Residual side: local rows per patch (interior / interface), row sources, interface reduction lists.
 bool patch_build_y(Integrator &I, PatchHost &H)
 {
-   const int ne = I.ne, nvd = I.nvd, pe = PATCH_PE, np = (int)I.pdesc.size();
+   const int ne = I.ne, nvd = I.nvd, pe = I.pe, ld = I.pe + 1, np = (int)I.pdesc.size();
    // which patches touch a dof: first patch id, or -2 when more than one
    std::vector<int> owner(I.ntotal, -1);
    {
@@ -239,7 +239,7 @@ bool patch_build_y(Integrator &I, PatchHost &H)
                int lr;
                if (owner[v] != -2) { lr = (int)(std::lower_bound(R.begin(), R.begin() + D.nrow_int, v) - R.begin()); }
                else { lr = (int)(std::lower_bound(R.begin() + D.nrow_int, R.end(), v) - R.begin()); }
-               srcs[lr].push_back((unsigned short)(i * PATCH_LD + l));
+               srcs[lr].push_back((unsigned short)(i * ld + l));
             }
          }
          if (!pack_sources(srcs, D.nrows, first, fold)) { ok = false; continue; }
@@ -289,7 +289,7 @@ bool patch_build_y(Integrator &I, PatchHost &H)
 // and are written straight to the CSR array; only the third goes through staging.
 bool patch_build_v(Integrator &I, PatchHost &H)
 {
-   const int nvd = I.nvd, pe = PATCH_PE, np = (int)I.pdesc.size();
+   const int nvd = I.nvd, pe = I.pe, ld = I.pe + 1, np = (int)I.pdesc.size();
    std::vector<std::vector<unsigned char>> blobs(np);
    std::vector<std::vector<long>> ifc_keys(np);  // (local row << 32 | column dof), sorted
    std::vector<std::vector<int>> ifc_gpos(np);   // CSR position of each key
@@ -411,7 +411,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
                   }
                   const int lo_ = std::min(i, j), hi_ = std::max(i, j);
                   const int k = hi_ * (hi_ + 1) / 2 + lo_; // symidx (madb_kernels.cuh)
-                  srcs[slot].push_back((unsigned short)(k * PATCH_LD + l));
+                  srcs[slot].push_back((unsigned short)(k * ld + l));
                }
             }
          }

@@ -70,7 +70,7 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
                                             const int dbg = 0)
 {
    (void)dbg;
-   static_assert(32 % ((NT / 32) * U) == 0 || ((NT / 32) * U) % 32 == 0, "chunk tables are padded to multiples of 32 chunks");
+   static_assert(NT % 32 == 0 && 32 % ((NT / 32) * U) == 0, "chunk tables are padded to multiples of 32 chunks");
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
 #define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
    const int nrows = D.nrows, nrow_int = D.nrow_int, nexc = D.nexc, nslots = D.nslots;
@@ -195,17 +195,66 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
 #undef MADB_SA
 }
 
-template <class Func, class Cfg, int MODE, bool UNROLLQ>
-__global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmArgs<Func, Cfg> a,
-                                                    const __grid_constant__ PatchDev P)
+/// Element computation of sorted element t (local index l in its patch) by one of NPART threads: slice PART of
+/// the upper triangle (columns [B0, B1), tri_split) is computed and stored to the staging buffer; slice 0 also
+/// produces the element vector.
+template <class Func, class Cfg, int MODE, bool UNROLLQ, int PART, int NPART, int LD>
+__device__ __forceinline__ void patch_compute_stage(const AsmArgs<Func, Cfg> &a, const int t, const int l, const bool wy, const bool wv,
+                                                    unsigned char *smraw, const int o_sa)
 {
-   constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = PATCH_PE, LD = PATCH_LD;
+   constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM;
+   constexpr bool HAS_V = (MODE & MODE_JAC) != 0;
+   constexpr int B0 = tri_split(NVD, NPART, PART), B1 = tri_split(NVD, NPART, PART + 1);
+   constexpr int PMODE = (PART == 0) ? MODE : (MODE & ~(MODE_RES | MODE_ACT));
+   constexpr bool HAS_Y = (PMODE & (MODE_RES | MODE_ACT)) != 0;
+   double r[HAS_Y ? NVD : 1];
+   if constexpr (use_sf2d<Func, Cfg, MODE>() && HAS_V && NPART == 1)
+   {
+      // matrix entries stream from the computation straight into the staging buffer
+      element_compute_sf2d<Func, Cfg, MODE>(a, t, r, [&](int k, double v) { if (wv) { *(double *)(smraw + o_sa + 8 * (k * LD + l)) = v; } });
+   }
+   else
+   {
+      double A[HAS_V ? NSYM : 1];
+      double energy;
+      element_compute<Func, Cfg, PMODE, UNROLLQ, B0, B1>(a, t, r, A, energy);
+      if constexpr (HAS_V)
+      {
+         if (wv)
+         {
+#pragma unroll
+            for (int bb = B0; bb < B1; bb++)
+            {
+#pragma unroll
+               for (int aa = 0; aa <= bb; aa++) { *(double *)(smraw + o_sa + 8 * (symidx(aa, bb) * LD + l)) = A[symidx(aa, bb)]; }
+            }
+         }
+      }
+   }
+   if constexpr (HAS_Y)
+   {
+      if (wy)
+      {
+#pragma unroll
+         for (int i = 0; i < NVD; i++) { *(double *)(smraw + 8 * (i * LD + l)) = r[i]; }
+      }
+   }
+}
+
+/// One CTA per patch: PE = patch_pe(NVD) elements, NPART = element_parts threads per element.
+template <class Func, class Cfg, int MODE, bool UNROLLQ>
+__global__ void __launch_bounds__(patch_pe(Cfg::NVD) * element_parts<Cfg, MODE>())
+   k_patch(const __grid_constant__ AsmArgs<Func, Cfg> a, const __grid_constant__ PatchDev P)
+{
+   constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = patch_pe(NVD), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
+   constexpr int NT = PE * NPART;
    constexpr bool HAS_Y = (MODE & (MODE_RES | MODE_ACT)) != 0, HAS_V = (MODE & MODE_JAC) != 0;
    constexpr int SR_BYTES = patch_al16(NVD * LD * 8), SA_BYTES = patch_al16(NSYM * LD * 8);
    extern __shared__ __align__(16) unsigned char smraw[];
    __shared__ PatchDesc D;
    __shared__ __align__(8) unsigned long long mbar;
    const int tid = threadIdx.x, p = blockIdx.x;
+   const int l = tid % PE, part = tid / PE;
    if (tid < (int)(sizeof(PatchDesc) / sizeof(int))) { ((int *)&D)[tid] = ((const int *)(P.desc + p))[tid]; }
    if (tid == 0) { mbar_init(&mbar, 1); }
    __syncthreads();
@@ -215,8 +264,6 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
    const int o_sa = wy ? SR_BYTES : 0;
    const int o_yb = o_sa + (wv ? SA_BYTES : 0);
    const int o_vb = o_yb + (wy ? P.max_yblob : 0);
-#define MADB_SR(i) (*(double *)(smraw + 8 * (i)))
-#define MADB_SA(i) (*(double *)(smraw + o_sa + 8 * (i)))
    if (tid == 0)
    {
       const unsigned bytes = (wy ? D.yblob_bytes : 0) + (wv ? D.vblob_bytes : 0);
@@ -225,45 +272,26 @@ __global__ void __launch_bounds__(PATCH_PE) k_patch(const __grid_constant__ AsmA
       if (wv && D.vblob_bytes) { bulk_g2s(smraw + o_vb, P.vblob + (size_t)D.vblob_off * 16, D.vblob_bytes, &mbar); }
    }
 
-   const int t = p * PE + tid;
-   const bool valid = tid < D.ne;
-   if (valid)
+   const int t = p * PE + l;
+   if (l < D.ne)
    {
-      double r[HAS_Y ? NVD : 1];
-      if constexpr (use_sf2d<Func, Cfg, MODE>() && HAS_V)
-      {
-         // matrix entries stream from the computation straight into the staging buffer
-         element_compute_sf2d<Func, Cfg, MODE>(a, t, r, [&](int k, double v) { if (wv) { MADB_SA(k * LD + tid) = v; } });
-      }
+      if constexpr (NPART == 1) { patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 0, 1, LD>(a, t, l, wy, wv, smraw, o_sa); }
       else
       {
-         double A[HAS_V ? NSYM : 1];
-         double energy;
-         element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy);
-         if constexpr (HAS_V)
+         static_assert(NPART == 4, "slices are dispatched on the warp index");
+         switch (part)
          {
-            if (wv)
-            {
-#pragma unroll
-               for (int k = 0; k < NSYM; k++) { MADB_SA(k * LD + tid) = A[k]; }
-            }
-         }
-      }
-      if constexpr (HAS_Y)
-      {
-         if (wy)
-         {
-#pragma unroll
-            for (int i = 0; i < NVD; i++) { MADB_SR(i * LD + tid) = r[i]; }
+            case 0: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 0, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
+            case 1: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 1, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
+            case 2: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 2, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
+            default: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 3, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
          }
       }
    }
    __syncthreads();
    mbar_wait(&mbar, 0);
-
-   patch_drain<0, PATCH_PE, 4>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
-#undef MADB_SR
-#undef MADB_SA
+   constexpr int NW = NT / 32, U = (32 / NW < 8) ? 32 / NW : 8;
+   patch_drain<0, NT, U>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
 }
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
@@ -453,8 +481,10 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    static int smem_set = 0;
    auto kern = k_patch<Func, Cfg, MODE, UNROLLQ>;
    const bool wy = (MODE & (MODE_RES | MODE_ACT)) && L.write_y, wv = (MODE & MODE_JAC) && L.write_vals;
-   const int smem_bytes = (wy ? patch_al16(Cfg::NVD * PATCH_LD * 8) + P.max_yblob : 0) +
-                          (wv ? patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_vblob : 0) + 16;
+   constexpr int PE = patch_pe(Cfg::NVD), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
+   const int smem_bytes = (wy ? patch_al16(Cfg::NVD * LD * 8) + P.max_yblob : 0) +
+                          (wv ? patch_al16(Cfg::NSYM * LD * 8) + P.max_vblob : 0) + 16;
+   if (smem_bytes > 224 * 1024) { return (int)cudaErrorInvalidConfiguration; }
    if (smem_bytes > smem_set)
    {
       const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -463,7 +493,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    }
    if (L.ev0) { cudaEventRecord(L.ev0, L.stream); }
    bool done = false;
-   if constexpr (MODE == (MODE_RES | MODE_JAC))
+   if constexpr (MODE == (MODE_RES | MODE_JAC) && PE == PATCH_PE && NPART == 1)
    {
       static const bool use_ws = getenv("MADB_PATCH_WS") ? atoi(getenv("MADB_PATCH_WS")) != 0 : true;
       if (wv && use_ws)
@@ -491,7 +521,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
          }
       }
    }
-   if (!done) { kern<<<P.npatch, PATCH_PE, smem_bytes, L.stream>>>(a, P); }
+   if (!done) { kern<<<P.npatch, PE * NPART, smem_bytes, L.stream>>>(a, P); }
    if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
    {
       IfcList ly = P.ylist, lv = P.vlist;

@@ -213,13 +213,13 @@ static int setup_integrator(Integrator &I)
    I.use_patches = I.ops.patch_ok && !I.ops.map_aos && !getenv("MADB_NO_PATCH");
    if (I.use_patches)
    {
-      I.use_patches = true;
+      I.pe = patch_pe(I.nvd);
       patch_order(I);
       if (I.pdesc.empty()) { I.use_patches = false; }
    }
    if (I.use_patches)
    {
-      I.stride = (int)I.pdesc.size() * PATCH_PE;
+      I.stride = (int)I.pdesc.size() * I.pe;
       I.color_off = {0, I.ne};
    }
    else
