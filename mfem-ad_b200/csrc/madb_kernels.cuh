@@ -94,7 +94,7 @@ MADB_HD constexpr int symidx(int a, int b) { return a <= b ? b * (b + 1) / 2 + a
 /// Everything the functional needs at one quadrature point, then the
 /// contribution of that point to the element vector / matrix.
 template <class Func, class Cfg>
-__device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const int q, const int t,
+__device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const Tables<Cfg> &tab, const int q, const int t,
                                               const double (&X)[Cfg::NGN][Cfg::DIM],
                                               const double (&u)[Cfg::NDOF_ALL],
                                               double (&xin)[Cfg::N_INPUT],
@@ -118,14 +118,14 @@ __device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const
 #pragma unroll
       for (int j = 0; j < DIM; j++)
       {
-         const double g = a.tab.gdphi[q][k][j];
+         const double g = tab.gdphi[q][k][j];
 #pragma unroll
          for (int i = 0; i < DIM; i++) { J[i][j] = fma(X[k][i], g, J[i][j]); }
       }
    }
    double detJ;
    invert<DIM>(J, Ji, detJ);
-   w = a.tab.w[q] * detJ; // ip.weight * Tr.Weight()
+   w = tab.w[q] * detJ; // ip.weight * Tr.Weight()
 
    // ---- inputs x (physical) and field parameters ---------------------------------
    static_for<NF>([&](auto F)
@@ -144,11 +144,11 @@ __device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const
          for (int i = 0; i < nd; i++)
          {
             const double ui = u[doff + c * nd + i];
-            if constexpr (Fd::HAS_VALUE) { val = fma(a.tab.phi[q][toff + i], ui, val); }
+            if constexpr (Fd::HAS_VALUE) { val = fma(tab.phi[q][toff + i], ui, val); }
             if constexpr (Fd::HAS_GRAD)
             {
 #pragma unroll
-               for (int k = 0; k < DIM; k++) { rg[k] = fma(a.tab.dphi[q][toff + i][k], ui, rg[k]); }
+               for (int k = 0; k < DIM; k++) { rg[k] = fma(tab.dphi[q][toff + i][k], ui, rg[k]); }
             }
          }
          double *dst = Cfg::template is_input<fi>() ? (xin + Cfg::template xoff<fi>()) : (qp + Cfg::template poff<fi>());
@@ -176,7 +176,7 @@ __device__ __forceinline__ void qpoint_inputs(const AsmArgs<Func, Cfg> &a, const
 /// B0, B1: only the matrix entries (a, b), a <= b, with b in [B0, B1) are accumulated (a thread may own a
 /// slice of the upper triangle: large element matrices are split over several threads, see k_element).
 template <class Func, class Cfg, int MODE, int B0 = 0, int B1 = Cfg::NVD>
-__device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q, const int t,
+__device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables<Cfg> &tab, const int q, const int t,
                                        const double (&X)[Cfg::NGN][Cfg::DIM],
                                        const double (&u)[Cfg::NDOF_ALL],
                                        const double (&vdir)[(MODE & MODE_ACT) ? Cfg::NVD : 1],
@@ -189,7 +189,7 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
    double xin[N];
    double qp[Func::N_QPRM > 0 ? Func::N_QPRM : 1];
    double Ji[DIM][DIM], w;
-   qpoint_inputs<Func, Cfg>(a, q, t, X, u, xin, qp, Ji, w);
+   qpoint_inputs<Func, Cfg>(a, tab, q, t, X, u, xin, qp, Ji, w);
 
    if constexpr (MODE == MODE_COEF)
    {
@@ -344,11 +344,11 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
                   for (int i = 0; i < nd; i++)
                   {
                      const double vi = vdir[vo + c * nd + i];
-                     if constexpr (Fd::HAS_VALUE) { val = fma(a.tab.phi[q][toff + i], vi, val); }
+                     if constexpr (Fd::HAS_VALUE) { val = fma(tab.phi[q][toff + i], vi, val); }
                      if constexpr (Fd::HAS_GRAD)
                      {
 #pragma unroll
-                        for (int k = 0; k < DIM; k++) { rg[k] = fma(a.tab.dphi[q][toff + i][k], vi, rg[k]); }
+                        for (int k = 0; k < DIM; k++) { rg[k] = fma(tab.dphi[q][toff + i][k], vi, rg[k]); }
                      }
                   }
                   int slot = xo + c * sd;
@@ -387,11 +387,11 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
                double bv[sdb];
                {
                   int s = 0;
-                  if constexpr (Fb::HAS_VALUE) { bv[s++] = a.tab.phi[q][tob + jb]; }
+                  if constexpr (Fb::HAS_VALUE) { bv[s++] = tab.phi[q][tob + jb]; }
                   if constexpr (Fb::HAS_GRAD)
                   {
 #pragma unroll
-                     for (int k = 0; k < DIM; k++) { bv[s + k] = a.tab.dphi[q][tob + jb][k]; }
+                     for (int k = 0; k < DIM; k++) { bv[s + k] = tab.dphi[q][tob + jb][k]; }
                   }
                }
 #pragma unroll
@@ -446,11 +446,11 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const int q,
                                     const int sa = xoa + ca * sda;
                                     ZD s {0.0, true};
                                     int k0 = 0;
-                                    if constexpr (Fa::HAS_VALUE) { s = zfmac(tcol[sa], a.tab.phi[q][toa + ia], s); k0 = 1; }
+                                    if constexpr (Fa::HAS_VALUE) { s = zfmac(tcol[sa], tab.phi[q][toa + ia], s); k0 = 1; }
                                     if constexpr (Fa::HAS_GRAD)
                                     {
 #pragma unroll
-                                       for (int k = 0; k < DIM; k++) { s = zfmac(tcol[sa + k0 + k], a.tab.dphi[q][toa + ia][k], s); }
+                                       for (int k = 0; k < DIM; k++) { s = zfmac(tcol[sa + k0 + k], tab.dphi[q][toa + ia][k], s); }
                                     }
                                     if (!s.z) { A[symidx(aa, b)] += s.v; }
                                  }
@@ -716,7 +716,7 @@ template <class Func, class Cfg, int MODE> constexpr bool use_sf2d()
 /// Gather + quadrature loop of sorted element t: element vector r, upper triangle of the element matrix A
 /// (columns b in [B0, B1) only).
 template <class Func, class Cfg, int MODE, bool UNROLLQ, int B0 = 0, int B1 = Cfg::NVD>
-__device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, const int t,
+__device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, const Tables<Cfg> &tab, const int t,
                                                 double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1],
                                                 double (&A)[(MODE & MODE_JAC) ? Cfg::NSYM : 1], double &energy)
 {
@@ -781,21 +781,49 @@ __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, con
    if constexpr (UNROLLQ)
    {
 #pragma unroll
-      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, q, t, X, u, vdir, f, r, A, energy); }
+      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, tab, q, t, X, u, vdir, f, r, A, energy); }
    }
    else
    {
 #pragma unroll 1
-      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, q, t, X, u, vdir, f, r, A, energy); }
+      for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, tab, q, t, X, u, vdir, f, r, A, energy); }
    }
 }
 
-/// first column of slice k when the upper triangle of an n x n matrix is cut into nparts slices of about equal size
-MADB_HD constexpr int tri_split(int n, int nparts, int k)
+/// shapedim of the field that element-vector index b belongs to
+template <class Cfg, int F = 0> MADB_HD constexpr int sd_of_vdof(int b)
 {
-   int b = 0;
-   while (b < n && b * (b + 1) / 2 * nparts < k * (n * (n + 1) / 2)) { b++; }
-   return k >= nparts ? n : b;
+   if constexpr (F >= Cfg::NF) { return 1; }
+   else
+   {
+      if constexpr (Cfg::template is_input<F>())
+      {
+         constexpr int n = Cfg::template nd<F>() * Cfg::template field<F>::VDIM, vo = Cfg::template voff<F>();
+         if (b >= vo && b < vo + n) { return Cfg::template sd<F>(); }
+      }
+      return sd_of_vdof<Cfg, F + 1>(b);
+   }
+}
+/// FP64 operations per point spent on column b of the upper triangle: tcol (N_INPUT * sd_b) + entries (sum_{a<=b} sd_a)
+template <class Cfg> MADB_HD constexpr int column_cost(int b)
+{
+   int c = Cfg::N_INPUT * sd_of_vdof<Cfg>(b);
+   for (int a = 0; a <= b; a++) { c += sd_of_vdof<Cfg>(a); }
+   return c;
+}
+/// First column of slice k when the upper triangle of the element matrix is cut into nparts slices of about
+/// equal cost; slice 0 also carries the element vector (about 2 sum_b sd_b operations per point).
+template <class Cfg> MADB_HD constexpr int tri_split(int nparts, int k)
+{
+   constexpr int n = Cfg::NVD;
+   if (k >= nparts) { return n; }
+   int res = 0, total = 0;
+   for (int b = 0; b < n; b++) { res += 2 * sd_of_vdof<Cfg>(b); }
+   total = res;
+   for (int b = 0; b < n; b++) { total += column_cost<Cfg>(b); }
+   int cum = res, b = 0;
+   while (b < n && cum * nparts < k * total) { cum += column_cost<Cfg>(b); b++; }
+   return k == 0 ? 0 : b;
 }
 /// threads per element in the colour-scatter kernel: large element matrices (ex4 / ex5 blocks, order-2
 /// elasticity) are split so that a thread's slice of the upper triangle stays in registers
@@ -806,13 +834,13 @@ template <class Func, class Cfg, int MODE, bool UNROLLQ, int PART, int NPART>
 __device__ __forceinline__ void element_body(const AsmArgs<Func, Cfg> &a, const int t)
 {
    constexpr int NVD = Cfg::NVD;
-   constexpr int B0 = tri_split(NVD, NPART, PART), B1 = tri_split(NVD, NPART, PART + 1);
+   constexpr int B0 = tri_split<Cfg>(NPART, PART), B1 = tri_split<Cfg>(NPART, PART + 1);
    // slices other than the first do not touch the element vector
    constexpr int PMODE = (PART == 0) ? MODE : (MODE & ~(MODE_RES | MODE_ACT));
    double r[(PMODE & (MODE_RES | MODE_ACT)) ? NVD : 1];
    double A[(PMODE & MODE_JAC) ? Cfg::NSYM : 1];
    double energy;
-   element_compute<Func, Cfg, PMODE, UNROLLQ, B0, B1>(a, t, r, A, energy);
+   element_compute<Func, Cfg, PMODE, UNROLLQ, B0, B1>(a, a.tab, t, r, A, energy);
 
    // ---- scatter --------------------------------------------------------------------
    // Map entries are read through the read-only path in row batches, ahead of the

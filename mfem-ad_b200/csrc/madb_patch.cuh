@@ -199,12 +199,12 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
 /// the upper triangle (columns [B0, B1), tri_split) is computed and stored to the staging buffer; slice 0 also
 /// produces the element vector.
 template <class Func, class Cfg, int MODE, bool UNROLLQ, int PART, int NPART, int LD>
-__device__ __forceinline__ void patch_compute_stage(const AsmArgs<Func, Cfg> &a, const int t, const int l, const bool wy, const bool wv,
-                                                    unsigned char *smraw, const int o_sa)
+__device__ __forceinline__ void patch_compute_stage(const AsmArgs<Func, Cfg> &a, const Tables<Cfg> &tab, const int t, const int l,
+                                                    const bool wy, const bool wv, unsigned char *smraw, const int o_sa)
 {
    constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM;
    constexpr bool HAS_V = (MODE & MODE_JAC) != 0;
-   constexpr int B0 = tri_split(NVD, NPART, PART), B1 = tri_split(NVD, NPART, PART + 1);
+   constexpr int B0 = tri_split<Cfg>(NPART, PART), B1 = tri_split<Cfg>(NPART, PART + 1);
    constexpr int PMODE = (PART == 0) ? MODE : (MODE & ~(MODE_RES | MODE_ACT));
    constexpr bool HAS_Y = (PMODE & (MODE_RES | MODE_ACT)) != 0;
    double r[HAS_Y ? NVD : 1];
@@ -217,7 +217,7 @@ __device__ __forceinline__ void patch_compute_stage(const AsmArgs<Func, Cfg> &a,
    {
       double A[HAS_V ? NSYM : 1];
       double energy;
-      element_compute<Func, Cfg, PMODE, UNROLLQ, B0, B1>(a, t, r, A, energy);
+      element_compute<Func, Cfg, PMODE, UNROLLQ, B0, B1>(a, tab, t, r, A, energy);
       if constexpr (HAS_V)
       {
          if (wv)
@@ -254,6 +254,7 @@ __global__ void __launch_bounds__(patch_pe(Cfg::NVD) * element_parts<Cfg, MODE>(
    __shared__ PatchDesc D;
    __shared__ __align__(8) unsigned long long mbar;
    const int tid = threadIdx.x, p = blockIdx.x;
+   // thread -> (local element l, slice part): threads [part * PE, (part + 1) * PE) compute slice `part` of the PE elements
    const int l = tid % PE, part = tid / PE;
    if (tid < (int)(sizeof(PatchDesc) / sizeof(int))) { ((int *)&D)[tid] = ((const int *)(P.desc + p))[tid]; }
    if (tid == 0) { mbar_init(&mbar, 1); }
@@ -271,20 +272,34 @@ __global__ void __launch_bounds__(patch_pe(Cfg::NVD) * element_parts<Cfg, MODE>(
       if (wy && D.yblob_bytes) { bulk_g2s(smraw + o_yb, P.yblob + (size_t)D.yblob_off * 16, D.yblob_bytes, &mbar); }
       if (wv && D.vblob_bytes) { bulk_g2s(smraw + o_vb, P.vblob + (size_t)D.vblob_off * 16, D.vblob_bytes, &mbar); }
    }
+   // When the quadrature loop is not unrolled the basis tables are indexed dynamically: constant-bank loads (LDC)
+   // of warps running different slices thrash the constant cache (measured: 2x on the ex4 block), so the tables
+   // are copied to shared memory once per CTA.
+   constexpr bool TAB_SMEM = !UNROLLQ && !use_sf2d<Func, Cfg, MODE>();
+   const Tables<Cfg> *tabp = &a.tab;
+   if constexpr (TAB_SMEM)
+   {
+      double *dst = (double *)(smraw + o_vb + (wv ? P.max_vblob : 0));
+      const double *src = (const double *)&a.tab;
+      for (int k = tid; k < (int)(sizeof(Tables<Cfg>) / sizeof(double)); k += NT) { dst[k] = src[k]; }
+      tabp = (const Tables<Cfg> *)dst;
+      __syncthreads();
+   }
+   const Tables<Cfg> &tab = *tabp;
 
    const int t = p * PE + l;
    if (l < D.ne)
    {
-      if constexpr (NPART == 1) { patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 0, 1, LD>(a, t, l, wy, wv, smraw, o_sa); }
+      if constexpr (NPART == 1) { patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 0, 1, LD>(a, tab, t, l, wy, wv, smraw, o_sa); }
       else
       {
          static_assert(NPART == 4, "slices are dispatched on the warp index");
          switch (part)
          {
-            case 0: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 0, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
-            case 1: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 1, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
-            case 2: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 2, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
-            default: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 3, 4, LD>(a, t, l, wy, wv, smraw, o_sa); break;
+            case 0: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 0, 4, LD>(a, tab, t, l, wy, wv, smraw, o_sa); break;
+            case 1: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 1, 4, LD>(a, tab, t, l, wy, wv, smraw, o_sa); break;
+            case 2: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 2, 4, LD>(a, tab, t, l, wy, wv, smraw, o_sa); break;
+            default: patch_compute_stage<Func, Cfg, MODE, UNROLLQ, 3, 4, LD>(a, tab, t, l, wy, wv, smraw, o_sa); break;
          }
       }
    }
@@ -370,7 +385,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          else
          {
             double A[NSYM], energy;
-            if (valid) { element_compute<Func, Cfg, MODE, UNROLLQ>(a, t, r, A, energy); }
+            if (valid) { element_compute<Func, Cfg, MODE, UNROLLQ>(a, a.tab, t, r, A, energy); }
             mbar_wait(&bar_empty[w], par);
             if (valid)
             {
@@ -482,8 +497,9 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    auto kern = k_patch<Func, Cfg, MODE, UNROLLQ>;
    const bool wy = (MODE & (MODE_RES | MODE_ACT)) && L.write_y, wv = (MODE & MODE_JAC) && L.write_vals;
    constexpr int PE = patch_pe(Cfg::NVD), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
+   constexpr bool TAB_SMEM = !UNROLLQ && !use_sf2d<Func, Cfg, MODE>();
    const int smem_bytes = (wy ? patch_al16(Cfg::NVD * LD * 8) + P.max_yblob : 0) +
-                          (wv ? patch_al16(Cfg::NSYM * LD * 8) + P.max_vblob : 0) + 16;
+                          (wv ? patch_al16(Cfg::NSYM * LD * 8) + P.max_vblob : 0) + (TAB_SMEM ? (int)sizeof(Tables<Cfg>) : 0) + 16;
    if (smem_bytes > 224 * 1024) { return (int)cudaErrorInvalidConfiguration; }
    if (smem_bytes > smem_set)
    {
