@@ -11,6 +11,7 @@ using SIMP5 = SIMPFunction<5>;
 using Elast2 = LinearElasticityEnergy<2>;
 using Elast3 = LinearElasticityEnergy<3>;
 using PGObsFD = PGFunctional<ObstacleEnergy<2>, FermiDiracEntropy, 0>;
+using LamPGObsFD = LambdaPGFunctional<ObstacleEnergy<2>, FermiDiracEntropy, 0>;
 
 MADB_EVAL_INSTANCE("ex0", Ex0Function)
 MADB_EVAL_INSTANCE("minsurf", MinS2)
@@ -23,3 +24,4 @@ MADB_EVAL_INSTANCE("simp", SIMP5)
 MADB_EVAL_INSTANCE("elasticity", Elast2)
 MADB_EVAL_INSTANCE("elasticity", Elast3)
 MADB_EVAL_INSTANCE("pg:0[obstacle,fermidirac]", PGObsFD)
+MADB_EVAL_INSTANCE("lambdapg:0[obstacle,fermidirac]", LamPGObsFD)

@@ -13,6 +13,9 @@ using PGGrad = PGFunctional<GradientObstacleEnergy<2>, HellingerEntropy<2>, 0>;
 // ex4 -o 1: H1 p2 x L2 p0, rule order 6 -> 4x4 ; ex4 -o 2 (default, config 5): H1 p3 x L2 p1, order 9 -> 5x5
 using Ex4o1 = Config<2, 4, Field<3, 1, EV_VALUE | EV_GRAD>, Field<1, 1, EV_VALUE>, Field<1, 1, EV_VALUE, ROLE_PARAM>>;
 using Ex4o2 = Config<2, 5, Field<4, 1, EV_VALUE | EV_GRAD>, Field<2, 1, EV_VALUE>, Field<2, 1, EV_VALUE, ROLE_PARAM>>;
+// ADLambdaPGFunctional (src/pg.hpp:216-243; unused by the reference's drivers): the lambda form on the ex4 -o 1 spaces
+using LamPGObs = LambdaPGFunctional<ObstacleEnergy<2>, FermiDiracEntropy, 0>;
+MADB_INSTANCE("lambdapg:0[obstacle,fermidirac]", LamPGObs, Ex4o1, false)
 MADB_INSTANCE("pg:0[obstacle,fermidirac]", PGObs, Ex4o1, false)
 MADB_INSTANCE("pg:0[obstacle,fermidirac]", PGObs, Ex4o2, false)
 

@@ -91,6 +91,11 @@ def pg(f, entropy, alpha, primal_idx=0):
     return FSpec("pg", f.n_input + entropy.n_input, [alpha], [primal_idx], [f, entropy], qoff=0)
 
 
+def lambdapg(f, entropy, alpha, primal_idx=0):
+    """ADLambdaPGFunctional(f, entropy, psi_k, idx) (src/pg.hpp:216-243): inputs [x, lambda]."""
+    return FSpec("lambdapg", f.n_input + entropy.n_input, [alpha], [primal_idx], [f, entropy], qoff=0)
+
+
 def make_pair(ctx, mesh, spaces, fspec, quad_order=-1, params=(), ess=(), block=None):
     """Builds (oracle form, CUDA integrator) from the same arrays.
 
