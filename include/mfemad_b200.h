@@ -129,6 +129,10 @@ int madb_lvpp_update(madb_ctx *ctx, int n, double alpha, const double *psi, doub
  * the transfer itself is NCCL send/recv between neighbours (mfem-ad_b200/parallel.py). */
 int madb_pack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, double *dst);
 int madb_unpack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, double *dst, int add);
+/* Unpack of a whole receive buffer in one launch: destination i = dst_idx[i] gets the values src[src4[4i..4i+3]]
+ * (-1: none) added in that order (ascending peer rank: deterministic), on top of the old value if add != 0.
+ * A dof shared by several ranks (a corner) has one destination entry with several sources. */
+int madb_unpack_multi(madb_ctx *ctx, int n, const int32_t *src4, const int32_t *dst_idx, const double *src, double *dst, int add);
 
 /* AD(Block)NonlinearFormIntegrator<modes...>(f, ir) attached to its form
  * (src/_ad_intg.hpp:71-155, :157-327).  fields: spaces[i] with ADEval modes[i];

@@ -59,6 +59,7 @@ def lib():
         L.madb_dofpg_nodal.argtypes = [vp, vp, C.c_int, C.c_double, dp, dp, dp, dp, dp, dp, dp, dp]
         L.madb_pack.argtypes = [vp, C.c_int, ip, dp, dp]
         L.madb_unpack.argtypes = [vp, C.c_int, ip, dp, dp, C.c_int]
+        L.madb_unpack_multi.argtypes = [vp, C.c_int, ip, ip, dp, dp, C.c_int]
         L.madb_lvpp_update.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_double)]
         L.madb_integrator_create.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, pp]
         L.madb_integrator_destroy.argtypes = [vp]

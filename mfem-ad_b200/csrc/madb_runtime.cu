@@ -132,6 +132,21 @@ __global__ void k_unpack(int n, const int *idx, const double *src, double *dst, 
    if (i < n) { dst[idx[i]] = add ? dst[idx[i]] + src[i] : src[i]; }
 }
 
+__global__ void k_unpack_multi(int n, const int4 *__restrict__ src4, const int *__restrict__ idx, const double *__restrict__ src,
+                               double *dst, int add)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) { return; }
+   const int4 s = src4[i];
+   const int d = idx[i];
+   const double a0 = src[s.x], a1 = (s.y >= 0) ? src[s.y] : 0.0, a2 = (s.z >= 0) ? src[s.z] : 0.0, a3 = (s.w >= 0) ? src[s.w] : 0.0;
+   double v = add ? dst[d] + a0 : a0;
+   if (s.y >= 0) { v += a1; }
+   if (s.z >= 0) { v += a2; }
+   if (s.w >= 0) { v += a3; }
+   dst[d] = v;
+}
+
 // y[ess] = 0  (NonlinearForm::Mult [MFEM-upstream])
 __global__ void k_ess_zero(const int *ess, int n, double *y)
 {
@@ -737,6 +752,15 @@ extern "C"
       if (n <= 0) { return 0; }
       CUDA_OK(cudaSetDevice(ctx->device));
       k_unpack<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, idx, src, dst, add);
+      CUDA_OK(cudaGetLastError());
+      return 0;
+   }
+
+   int madb_unpack_multi(madb_ctx *ctx, int n, const int32_t *src4, const int32_t *dst_idx, const double *src, double *dst, int add)
+   {
+      if (n <= 0) { return 0; }
+      CUDA_OK(cudaSetDevice(ctx->device));
+      k_unpack_multi<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, (const int4 *)src4, dst_idx, src, dst, add);
       CUDA_OK(cudaGetLastError());
       return 0;
    }

@@ -118,31 +118,47 @@ class SharedDofExchange:
     def _exchange(self, vec, send, recv, add, tag):
         """One all-to-all-v (ncclGroup of send/recv pairs in which EVERY rank takes part, empty messages for
         non-neighbours) instead of hand-built point-to-point batches: the same traffic, but the collective is
-        symmetric across ranks, which NCCL's lazy connection set-up requires at more than two ranks."""
+        symmetric across ranks, which NCCL's lazy connection set-up requires at more than two ranks.
+        Pack and unpack are one kernel each; a dof received from several sharers (a corner) is one destination
+        with its sources in ascending peer rank: fixed summation order."""
         key = ("a2a", tag)
         if key not in self._bufs:
             scount = [len(send[r]) if r in send else 0 for r in range(self.world)]
             rcount = [len(recv[r]) if r in recv else 0 for r in range(self.world)]
             sidx = np.concatenate([send[r] for r in range(self.world) if r in send]) if sum(scount) else np.zeros(0, np.int64)
             ridx = np.concatenate([recv[r] for r in range(self.world) if r in recv]) if sum(rcount) else np.zeros(0, np.int64)
+            # destinations with their receive-buffer positions (ascending position = ascending peer)
+            order = np.argsort(ridx, kind="stable")
+            dst, start = np.unique(ridx[order], return_index=True)
+            counts = np.diff(np.append(start, ridx.size))
+            assert counts.size == 0 or counts.max() <= 4, "a dof shared by more than 5 ranks"
+            src4 = np.full((dst.size, 4), -1, dtype=np.int32)
+            for k in range(4):
+                m = counts > k
+                src4[m, k] = order[start[m] + k]
             self._bufs[key] = (scount, rcount,
                                torch.from_numpy(np.ascontiguousarray(sidx, dtype=np.int32)).to(self.device),
-                               torch.from_numpy(np.ascontiguousarray(ridx, dtype=np.int32)).to(self.device),
+                               torch.from_numpy(np.ascontiguousarray(dst, dtype=np.int32)).to(self.device),
+                               torch.from_numpy(src4).to(self.device),
                                torch.empty(max(sum(scount), 1), dtype=torch.float64, device=self.device),
                                torch.empty(max(sum(rcount), 1), dtype=torch.float64, device=self.device))
-        scount, rcount, sidx, ridx, sbuf, rbuf = self._bufs[key]
+        scount, rcount, sidx, dst, src4, sbuf, rbuf = self._bufs[key]
         ns, nr = sum(scount), sum(rcount)
         if ns:
             self._pack(vec, sidx, sbuf[:ns])
         dist.all_to_all_single(rbuf[:nr], sbuf[:ns], rcount, scount, group=self.group)
         if nr:
-            # received segments are ordered by ascending peer rank: fixed summation order.  A dof received from
-            # several sharers (a corner) appears once per peer; unpack peer by peer so that no two threads collide.
-            off = 0
-            for r in range(self.world):
-                if rcount[r]:
-                    self._unpack(vec, ridx[off:off + rcount[r]], rbuf[off:off + rcount[r]], add)
-                    off += rcount[r]
+            if vec.is_cuda:
+                from . import lib, _check
+                _check(lib().madb_unpack_multi(self.ctx.h, dst.numel(), src4.data_ptr(), dst.data_ptr(), rbuf.data_ptr(),
+                                               vec.data_ptr(), int(add)))
+            else:
+                d = dst.long()
+                acc = vec[d].clone() if add else torch.zeros(d.numel(), dtype=vec.dtype)
+                for k in range(4):
+                    m = src4[:, k] >= 0
+                    acc[m] = acc[m] + rbuf[src4[m, k].long()]
+                vec[d] = acc
 
     def reduce_to_owner(self, y):
         """P^T: the owner's copy becomes the sum over all sharers (own value first, then ascending rank)."""
