@@ -72,7 +72,6 @@ struct IfcListDev // interface reduction lists of one side (see k_ifc_reduce)
 struct PatchDev
 {
    int npatch;
-   int debug;                // MADB_PATCH_DEBUG: 1 = skip the CSR write-out, 2 = skip the element computation (timing experiments)
    int max_yblob, max_vblob; // bytes, shared-memory sizing
    const PatchDesc *desc;
    const unsigned char *yblob, *vblob;

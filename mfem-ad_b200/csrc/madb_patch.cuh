@@ -1,15 +1,20 @@
 // madb_patch.cuh -- patch assembly kernels (device side of madb_patch.cpp).
 //
-// One CTA = one patch of PATCH_PE elements, one thread per element:
+// A patch = patch_pe(NVD) elements of the mesh (128, or 64 for element matrices of 11-20 dofs).  For one patch:
 //   0. one elected thread starts bulk copies (cp.async.bulk, mbarrier completion) of the
-//      patch's gather maps into shared memory; they land while the CTA computes
-//   1. gather + quadrature loop in registers (element_compute, madb_kernels.cuh)
-//   2. every thread stages its element vector / upper-triangular element matrix in
-//      shared memory ([entry][element], padded leading dimension)
-//   3. every row / CSR entry ("slot") of the patch is summed from its sources in ascending
-//      element order and written once, coalesced: interior rows straight to y / the CSR
-//      values (runs of consecutive CSR positions), interface rows to a staging buffer
-//   4. k_ifc_reduce adds the staged partial rows in ascending patch order.
+//      patch's gather maps into shared memory; they land while the threads compute
+//   1. gather + quadrature loop in registers (element_compute / element_compute_sf2d, madb_kernels.cuh):
+//      one thread per element, or 4 threads per element each owning a slice of the upper triangle
+//   2. the element vector / upper-triangular element matrix is staged in shared memory
+//      ([entry][element], padded leading dimension); the sum-factorised path streams its entries there
+//   3. fold: the further sources of every row / CSR entry ("slot") are added onto its first source, phase by
+//      phase (ascending element order); then every slot is read from its first source and written once,
+//      coalesced: interior rows straight to y / the CSR values (chunk descriptors: 32 consecutive slots ->
+//      CSR positions), entries of interface rows only this patch touches through explicit positions,
+//      entries shared with other patches to a staging buffer
+//   4. k_ifc_reduce adds the staged partial rows / entries in ascending patch order.
+// Two kernels: k_patch (one CTA per patch) and k_patch_ws (persistent, warp-specialised: compute warpgroups
+// and writer warpgroups overlap steps 1-2 and 3 of consecutive patches; fused residual + Jacobian).
 // Replaces AddElementVector / SparseMatrix::AddSubMatrix of MFEM's element loop
 //  without atomics and without order dependence.
 #pragma once
@@ -66,10 +71,8 @@ template <int BAR, int NT> __device__ __forceinline__ void patch_bar()
 template <int BAR, int NT, int U>
 __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
                                             const bool wy, const bool wv, const int tid, double *__restrict__ y,
-                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage,
-                                            const int dbg = 0)
+                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage)
 {
-   (void)dbg;
    static_assert(NT % 32 == 0 && 32 % ((NT / 32) * U) == 0, "chunk tables are padded to multiples of 32 chunks");
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
 #define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
          if (p >= P.npatch) { break; }
          const int t = p * PE + tid;
-         const bool valid = t < a.end && !(P.debug & 2);
+         const bool valid = t < a.end;
          double r[NVD];
          const unsigned par = (it & 1) ^ 1; // parity of "the writer has drained the previous patch of this buffer"
          if constexpr (use_sf2d<Func, Cfg, MODE>())
@@ -427,7 +430,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          }
       }
       const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_vb = o_yb + P.max_yblob;
-      const bool wvd = !(P.debug & 1);
       for (int it = 0;; it++)
       {
          bool any = false;
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
             unsigned char *base = smraw + (size_t)w * wg_bytes;
             mbar_wait(&bar_blob[w], it & 1); // maps and descriptor (Dd[w], stable until the next prefetch) have landed
             mbar_wait(&bar_full[w], it & 1); // the compute warpgroup has staged the patch
-            patch_drain<1, WS_NT, 32 / (WS_NT / 32)>(base, o_sa, o_yb, o_vb, Dd[w], wy, wvd, wtid, a.y, a.vals, P.ystage, P.vstage);
+            patch_drain<1, WS_NT, 32 / (WS_NT / 32)>(base, o_sa, o_yb, o_vb, Dd[w], wy, true, wtid, a.y, a.vals, P.ystage, P.vstage);
             mbar_arrive(&bar_empty[w]);
             // all writer threads are done with the maps of this buffer: fetch those of its next patch
             patch_bar<1, WS_NT>();

@@ -294,7 +294,6 @@ static int setup_integrator(Integrator &I)
       CUDA_OK(cudaMalloc((void **)&I.d_ystage, std::max<size_t>(H.stage_size, 1) * sizeof(double)));
       PatchDev &P = I.pdev;
       P.npatch = (int)I.pdesc.size();
-      P.debug = getenv("MADB_PATCH_DEBUG") ? atoi(getenv("MADB_PATCH_DEBUG")) : 0;
       P.max_yblob = I.max_yblob;
       P.max_vblob = 0;
       P.desc = I.d_pdesc;
