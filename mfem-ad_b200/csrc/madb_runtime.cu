@@ -201,7 +201,23 @@ static int upload_ifc(const PatchHost &H, int *(&d)[5], IfcListDev &L)
    return 0;
 }
 
-static int setup_integrator(Integrator &I)
+static int ensure_pattern_device(Integrator &I);
+static void release_device_maps(Integrator &I)
+{
+   cudaFree(I.d_e2n); cudaFree(I.d_vmap); cudaFree(I.d_pmap); cudaFree(I.d_perm); cudaFree(I.d_e2csr);
+   cudaFree(I.d_pdesc); cudaFree(I.d_yblob); cudaFree(I.d_vblob); cudaFree(I.d_ystage); cudaFree(I.d_vstage);
+   cudaFree(I.d_rowptr); cudaFree(I.d_colidx);
+   I.d_e2n = I.d_vmap = I.d_pmap = I.d_perm = I.d_e2csr = nullptr;
+   I.d_pdesc = nullptr;
+   I.d_yblob = I.d_vblob = nullptr;
+   I.d_ystage = I.d_vstage = nullptr;
+   I.d_rowptr = I.d_colidx = nullptr;
+   for (int a = 0; a < 2; a++) { for (int b = 0; b < 5; b++) { cudaFree(I.d_ifc[a][b]); I.d_ifc[a][b] = nullptr; } }
+   I.pdev = PatchDev {};
+   I.pdesc.clear();
+}
+
+static int setup_integrator(Integrator &I, bool allow_patches = true)
 {
    const int dim = I.mesh->dim;
    I.ne = I.mesh->ne;
@@ -225,7 +241,7 @@ static int setup_integrator(Integrator &I)
 
    // Element order.  Patch assembly (madb_patch.cpp) when the rows of a patch fit in shared memory:
    // compact patches of PATCH_PE elements; otherwise global colouring, one launch per colour.
-   I.use_patches = I.ops.patch_ok && !I.ops.map_aos && !getenv("MADB_NO_PATCH");
+   I.use_patches = allow_patches && I.ops.patch_ok && !I.ops.map_aos && !getenv("MADB_NO_PATCH");
    if (I.use_patches)
    {
       I.pe = patch_pe(I.nvd);
@@ -365,6 +381,26 @@ static int setup_integrator(Integrator &I)
    }
    I.pdata.assign(I.fields.size(), nullptr);
    I.d_pstage.assign(I.fields.size(), nullptr);
+   if (I.use_patches && I.pe != PATCH_PE)
+   {
+      // Large element matrices (64-element patches): the staged matrices plus the gather maps must fit in the
+      // shared memory of one CTA.  The size of the maps depends on the dof numbering (irregular chunks carry
+      // explicit CSR positions), so it is only known once they are built: build them now, and fall back to the
+      // colour-scatter path when they do not fit.
+      const int rc = ensure_pattern_device(I);
+      if (rc) { return rc; }
+      const long ld = I.pe + 1;
+      const long tables = ((long)I.nq * ntab * (1 + dim) + (long)I.nq * ngn * dim + I.nq) * 8;
+      const long need = patch_al16((int)(I.nvd * ld * 8)) + patch_al16((int)((long)I.nvd * (I.nvd + 1) / 2 * ld * 8)) +
+                        I.max_yblob + I.max_vblob + tables + 64;
+      if (need > 220 * 1024)
+      {
+         release_device_maps(I);
+         I.have_pattern = false;
+         I.have_patch_vals = false;
+         return setup_integrator(I, false);
+      }
+   }
    return 0;
 }
 

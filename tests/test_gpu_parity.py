@@ -186,6 +186,46 @@ def _block_state(mesh, spaces, seed=7):
     return np.concatenate(parts)
 
 
+@pytest.mark.parametrize("case", ["ex4o2", "ex4o2perm", "ex5o2", "elast2"])
+def test_large_element_matrices_many_patches(ctx, case):
+    """Element matrices of 17-20 dofs: 64-element patches, 4 threads per element (slices of the upper triangle),
+    several patches so that interface rows, staging and the fixed-order reduction are exercised."""
+    mesh = G.cartesian_mesh((19, 14), perturb=0.15)
+    if case in ("ex4o2", "ex4o2perm"):
+        order = 2
+        h1 = G.h1_space(mesh, order + 1, mode=O.VALUE | O.GRAD)
+        ess = G.boundary_dofs(mesh, h1)
+        if case == "ex4o2perm":
+            # random dof numbering: every 32-entry chunk of the CSR image is irregular, the gather maps do not fit
+            # in shared memory next to the staged 20x20 matrices -> the integrator falls back to the colour path
+            h1 = G.permute_dofs(h1, 3)
+            ess = h1["perm"][ess]
+        l2 = G.l2_space(mesh, order - 1, mode=O.VALUE)
+        psik = np.random.default_rng(11).normal(0, 1, l2["ndofs"])
+        of, gi = S.make_pair(ctx, mesh, [h1, l2, dict(l2, role=1)], S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), 0.4),
+                             quad_order=3 * order + 3, ess=ess, params=[dict(type=O.PRM_GF, size=1, data=psik, space=l2)])
+        gi.set_param_field(2, psik)
+        x = _block_state(mesh, [h1, l2])
+    elif case == "ex5o2":
+        u = G.h1_space(mesh, 2, mode=O.GRAD)
+        lat = G.h1_space(mesh, 1, vdim=2, mode=O.VALUE | O.VECTOR)
+        psik = np.random.default_rng(13).normal(0, 1, 2 * lat["ndofs"])
+        of, gi = S.make_pair(ctx, mesh, [u, lat, dict(lat, role=1)], S.pg(S.gradobstacle(2), S.hellinger(2, 0.7), 0.4),
+                             params=[dict(type=O.PRM_GF, size=2, data=psik, space=lat)])
+        gi.set_param_field(2, psik)
+        x = _block_state(mesh, [u, lat])
+    else:
+        s = G.h1_space(mesh, 2, vdim=2, mode=O.GRAD | O.VECTOR)
+        of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 2.0, 0.7), block=1)
+        x = _block_state(mesh, [s])
+    st = gi.patch_stats()
+    if case == "ex4o2perm":
+        assert st["patches"] in (0, (19 * 14 + 63) // 64)
+    else:
+        assert st["patches"] == (19 * 14 + 63) // 64 and st["ifc_dofs"] > 0
+    _compare(of, gi, x)
+
+
 def test_lambda_pg_block(ctx):
     """ADLambdaPGFunctional (src/pg.hpp:216-243) on the ex4 -o 1 spaces: unknowns (u, lambda), psi_k a parameter."""
     order = 1
