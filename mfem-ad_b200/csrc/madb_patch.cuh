@@ -495,7 +495,12 @@ template <class Func, class Cfg, int MODE, bool UNROLLQ>
 int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
 {
    const PatchDev &P = *L.patch;
-   static int smem_set = 0;
+   // dynamic shared-memory limits are per device and per kernel: remember what was set on each device
+   static int smem_set_dev[64] = {0}, ws_smem_set_dev[64] = {0}, nsm_dev[64] = {0};
+   int dev = 0;
+   cudaGetDevice(&dev);
+   dev &= 63;
+   int &smem_set = smem_set_dev[dev], &ws_smem_set = ws_smem_set_dev[dev], &nsm = nsm_dev[dev];
    auto kern = k_patch<Func, Cfg, MODE, UNROLLQ>;
    const bool wy = (MODE & (MODE_RES | MODE_ACT)) && L.write_y, wv = (MODE & MODE_JAC) && L.write_vals;
    constexpr int PE = patch_pe(Cfg::NVD), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
@@ -516,15 +521,9 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       static const bool use_ws = getenv("MADB_PATCH_WS") ? atoi(getenv("MADB_PATCH_WS")) != 0 : true;
       if (wv && use_ws)
       {
-         static int ws_smem_set = 0, nsm = 0;
          auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
          const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yblob + P.max_vblob) + 16;
-         if (nsm == 0)
-         {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-         }
+         if (nsm == 0) { cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
          if (ws_bytes <= 220 * 1024)
          {
             if (ws_bytes > ws_smem_set)
@@ -540,6 +539,8 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       }
    }
    if (!done) { kern<<<P.npatch, PE * NPART, smem_bytes, L.stream>>>(a, P); }
+   (void)ws_smem_set;
+   (void)nsm;
    if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }
    {
       IfcList ly = P.ylist, lv = P.vlist;
