@@ -150,6 +150,13 @@ int madb_integrator_sizes(madb_integrator *I, int64_t *ntotal, int *nq_el, int *
  * and max matrix slots per patch, interface dofs, interface matrix entries, staged residual and matrix
  * partials, CSR runs.  Matrix-side figures are 0 until the sparsity pattern has been built. */
 int madb_integrator_patch_stats(madb_integrator *I, int64_t *out);
+/* Host-only self test of the patch-assembly maps (no CUDA device needed): builds the maps for one H1 space of the
+ * given order / vdim on the given mesh, assembles integer-valued element vectors and matrices directly and through
+ * an emulation of the kernels' use of the maps, and returns the largest difference (must be 0).
+ * stats[0..5]: patches, interface dofs, interface matrix entries, staged matrix partials, largest map blob (bytes), nnz. */
+int madb_patch_selftest(int dim, int ne, const int32_t *e2n, int nnodes, const double *coords, int order, int vdim,
+                        int ordering, int ndofs, const int32_t *e2l, double *max_err, int64_t *stats);
+
 /* Device timing of the element kernel(s) of the last mult / assemble / grad_mult call: CUDA events on the
  * context stream around the dominant kernel (the interface reduction and essential-dof kernels excluded). */
 int madb_integrator_set_timing(madb_integrator *I, int on);

@@ -65,6 +65,8 @@ def lib():
         L.madb_integrator_destroy.argtypes = [vp]
         L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.madb_integrator_patch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.madb_patch_selftest.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, ip,
+                                          C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.madb_integrator_set_timing.argtypes = [vp, C.c_int]
         L.madb_integrator_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
         L.madb_integrator_set_param_field.argtypes = [vp, C.c_int, dp]
@@ -326,6 +328,18 @@ def dofpg_nodal(ctx, entropy, alpha, u, psi, psik, w, r_u=None):
     _check(lib().madb_dofpg_nodal(ctx.h, entropy.h, n, alpha, _ptr(u), _ptr(psi), _ptr(psik), _ptr(w), _ptr(r_u),
                                   _ptr(r_psi), _ptr(d_pp), _ptr(d_up)))
     return r_u, r_psi, d_pp, d_up
+
+
+def patch_selftest(mesh, space):
+    """Host-only check of the patch-assembly maps (madb_patch_selftest): returns (max_err, stats dict)."""
+    e2n, coords, e2l = _i32(mesh["e2n"]), _f64(mesh["coords"]), _i32(space["e2l"])
+    err = C.c_double()
+    st = (C.c_int64 * 6)()
+    _check(lib().madb_patch_selftest(mesh["dim"], e2n.shape[0], e2n.ctypes.data, coords.shape[0], coords.ctypes.data,
+                                     space["order"], space.get("vdim", 1), space.get("ordering", BYNODES), space["ndofs"],
+                                     e2l.ctypes.data, C.byref(err), st))
+    keys = ("patches", "ifc_dofs", "ifc_entries", "staged_vals", "max_blob_bytes", "nnz")
+    return err.value, dict(zip(keys, [int(v) for v in st]))
 
 
 def lvpp_update(ctx, alpha, psi, psik, lambda_prev, w=None):

@@ -263,5 +263,6 @@ struct PatchHost // maps of one side (residual or matrix)
 void patch_order(Integrator &I);                      // fills I.perm (patch order) and I.pdesc[].ne
 bool patch_build_y(Integrator &I, PatchHost &H);       // needs I.perm; false: not representable
 bool patch_build_v(Integrator &I, PatchHost &H);       // needs the CSR pattern
+int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats); // host-only emulation (CPU tests)
 
 } // namespace madb

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <array>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -506,6 +507,154 @@ bool patch_build_v(Integrator &I, PatchHost &H)
    group_by_dst(tup, H);
    I.have_patch_vals = true;
    return true;
+}
+
+} // namespace madb
+
+// ---------------------------------------------------------------------------------------------
+// Host-only self test of the patch maps (no CUDA): builds the maps for one H1 field, assembles
+// integer-valued element vectors / symmetric element matrices (exact in FP64, so the summation
+// order does not matter) once directly and once by emulating what the kernels do with the maps
+// (stage, fold phases, first-source gather, chunk descriptors, irregular chunks, staging,
+// interface reduction), and returns the largest difference.  Used by the CPU test-suite.
+// ---------------------------------------------------------------------------------------------
+namespace madb
+{
+
+int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
+{
+   Integrator I;
+   I.mesh = &mesh;
+   FieldDesc fd;
+   fd.space = &space;
+   fd.mode = 4; // GRAD
+   fd.role = 0;
+   I.fields.push_back(fd);
+   I.ne = mesh.ne;
+   I.nvd = space.nd_el() * space.vdim;
+   I.ndof_all = I.nvd;
+   I.ntotal = space.vsize();
+   I.goff.assign(1, 0);
+   if (!patch_eligible(I.nvd)) { set_error("patch_selftest: element matrix too large for the patch scheme"); return 1; }
+   I.pe = patch_pe(I.nvd);
+   I.use_patches = true;
+   patch_order(I);
+   if (I.pdesc.empty()) { set_error("patch_selftest: patch_order failed"); return 1; }
+   const int pe = I.pe, ld = pe + 1, nvd = I.nvd, nsym = nvd * (nvd + 1) / 2, np = (int)I.pdesc.size();
+   I.stride = np * pe;
+   PatchHost HY, HV;
+   if (!patch_build_y(I, HY)) { set_error("patch_selftest: patch_build_y failed"); return 1; }
+   build_pattern(I);
+   if (!I.have_pattern) { return 1; }
+   if (!patch_build_v(I, HV)) { return 1; }
+   const long N = I.ntotal, nnz = (long)I.colidx.size();
+   auto rval = [](int e, int i) { return (double)((e * 7 + i * 3) % 11 - 5); };
+   auto aval = [](int e, int a, int b) { const int lo = std::min(a, b), hi = std::max(a, b); return (double)((e * 5 + lo * 13 + hi * 17) % 23 - 11); };
+   // direct assembly
+   std::vector<double> y_ref(N, 0.0), v_ref(nnz, 0.0), y(N, -777.0), v(nnz, -777.0);
+   std::vector<int> vd;
+   for (int e = 0; e < I.ne; e++)
+   {
+      build_vdofs(I, e, vd);
+      for (int i = 0; i < nvd; i++)
+      {
+         y_ref[vd[i]] += rval(e, i);
+         const int *cb = I.colidx.data() + I.rowptr[vd[i]], *ce = I.colidx.data() + I.rowptr[vd[i] + 1];
+         for (int j = 0; j < nvd; j++) { v_ref[std::lower_bound(cb, ce, vd[j]) - I.colidx.data()] += aval(e, i, j); }
+      }
+   }
+   // emulation of the kernels
+   std::vector<double> ystage(std::max<long>(HY.stage_size, 1), -555.0), vstage(std::max<long>(HV.stage_size, 1), -555.0);
+   std::vector<double> sR((size_t)nvd * ld), sA((size_t)nsym * ld);
+   for (int p = 0; p < np; p++)
+   {
+      const PatchDesc &D = I.pdesc[p];
+      std::fill(sR.begin(), sR.end(), 1e300);
+      std::fill(sA.begin(), sA.end(), 1e300);
+      for (int l = 0; l < D.ne; l++)
+      {
+         const int e = I.perm[p * pe + l];
+         for (int i = 0; i < nvd; i++) { sR[(size_t)i * ld + l] = rval(e, i); }
+         for (int b = 0; b < nvd; b++) { for (int a = 0; a <= b; a++) { sA[(size_t)(b * (b + 1) / 2 + a) * ld + l] = aval(e, a, b); } }
+      }
+      // y side
+      {
+         const unsigned char *yb = HY.blob.data() + (size_t)D.yblob_off * 16;
+         const unsigned short *ysrc = (const unsigned short *)yb;
+         const unsigned *yfold = (const unsigned *)(yb + patch_al16(2 * D.nrows));
+         const int *ylist = (const int *)((const unsigned char *)yfold + patch_al16(4 * D.nyfold));
+         int base = 8;
+         for (int ph = 0; ph < 8; ph++)
+         {
+            const int n = (int)yfold[ph];
+            for (int i = 0; i < n; i++) { const unsigned w = yfold[base + i]; sR[w & 0xffffu] += sR[w >> 16]; }
+            base += n;
+         }
+         for (int lr = 0; lr < D.nrows; lr++)
+         {
+            const double val = sR[ysrc[lr]];
+            if (lr < D.nrow_int) { y[ylist[lr]] = val; }
+            else { ystage[D.ystage_off + (lr - D.nrow_int)] = val; }
+         }
+      }
+      // matrix side
+      {
+         const unsigned char *vb = HV.blob.data() + (size_t)D.vblob_off * 16;
+         const unsigned short *vsrc = (const unsigned short *)vb;
+         const unsigned *vfold = (const unsigned *)(vb + patch_al16(2 * D.nvsrc));
+         const int *chunks = (const int *)((const unsigned char *)vfold + patch_al16(4 * D.nvfold));
+         const unsigned short *isrc = (const unsigned short *)((const unsigned char *)chunks + patch_al16(16 * D.nchunk));
+         const int *over = (const int *)((const unsigned char *)isrc + patch_al16(64 * D.nirr));
+         int base = 8;
+         for (int ph = 0; ph < 8; ph++)
+         {
+            const int n = (int)vfold[ph];
+            for (int i = 0; i < n; i++) { const unsigned w = vfold[base + i]; sA[w & 0xffffu] += sA[w >> 16]; }
+            base += n;
+         }
+         for (int c = 0; c < D.nchunk; c++)
+         {
+            const int *d = chunks + 4 * c;
+            for (int lane = 0; lane < 32; lane++)
+            {
+               if (lane < d[3]) { v[((lane < d[2]) ? d[0] : d[1]) + lane] = sA[vsrc[c * 32 + lane]]; }
+            }
+         }
+         for (int k = 0; k < D.nirr * 32; k++) { if (over[k] >= 0) { v[over[k]] = sA[isrc[k]]; } }
+         for (int s = D.nexc; s < D.nslots; s++) { vstage[D.stage_off + (s - D.nexc)] = sA[vsrc[s]]; }
+      }
+   }
+   auto reduce = [](const PatchHost &H, const std::vector<double> &stage, std::vector<double> &out)
+   {
+      for (size_t i = 0; i < H.dst4.size(); i++)
+      {
+         double s = 0.0;
+         for (int k = 0; k < 4; k++) { if (H.src4[4 * i + k] >= 0) { s += stage[H.src4[4 * i + k]]; } }
+         out[H.dst4[i]] = s;
+      }
+      for (size_t i = 0; i < H.dst.size(); i++)
+      {
+         double s = 0.0;
+         for (int k = H.ptr[i]; k < H.ptr[i + 1]; k++) { s += stage[H.src[k]]; }
+         out[H.dst[i]] = s;
+      }
+   };
+   reduce(HY, ystage, y);
+   reduce(HV, vstage, v);
+   double err = 0.0;
+   for (long i = 0; i < N; i++) { err = std::max(err, std::fabs(y[i] - y_ref[i])); }
+   for (long i = 0; i < nnz; i++) { err = std::max(err, std::fabs(v[i] - v_ref[i])); }
+   *max_err = err;
+   if (stats)
+   {
+      stats[0] = np;
+      stats[1] = (long)HY.dst4.size() + (long)HY.dst.size();
+      stats[2] = (long)HV.dst4.size() + (long)HV.dst.size();
+      stats[3] = HV.stage_size;
+      stats[4] = I.max_vblob;
+      stats[5] = nnz;
+   }
+   return 0;
 }
 
 } // namespace madb

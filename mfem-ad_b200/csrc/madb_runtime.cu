@@ -903,6 +903,23 @@ extern "C"
       }
       return 0;
    }
+   int madb_patch_selftest(int dim, int ne, const int32_t *e2n, int nnodes, const double *coords, int order, int vdim,
+                           int ordering, int ndofs, const int32_t *e2l, double *max_err, int64_t *stats)
+   {
+      if (dim < 1 || dim > 3 || ne <= 0 || !e2n || !coords || !e2l || order < 1 || vdim < 1) { set_error("madb_patch_selftest: bad arguments"); return 1; }
+      Mesh m;
+      m.ctx = nullptr; m.dim = dim; m.ne = ne; m.geom_order = 1; m.nnodes = nnodes;
+      m.e2n.assign(e2n, e2n + (size_t)ne * (1 << dim));
+      m.coords.assign(coords, coords + (size_t)nnodes * dim);
+      Space s;
+      s.ctx = nullptr; s.mesh = &m; s.basis = BASIS_H1; s.order = order; s.vdim = vdim; s.ordering = ordering; s.ndofs = ndofs;
+      s.e2l.assign(e2l, e2l + (size_t)ne * s.nd_el());
+      long st[6] = {0, 0, 0, 0, 0, 0};
+      const int rc = patch_selftest(m, s, max_err, st);
+      if (stats) { for (int k = 0; k < 6; k++) { stats[k] = st[k]; } }
+      return rc;
+   }
+
    int madb_integrator_set_timing(madb_integrator *I, int on)
    {
       CUDA_OK(cudaSetDevice(I->ctx->device));

@@ -1,0 +1,63 @@
+"""CPU tests of the patch-assembly maps (csrc/madb_patch.cpp) through madb_patch_selftest: the host emulation of
+what the kernels do with the maps must reproduce the direct element-by-element assembly exactly (integer-valued
+element data), for structured and shuffled meshes, random dof numberings, vector spaces, hexes and the
+64-element-patch scheme of large element matrices.  No GPU needed."""
+import numpy as np
+import pytest
+
+import mfem_ad_b200 as M
+from mfem_ad_b200 import meshgen as G
+
+
+def _case(name):
+    if name == "q2":
+        mesh = G.cartesian_mesh((31, 26), perturb=0.2)
+        return mesh, G.h1_space(mesh, 2)
+    if name == "q1":
+        mesh = G.cartesian_mesh((40, 33))
+        return mesh, G.h1_space(mesh, 1)
+    if name == "q2perm":
+        mesh = G.cartesian_mesh((31, 26))
+        return mesh, G.permute_dofs(G.h1_space(mesh, 2), 3)
+    if name == "q2shuffled":
+        mesh = G.cartesian_mesh((31, 26), perturb=0.1)
+        s = G.permute_dofs(G.h1_space(mesh, 2), 4)
+        mesh, (s,) = G.shuffle_mesh(mesh, [s], 8)
+        return mesh, s
+    if name == "q1v2":
+        mesh = G.cartesian_mesh((23, 19))
+        return mesh, G.h1_space(mesh, 1, vdim=2, ordering=1)
+    if name == "hex":
+        mesh = G.cartesian_mesh((9, 8, 7))
+        return mesh, G.h1_space(mesh, 1)
+    if name == "q3":  # 16 dofs per element: 64-element patches
+        mesh = G.cartesian_mesh((19, 14))
+        return mesh, G.h1_space(mesh, 3)
+    if name == "q2v2":  # 18 dofs per element
+        mesh = G.cartesian_mesh((17, 13))
+        return mesh, G.h1_space(mesh, 2, vdim=2)
+    if name == "one_patch":
+        mesh = G.cartesian_mesh((5, 4))
+        return mesh, G.h1_space(mesh, 2)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["q2", "q1", "q2perm", "q2shuffled", "q1v2", "hex", "q3", "q2v2", "one_patch"])
+def test_patch_maps_reproduce_direct_assembly(name):
+    mesh, space = _case(name)
+    err, st = M.patch_selftest(mesh, space)
+    assert err == 0.0, (name, err, st)
+    ne = mesh["e2n"].shape[0]
+    nvd = (space["order"] + 1) ** mesh["dim"] * space.get("vdim", 1)
+    pe = 128 if nvd <= 10 else 64
+    assert st["patches"] == (ne + pe - 1) // pe
+    if st["patches"] > 1:
+        assert st["ifc_dofs"] > 0 and st["ifc_entries"] > 0 and st["staged_vals"] >= 2 * st["ifc_entries"]
+    else:
+        assert st["ifc_dofs"] == 0 and st["staged_vals"] == 0
+
+
+def test_patch_maps_too_large_element_matrix_is_refused():
+    mesh = G.cartesian_mesh((6, 5))
+    with pytest.raises(M.MadbError, match="too large"):
+        M.patch_selftest(mesh, G.h1_space(mesh, 4))  # 25 dofs per element
