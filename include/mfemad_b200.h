@@ -105,6 +105,12 @@ int madb_functional_destroy(madb_functional *f);
 int madb_functional_eval(madb_ctx *ctx, madb_functional *f, int n_input, int npts, const double *x,
                          const double *qprm, double *value, double *grad, double *hess);
 
+/* ADVectorFunction (src/ad_native.hpp:198-265; Gradient / Hessian src/ad_native.cpp:232-276) at npts points:
+ * value [npts][n_output], Jacobian jac [npts][n_output][n_input], Hessians hess [npts][n_output][n_input][n_input]
+ * (any output may be NULL).  Only ex0 uses a vector function in the reference (ex0.cpp:23-35, kind "ex0vec"). */
+int madb_vecfunction_eval(madb_ctx *ctx, madb_functional *f, int n_input, int n_output, int npts, const double *x,
+                          double *value, double *jac, double *hess);
+
 /* DOF-collocated proximal-Galerkin terms of ADDofPGNonlinearFormIntegrator
  * (src/_dof_pg.hpp:17-63, src/dof_pg.hpp:66-128 residual, :131-231 Jacobian diagonals) for one
  * primal/latent pair with a scalar entropy, one thread per dof:

@@ -65,6 +65,7 @@ def lib():
         L.madb_integrator_destroy.argtypes = [vp]
         L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.madb_integrator_patch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
+        L.madb_vecfunction_eval.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
         L.madb_patch_selftest.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, ip,
                                           C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.madb_integrator_set_timing.argtypes = [vp, C.c_int]
@@ -183,6 +184,15 @@ class Functional:
         _check(lib().madb_functional_eval(self.ctx.h, self.h, n, npts, x.ctypes.data, _ptr(q), v.ctypes.data,
                                           g.ctypes.data, h.ctypes.data))
         return v, g, h
+
+    def eval_vector(self, x, n_output):
+        """ADVectorFunction: value [npts, m], Jacobian [npts, m, n], Hessians [npts, m, n, n] (src/ad_native.cpp:232-276)."""
+        x = _f64(np.atleast_2d(x))
+        npts, n = x.shape
+        v, J, H = np.zeros((npts, n_output)), np.zeros((npts, n_output, n)), np.zeros((npts, n_output, n, n))
+        _check(lib().madb_vecfunction_eval(self.ctx.h, self.h, n, n_output, npts, x.ctypes.data, v.ctypes.data, J.ctypes.data,
+                                           H.ctypes.data))
+        return v, J, H
 
     def eval_device(self, x, value=None, grad=None, hess=None, qprm=None):
         """Same on buffers that already live on the device (torch tensors): x[npts, n]; outputs may be None."""

@@ -25,3 +25,6 @@ MADB_EVAL_INSTANCE("elasticity", Elast2)
 MADB_EVAL_INSTANCE("elasticity", Elast3)
 MADB_EVAL_INSTANCE("pg:0[obstacle,fermidirac]", PGObsFD)
 MADB_EVAL_INSTANCE("lambdapg:0[obstacle,fermidirac]", LamPGObsFD)
+
+// ADVectorFunction of ex0 (ex0.cpp:23-35): value, Jacobian and Hessians on the device
+MADB_VEC_EVAL_INSTANCE("ex0vec", Ex0VectorFunction)

@@ -122,11 +122,79 @@ template <class Func> int eval_launch(cudaStream_t s, int npts, const double *fp
    return (int)cudaGetLastError();
 }
 
+// ---- ADVectorFunction (src/ad_native.hpp:198-265, src/ad_native.cpp:232-276): F: R^n -> R^m -------------------
+// value F[m], Jacobian J[m][n] (row = output) and Hessians H[m][n][n], one hyper-dual pass for all outputs.
+// A vector functional provides N_INPUT, N_OUTPUT, N_PARAM, load() and
+//    template <class T> void operator()(const T *x, T *result) const     (the AD_VEC_IMPL body)
+struct VecEvalOps
+{
+   int (*launch)(cudaStream_t, int npts, const double *fparams_host, const double *x, double *value, double *jac, double *hess);
+   int n_input, n_output, n_fparam;
+};
+std::map<std::string, VecEvalOps> &vec_eval_registry();
+struct VecEvalRegistrar
+{
+   VecEvalRegistrar(const std::string &key, const VecEvalOps &ops);
+};
+template <class Func> struct VecEvalArgs
+{
+   int npts;
+   const double *x;
+   double *value, *jac, *hess;
+   double fparams[Func::N_PARAM > 0 ? Func::N_PARAM : 1];
+};
+template <class Func> __global__ void __launch_bounds__(128) k_eval_vec(const VecEvalArgs<Func> a)
+{
+   constexpr int N = Func::N_INPUT, M = Func::N_OUTPUT;
+   const int p = blockIdx.x * blockDim.x + threadIdx.x;
+   if (p >= a.npts) { return; }
+   Func f;
+   f.load(a.fparams);
+   using T = AD<N, 2>;
+   T xs[N], res[M];
+#pragma unroll
+   for (int m = 0; m < N; m++) { xs[m] = ad_seed<N, 2>(a.x[(size_t)p * N + m], m); }
+   f(xs, res);
+#pragma unroll
+   for (int o = 0; o < M; o++)
+   {
+      if (a.value) { a.value[(size_t)p * M + o] = res[o].v; }
+      if (a.jac)
+      {
+#pragma unroll
+         for (int i = 0; i < N; i++) { a.jac[((size_t)p * M + o) * N + i] = res[o].g[i]; }
+      }
+      if (a.hess)
+      {
+#pragma unroll
+         for (int i = 0; i < N; i++)
+         {
+#pragma unroll
+            for (int j = 0; j < N; j++) { a.hess[(((size_t)p * M + o) * N + i) * N + j] = res[o].hess(i, j); }
+         }
+      }
+   }
+}
+template <class Func> int vec_eval_launch(cudaStream_t s, int npts, const double *fp, const double *x, double *value, double *jac,
+                                          double *hess)
+{
+   VecEvalArgs<Func> a;
+   a.npts = npts; a.x = x; a.value = value; a.jac = jac; a.hess = hess;
+   for (int i = 0; i < Func::N_PARAM; i++) { a.fparams[i] = fp[i]; }
+   k_eval_vec<Func><<<(npts + 127) / 128, 128, 0, s>>>(a);
+   return (int)cudaGetLastError();
+}
+
 #define MADB_EVAL_CAT2(a, b) a##b
 #define MADB_EVAL_CAT(a, b) MADB_EVAL_CAT2(a, b)
 #define MADB_EVAL_INSTANCE(KIND, FUNC)                                                                              \
    static ::madb::EvalRegistrar MADB_EVAL_CAT(madb_evreg_, __COUNTER__)(                                            \
       std::string(KIND) + "|n" + std::to_string(FUNC::N_INPUT),                                                     \
       ::madb::EvalOps {&::madb::eval_launch<FUNC>, FUNC::N_INPUT, FUNC::N_PARAM, FUNC::N_QPRM, ::madb::dofpg_ptr<FUNC>()});
+
+#define MADB_VEC_EVAL_INSTANCE(KIND, FUNC)                                                                          \
+   static ::madb::VecEvalRegistrar MADB_EVAL_CAT(madb_vevreg_, __COUNTER__)(                                        \
+      std::string(KIND) + "|n" + std::to_string(FUNC::N_INPUT) + "m" + std::to_string(FUNC::N_OUTPUT),              \
+      ::madb::VecEvalOps {&::madb::vec_eval_launch<FUNC>, FUNC::N_INPUT, FUNC::N_OUTPUT, FUNC::N_PARAM});
 
 } // namespace madb

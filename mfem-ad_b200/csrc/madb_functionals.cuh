@@ -29,6 +29,18 @@ struct Ex0Function
    }
 };
 
+// ex0.cpp:23-35  F = (sin(x0 x1), cos(x0 x1 x2))   (ADVectorFunction, AD_VEC_IMPL)
+struct Ex0VectorFunction
+{
+   static constexpr int N_INPUT = 3, N_OUTPUT = 2, N_PARAM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD void operator()(const T *x, T *result) const
+   {
+      result[0] = sin(x[0] * x[1]);
+      result[1] = cos(x[0] * x[1] * x[2]);
+   }
+};
+
 // src/ad_native.hpp:413-420
 template <int N> struct MassEnergy
 {

@@ -29,6 +29,13 @@ std::map<std::string, EvalOps> &eval_registry()
 }
 EvalRegistrar::EvalRegistrar(const std::string &key, const EvalOps &ops) { eval_registry()[key] = ops; }
 
+std::map<std::string, VecEvalOps> &vec_eval_registry()
+{
+   static std::map<std::string, VecEvalOps> r;
+   return r;
+}
+VecEvalRegistrar::VecEvalRegistrar(const std::string &key, const VecEvalOps &ops) { vec_eval_registry()[key] = ops; }
+
 std::string Functional::key() const
 {
    std::string k = kind;
@@ -737,6 +744,37 @@ extern "C"
       if (sx.owned || sv.owned || sg.owned || sh.owned) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
       sx.finish(); sq.finish();
       if (sv.finish() || sg.finish() || sh.finish()) { set_error("madb_functional_eval: copy back failed"); return 2; }
+      return 0;
+   }
+
+   int madb_vecfunction_eval(madb_ctx *ctx, madb_functional *f, int n_input, int n_output, int npts, const double *x,
+                             double *value, double *jac, double *hess)
+   {
+      CUDA_OK(cudaSetDevice(ctx->device));
+      const std::string key = f->key() + "|n" + std::to_string(n_input) + "m" + std::to_string(n_output);
+      auto it = vec_eval_registry().find(key);
+      if (it == vec_eval_registry().end())
+      {
+         set_error("no pointwise AD kernel compiled for the vector function '" + key + "' (add MADB_VEC_EVAL_INSTANCE)");
+         return 1;
+      }
+      const VecEvalOps &E = it->second;
+      std::vector<double> fp;
+      f->flat_params(fp);
+      if ((int)fp.size() != E.n_fparam) { set_error("vector function '" + key + "': wrong number of parameters"); return 1; }
+      fp.push_back(0.0);
+      const size_t n = n_input, m = n_output, P = npts;
+      Staged sx, sv, sj, sh;
+      if (sx.in(x, P * n) || sv.out(value, P * m) || sj.out(jac, P * m * n) || sh.out(hess, P * m * n * n))
+      {
+         set_error("madb_vecfunction_eval: device staging failed");
+         return 2;
+      }
+      const int rc = E.launch(ctx->stream, npts, fp.data(), sx.d, sv.d, sj.d, sh.d);
+      if (rc) { set_error(std::string("vector eval kernel: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
+      if (sx.owned || sv.owned || sj.owned || sh.owned) { CUDA_OK(cudaStreamSynchronize(ctx->stream)); }
+      sx.finish();
+      if (sv.finish() || sj.finish() || sh.finish()) { set_error("madb_vecfunction_eval: copy back failed"); return 2; }
       return 0;
    }
 

@@ -58,6 +58,31 @@ def test_ex0_known_answers_on_device(ctx):
     assert np.max(np.abs(h[0] - Href)) <= 1e-14
 
 
+def test_ex0_vector_function_on_device(ctx):
+    # ADVectorFunction (ex0.cpp:23-35): "Jacobian2 error" and the Hessian slices of ex0.cpp:153-158 on the device
+    import mfem_ad_b200 as M
+    f = M.Functional(ctx, "ex0vec")
+    x0 = np.array([[0.5, 1.0, -1.0]])
+    v, J, H = f.eval_vector(x0, 2)
+    assert np.max(np.abs(v[0] - np.array([np.sin(0.5), np.cos(-0.5)]))) <= 1e-15
+    Jref = np.array([[0.8775825618903728, 0.4387912809451864, 0.0],
+                     [-0.479425538604203, -0.2397127693021015, 0.2397127693021015]])
+    assert np.max(np.abs(J[0] - Jref)) <= 1e-14
+    H0 = np.array([[-0.479425538604203, 0.6378697925882713, 0], [0.6378697925882713, -0.11985638465105075, 0], [0, 0, 0]])
+    H1 = np.array([[-0.8775825618903728, -0.9182168195493894, 0.9182168195493894],
+                   [-0.9182168195493894, -0.2193956404725932, 0.4591084097746947],
+                   [0.9182168195493894, 0.4591084097746947, -0.2193956404725932]])
+    assert np.max(np.abs(H[0, 0] - H0)) <= 1e-14 and np.max(np.abs(H[0, 1] - H1)) <= 1e-14
+    # many points against the oracle
+    g = O.Functional()
+    g.add(O.K_EX0VEC, 3, n_output=2)
+    X = np.random.default_rng(2).normal(0, 1, (50, 3))
+    v, J, H = f.eval_vector(X, 2)
+    for p in range(X.shape[0]):
+        assert np.max(np.abs(J[p] - g.vec_gradient(X[p]))) <= 1e-13
+        assert np.max(np.abs(H[p] - g.vec_hessian(X[p]))) <= 1e-13
+
+
 @pytest.mark.parametrize("fs,n,qn", [
     (S.FSpec("ex0", 3), 3, 0), (S.minsurf(2, 0.5), 2, 0), (S.shannon(0.25, -1), 1, 0),
     (S.fermidirac(0.0, 0.5), 1, 0), (S.hellinger(2, 0.7), 2, 0), (S.simplex(5, 1.5), 5, 0),
