@@ -28,3 +28,9 @@ MADB_EVAL_INSTANCE("lambdapg:0[obstacle,fermidirac]", LamPGObsFD)
 
 // ADVectorFunction of ex0 (ex0.cpp:23-35): value, Jacobian and Hessians on the device
 MADB_VEC_EVAL_INSTANCE("ex0vec", Ex0VectorFunction)
+
+// Lagrangian / ALFunctional (src/ad_native.hpp:570-691; unused by the reference's drivers)
+using LagDM = LagrangianOf<DiffusionEnergy<2, 0>, MinS2, -1>;
+using ALDM = ALFunctionalOf<DiffusionEnergy<2, 0>, MinS2, -1>;
+MADB_EVAL_INSTANCE("lagrangian:-1[diffusion:0,minsurf]", LagDM)
+MADB_EVAL_INSTANCE("al:-1[diffusion:0,minsurf]", ALDM)

@@ -12,3 +12,11 @@ MADB_INSTANCE("diffusion:0", Diff2, Q1, true)
 MADB_INSTANCE("diffusion:0", Diff2, Q2, true)
 MADB_INSTANCE("minsurf", MinS2, Q1, true)
 MADB_INSTANCE("minsurf", MinS2, Q2, true)
+
+// Lagrangian f(grad u) + lambda c(grad u): H1 order 1 x L2 order 0 (block integrator, GRAD / VALUE);
+// augmented Lagrangian on the order-2 space (sum-factorised path)
+using LagDM = LagrangianOf<Diff2, MinS2, -1>;
+using ALDM = ALFunctionalOf<Diff2, MinS2, -1>;
+using Q1L0 = Config<2, 3, Field<2, 1, EV_GRAD>, Field<1, 1, EV_VALUE>>;
+MADB_INSTANCE("lagrangian:-1[diffusion:0,minsurf]", LagDM, Q1L0, true)
+MADB_INSTANCE("al:-1[diffusion:0,minsurf]", ALDM, Q2, true)

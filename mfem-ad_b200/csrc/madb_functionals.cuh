@@ -193,6 +193,60 @@ template <class E> struct DiffEnergy
    }
 };
 
+// src/ad_native.hpp:570-621: Lagrangian f(x) + lambda c(x) with ONE equality constraint; inputs [x, lambda].
+// MODE is the reference's eval_mode (-1 full, -2 objective only, 0 the constraint), a structural integer here.
+template <class F, class C, int MODE> struct LagrangianOf
+{
+   static_assert(F::N_INPUT == C::N_INPUT && F::N_QPRM == 0 && C::N_QPRM == 0, "objective and constraint act on the same x");
+   static constexpr int NF = F::N_INPUT;
+   static constexpr int N_INPUT = NF + 1, N_PARAM = F::N_PARAM + C::N_PARAM, N_QPRM = 0;
+   F f;
+   C c;
+   MADB_HD void load(const double *p)
+   {
+      f.load(p);
+      c.load(p + F::N_PARAM);
+   }
+   template <class T> MADB_HD T operator()(const T *x_and_lambda, const double *qp) const
+   {
+      if constexpr (MODE >= 0) { return c(x_and_lambda, qp); }
+      else
+      {
+         T result = f(x_and_lambda, qp);
+         if constexpr (MODE == -2) { return result; }
+         else { return result + c(x_and_lambda, qp) * x_and_lambda[NF]; }
+      }
+   }
+};
+
+// src/ad_native.hpp:624-691: augmented Lagrangian f(x) + c~ (lambda + mu/2 c~), c~ = c(x) - rhs, one constraint;
+// parameters [mu, rhs, lambda] (SetPenalty / SetEqRHS / SetLambda), then those of f and c.
+template <class F, class C, int MODE> struct ALFunctionalOf
+{
+   static_assert(F::N_INPUT == C::N_INPUT && F::N_QPRM == 0 && C::N_QPRM == 0, "objective and constraint act on the same x");
+   static constexpr int N_INPUT = F::N_INPUT, N_PARAM = 3 + F::N_PARAM + C::N_PARAM, N_QPRM = 0;
+   double mu, rhs, lambda;
+   F f;
+   C c;
+   MADB_HD void load(const double *p)
+   {
+      mu = p[0]; rhs = p[1]; lambda = p[2];
+      f.load(p + 3);
+      c.load(p + 3 + F::N_PARAM);
+   }
+   template <class T> MADB_HD T operator()(const T *x, const double *qp) const
+   {
+      T cx = c(x, qp) - rhs;
+      if constexpr (MODE >= 0) { return cx; }
+      else
+      {
+         T result = f(x, qp);
+         if constexpr (MODE == -2) { return result; }
+         else { return result + cx * (lambda + (mu * 0.5) * cx); }
+      }
+   }
+};
+
 // ---------------------------------------------------------------------------
 // Dual entropies (src/pg.hpp:253-376): gradients are the latent->primal maps
 // ---------------------------------------------------------------------------

@@ -12,7 +12,7 @@ class FSpec:
     # ---- CPU oracle ----
     _OK = dict(ex0=O.K_EX0, mass=O.K_MASS, diffusion=O.K_DIFFUSION, diff=O.K_DIFF, elasticity=O.K_ELASTICITY,
                minsurf=O.K_MINSURF, obstacle=O.K_OBSTACLE, gradobstacle=O.K_GRADOBSTACLE, pg=O.K_PG,
-               lambdapg=O.K_LAMBDAPG, shannon=O.K_SHANNON, fermidirac=O.K_FERMIDIRAC, hellinger=O.K_HELLINGER,
+               lambdapg=O.K_LAMBDAPG, lagrangian=O.K_LAGRANGIAN, al=O.K_AL, shannon=O.K_SHANNON, fermidirac=O.K_FERMIDIRAC, hellinger=O.K_HELLINGER,
                simplex=O.K_SIMPLEX, simp=O.K_SIMP, paramcompliance=O.K_PARAMCOMPLIANCE, empty=O.K_EMPTY)
 
     def _add(self, F):
@@ -89,6 +89,16 @@ def simp(E, p):
 def pg(f, entropy, alpha, primal_idx=0):
     """ADPGFunctional(f, entropy, psi_k, idx): psi_k is the first per-point parameter."""
     return FSpec("pg", f.n_input + entropy.n_input, [alpha], [primal_idx], [f, entropy], qoff=0)
+
+
+def lagrangian(f, c, mode=-1):
+    """Lagrangian f(x) + lambda c(x), one equality constraint (src/ad_native.hpp:570-621); inputs [x, lambda]."""
+    return FSpec("lagrangian", f.n_input + 1, [], [mode], [f, c])
+
+
+def al(f, c, mu, rhs, lam, mode=-1):
+    """ALFunctional f + c~ (lambda + mu/2 c~), c~ = c - rhs (src/ad_native.hpp:624-691)."""
+    return FSpec("al", f.n_input, [mu, rhs, lam], [mode], [f, c])
 
 
 def lambdapg(f, entropy, alpha, primal_idx=0):

@@ -90,6 +90,8 @@ def test_ex0_vector_function_on_device(ctx):
     (S.elasticity(2, 2.0, 0.7), 4, 0), (S.elasticity(3, 2.0, 0.7), 9, 0),
     (S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), 0.7), 4, 1),
     (S.lambdapg(S.obstacle(2), S.fermidirac(0.0, 0.5), 0.7), 4, 1),
+    (S.lagrangian(S.diffusion(2), S.minsurf(2, 0.5)), 3, 0),
+    (S.al(S.diffusion(2), S.minsurf(2, 0.5), 2.5, 1.2, -0.7), 2, 0),
 ])
 def test_pointwise_ad_matches_oracle(ctx, fs, n, qn):
     rng = np.random.default_rng(5)
@@ -249,6 +251,25 @@ def test_large_element_matrices_many_patches(ctx, case):
     else:
         assert st["patches"] == (19 * 14 + 63) // 64 and st["ifc_dofs"] > 0
     _compare(of, gi, x)
+
+
+def test_lagrangian_and_augmented_lagrangian_forms(ctx):
+    """Lagrangian (block: H1 order 1 x L2 order 0, x = [grad u, lambda]) and ALFunctional (order-2 space,
+    sum-factorised path) of src/ad_native.hpp:570-691 against the oracle; several patches."""
+    mesh = G.cartesian_mesh((17, 11), perturb=0.15)
+    h1 = G.h1_space(mesh, 1, mode=O.GRAD)
+    l0 = G.l2_space(mesh, 0, mode=O.VALUE)
+    of, gi = S.make_pair(ctx, mesh, [h1, l0], S.lagrangian(S.diffusion(2), S.minsurf(2, 0.5)))
+    _compare(of, gi, _block_state(mesh, [h1, l0]))
+    h2 = G.h1_space(mesh, 2, mode=O.GRAD)
+    fs = S.al(S.diffusion(2), S.minsurf(2, 0.5), 2.5, 1.2, -0.7)
+    of, gi = S.make_pair(ctx, mesh, [h2], fs)
+    x = _state(mesh, h2)
+    _compare(of, gi, x)
+    gi.fn.set_params([4.0, 1.2, 0.3])  # SetPenalty / SetLambda between outer iterations
+    of2 = O.OracleForm(mesh, [h2], S.al(S.diffusion(2), S.minsurf(2, 0.5), 4.0, 1.2, 0.3).oracle())
+    assert S.csr_rel_err(gi.mult(x), of2.mult(x)) <= TOL
+    assert S.csr_rel_err(gi.grad(x), of2.grad(x)[2]) <= TOL
 
 
 def test_lambda_pg_block(ctx):
