@@ -15,7 +15,8 @@ using Simplex5 = SimplexEntropy<5>;
 using CfgState = Config<2, 3, Field<2, 2, EV_GRAD>, Field<2, 5, EV_VALUE, ROLE_PARAM>>;
 using CfgDesign = Config<2, 3, Field<2, 5, EV_VALUE>, Field<2, 2, EV_GRAD, ROLE_PARAM>>;
 using CfgLatent = Config<2, 3, Field<2, 5, EV_VALUE>>;
-MADB_INSTANCE("paramcompliance[simp,simp]", State, CfgState, true)
+// quadrature loop NOT unrolled: unrolled, the kernel is 13.8 k instructions (220 KB) and instruction-cache bound (2x slower)
+MADB_INSTANCE("paramcompliance[simp,simp]", State, CfgState, false)
 MADB_INSTANCE("designcompliance[simp,simp]", Design, CfgDesign, false)
 MADB_INSTANCE("simplex", Simplex5, CfgLatent, false)
 
