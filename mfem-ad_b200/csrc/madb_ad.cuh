@@ -26,6 +26,37 @@
 namespace madb
 {
 
+// Branch-free reciprocal / reciprocal square root for NORMAL positive-or-negative arguments away from the
+// over/underflow range: MUFU.RCP64H / MUFU.RSQ64H seed (about 20 bits) + two Newton steps (quadratic: 2^-40, 2^-80 ->
+// rounding error only).  CUDA's 1.0/x and rsqrt(x) carry a slow-path test and CALL per use: every use splits the
+// unrolled quadrature loop into basic blocks and ptxas cannot interleave the FP64 chains of neighbouring points
+// (k_patch_ws: 64 such blocks per element).  0, inf, NaN and denormal arguments give inf/NaN, not IEEE results:
+// use them only where the argument is known to be regular (Jacobian determinants, arguments tested by the caller).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ double frcp(double x)
+{
+   double r;
+   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+   double e = fma(-x, r, 1.0);
+   r = fma(r, e, r);
+   e = fma(-x, r, 1.0);
+   return fma(r, e, r);
+}
+__device__ __forceinline__ double frsqrt(double x)
+{
+   double r;
+   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+   const double hx = 0.5 * x;
+   double e = fma(-hx * r, r, 0.5); // (1 - x r^2) / 2
+   r = fma(r, e, r);
+   e = fma(-hx * r, r, 0.5);
+   return fma(r, e, r);
+}
+#else
+inline double frcp(double x) { return 1.0 / x; }
+inline double frsqrt(double x) { return 1.0 / std::sqrt(x); }
+#endif
+
 // (value, structurally-zero) pair used inside the operators
 struct ZD
 {
@@ -254,18 +285,24 @@ template <int N, int O> MADB_HD AD<N, O> sqrt(const AD<N, O> &a)
 #if defined(__CUDA_ARCH__)
    // one reciprocal square root instead of a square root and two divisions:
    //   r = a^-1/2,  f = a r (one Newton correction),  f' = r/2,  f'' = -r^3/4
-   if (a.v > 0.0)
+   // branch-free (see frsqrt): denormal / huge arguments are rescaled by selects, 0 keeps the IEEE results of the
+   // reference (0, inf, -inf), negative arguments give NaN; only +inf differs (NaN instead of inf)
    {
-      const double r = ::rsqrt(a.v);
+      const bool tiny = a.v < 1e-290, huge = a.v > 1e290;
+      const double sc = tiny ? 0x1p600 : (huge ? 0x1p-600 : 1.0), rs = tiny ? 0x1p300 : (huge ? 0x1p-300 : 1.0);
+      double r = frsqrt(a.v * sc) * rs;
+      r = (a.v == 0.0) ? (double)INFINITY : r;
       double s = a.v * r;
       s = fma(0.5 * r, fma(-s, s, a.v), s);
+      s = (a.v == 0.0) ? 0.0 : s;
       const double f1 = 0.5 * r;
       return ad_chain(a, s, f1, -0.5 * f1 * (r * r));
    }
-#endif
+#else
    const double s = ::sqrt(a.v);
    const double f1 = 0.5 / s;
    return ad_chain(a, s, f1, -0.5 * f1 / a.v);
+#endif
 }
 template <int N, int O> MADB_HD AD<N, O> exp(const AD<N, O> &a)
 {

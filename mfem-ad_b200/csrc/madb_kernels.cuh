@@ -59,12 +59,12 @@ template <int DIM> MADB_HD void invert(const double (&J)[DIM][DIM], double (&Ji)
    if constexpr (DIM == 1)
    {
       det = J[0][0];
-      Ji[0][0] = 1.0 / det;
+      Ji[0][0] = frcp(det);
    }
    else if constexpr (DIM == 2)
    {
       det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-      const double t = 1.0 / det;
+      const double t = frcp(det);
       Ji[0][0] = J[1][1] * t;
       Ji[0][1] = -J[0][1] * t;
       Ji[1][0] = -J[1][0] * t;
@@ -76,7 +76,7 @@ template <int DIM> MADB_HD void invert(const double (&J)[DIM][DIM], double (&Ji)
       const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
       const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
       det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
-      const double t = 1.0 / det;
+      const double t = frcp(det);
       Ji[0][0] = c00 * t;
       Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * t;
       Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * t;
@@ -470,9 +470,19 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables
 /// The element vector is returned in r; the entries of the upper triangle of the element matrix are handed
 /// to sink(k, value), k = symidx(I, J), one by one at the end (they never all live in registers: the
 /// pulled-back Hessians of the NQ x NQ points are kept instead, 3 doubles per point).
-template <class Func, class Cfg, int MODE, class Sink>
+/// SMEM_IN: the element's inputs were gathered by somebody else (the loader warpgroup of k_patch_ws) into
+/// in[k * in_ld]: k = 0..7 vertex coordinates (vertex-major), k = 8.. the NVD dof values.
+/// Hooks (k_patch_ws): after_inputs() runs once the inputs are in registers, pre_matrix() between the quadrature
+/// loop (r is final there) and the emission of the matrix entries.
+struct NoHook
+{
+   __device__ __forceinline__ void operator()() const {}
+};
+template <class Func, class Cfg, int MODE, bool SMEM_IN = false, class Sink, class HookIn = NoHook, class HookPre = NoHook>
 __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a, const int t,
-                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink)
+                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink,
+                                                     const double *in = nullptr, const int in_ld = 0,
+                                                     HookIn &&after_inputs = HookIn(), HookPre &&pre_matrix = HookPre())
 {
    constexpr int ND = Cfg::template field<0>::ND1D, NQ = Cfg::NQ1D, NVD = Cfg::NVD;
    constexpr bool RES = (MODE & MODE_RES) != 0, JAC = (MODE & MODE_JAC) != 0, ACT = (MODE & MODE_ACT) != 0;
@@ -482,21 +492,33 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
 
    // ---- gather ---------------------------------------------------------------------------
    double X[4][2];
-#pragma unroll
-   for (int k = 0; k < 4; k++)
-   {
-      const int n = a.e2n[(size_t)k * a.stride + t];
-      X[k][0] = a.coords[(size_t)n * 2];
-      X[k][1] = a.coords[(size_t)n * 2 + 1];
-   }
    double u[ND][ND], vd[ACT ? ND : 1][ACT ? ND : 1];
-#pragma unroll
-   for (int i = 0; i < NVD; i++)
+   if constexpr (SMEM_IN)
    {
-      const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
-      u[i / ND][i % ND] = a.x[idx];
-      if constexpr (ACT) { vd[i / ND][i % ND] = a.v[idx]; }
+      static_assert(!ACT, "staged inputs: residual / Jacobian only");
+#pragma unroll
+      for (int k = 0; k < 8; k++) { X[k / 2][k % 2] = in[k * in_ld]; }
+#pragma unroll
+      for (int i = 0; i < NVD; i++) { u[i / ND][i % ND] = in[(8 + i) * in_ld]; }
    }
+   else
+   {
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+      {
+         const int n = a.e2n[(size_t)k * a.stride + t];
+         X[k][0] = a.coords[(size_t)n * 2];
+         X[k][1] = a.coords[(size_t)n * 2 + 1];
+      }
+#pragma unroll
+      for (int i = 0; i < NVD; i++)
+      {
+         const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
+         u[i / ND][i % ND] = a.x[idx];
+         if constexpr (ACT) { vd[i / ND][i % ND] = a.v[idx]; }
+      }
+   }
+   after_inputs();
    Func f;
    f.load(a.fparams);
 
@@ -569,7 +591,7 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
          }
          const double J01 = Jc1[q1][0], J11 = Jc1[q1][1];
          const double det = J00 * J11 - J01 * J10;
-         const double rdet = 1.0 / det;
+         const double rdet = frcp(det);
          // physical gradient = J^-T (ref grad) = adj^T (ref grad) / det,  adj = [[J11,-J01],[-J10,J00]]
          double xin[2];
          xin[0] = (J11 * rg0 - J10 * rg1) * rdet;
@@ -650,6 +672,7 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
 
    }
 
+   pre_matrix();
    // ---- element matrix: for every pair (i1 <= j1) of 1-D x-indices contract over q1, then emit the (i2, j2) block ----
    if constexpr (JAC)
    {
