@@ -470,19 +470,15 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables
 /// The element vector is returned in r; the entries of the upper triangle of the element matrix are handed
 /// to sink(k, value), k = symidx(I, J), one by one at the end (they never all live in registers: the
 /// pulled-back Hessians of the NQ x NQ points are kept instead, 3 doubles per point).
-/// SMEM_IN: the element's inputs were gathered by somebody else (the loader warpgroup of k_patch_ws) into
-/// in[k * in_ld]: k = 0..7 vertex coordinates (vertex-major), k = 8.. the NVD dof values.
-/// Hooks (k_patch_ws): after_inputs() runs once the inputs are in registers, pre_matrix() between the quadrature
-/// loop (r is final there) and the emission of the matrix entries.
+/// pre_matrix() (k_patch_ws) runs between the quadrature loop (r is final there) and the emission of the matrix entries.
 struct NoHook
 {
    __device__ __forceinline__ void operator()() const {}
 };
-template <class Func, class Cfg, int MODE, bool SMEM_IN = false, class Sink, class HookIn = NoHook, class HookPre = NoHook>
+template <class Func, class Cfg, int MODE, class Sink, class HookPre = NoHook>
 __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a, const int t,
                                                      double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink,
-                                                     const double *in = nullptr, const int in_ld = 0,
-                                                     HookIn &&after_inputs = HookIn(), HookPre &&pre_matrix = HookPre())
+                                                     HookPre &&pre_matrix = HookPre())
 {
    constexpr int ND = Cfg::template field<0>::ND1D, NQ = Cfg::NQ1D, NVD = Cfg::NVD;
    constexpr bool RES = (MODE & MODE_RES) != 0, JAC = (MODE & MODE_JAC) != 0, ACT = (MODE & MODE_ACT) != 0;
@@ -493,32 +489,20 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
    // ---- gather ---------------------------------------------------------------------------
    double X[4][2];
    double u[ND][ND], vd[ACT ? ND : 1][ACT ? ND : 1];
-   if constexpr (SMEM_IN)
+#pragma unroll
+   for (int k = 0; k < 4; k++)
    {
-      static_assert(!ACT, "staged inputs: residual / Jacobian only");
-#pragma unroll
-      for (int k = 0; k < 8; k++) { X[k / 2][k % 2] = in[k * in_ld]; }
-#pragma unroll
-      for (int i = 0; i < NVD; i++) { u[i / ND][i % ND] = in[(8 + i) * in_ld]; }
+      const int n = a.e2n[(size_t)k * a.stride + t];
+      X[k][0] = a.coords[(size_t)n * 2];
+      X[k][1] = a.coords[(size_t)n * 2 + 1];
    }
-   else
+#pragma unroll
+   for (int i = 0; i < NVD; i++)
    {
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-      {
-         const int n = a.e2n[(size_t)k * a.stride + t];
-         X[k][0] = a.coords[(size_t)n * 2];
-         X[k][1] = a.coords[(size_t)n * 2 + 1];
-      }
-#pragma unroll
-      for (int i = 0; i < NVD; i++)
-      {
-         const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
-         u[i / ND][i % ND] = a.x[idx];
-         if constexpr (ACT) { vd[i / ND][i % ND] = a.v[idx]; }
-      }
+      const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
+      u[i / ND][i % ND] = a.x[idx];
+      if constexpr (ACT) { vd[i / ND][i % ND] = a.v[idx]; }
    }
-   after_inputs();
    Func f;
    f.load(a.fparams);
 

@@ -15,6 +15,7 @@
 #include "madb_host.hpp"
 
 #include <algorithm>
+#include <cstdio>
 #include <array>
 #include <cmath>
 #include <cstring>
@@ -128,28 +129,42 @@ struct BlobWriter
 
 // Sources per destination (shared-memory locations, ascending element order) -> first source per destination
 // plus the fold list: in phase k (k >= 1) the k-th source of every destination is added onto its first source,
-// so afterwards the first source holds the complete sum.  Destinations with identical source lists (the (i,j)
+// so afterwards the first source holds the complete sum (ascending element order for every destination).  Destinations with identical source lists (the (i,j)
 // and (j,i) entries of a symmetric element matrix) share their folds.  Layout of `fold`:
 // 8 counts (phases 1..8; u32) followed by the (dst | src << 16) words, phase by phase.
 bool pack_sources(const std::vector<std::vector<unsigned short>> &srcs, int ndst, std::vector<unsigned short> &first,
                   std::vector<unsigned> &fold)
 {
    first.assign(ndst, 0);
-   std::vector<std::vector<unsigned>> ph(PATCH_MAXEXTRA + 1);
+   // one record per distinct first source: (number of further sources, first source, list)
+   std::vector<std::pair<std::pair<int, unsigned short>, const std::vector<unsigned short> *>> rec;
    for (int d = 0; d < ndst; d++)
    {
       const std::vector<unsigned short> &L = srcs[d];
-      if (L.empty() || (int)L.size() > 1 + PATCH_MAXEXTRA) { return false; }
+      if (L.empty()) { continue; } // dummy slot (alignment): never stored
+      if ((int)L.size() > 1 + PATCH_MAXEXTRA) { return false; }
       first[d] = L[0];
-      for (size_t k = 1; k < L.size(); k++) { ph[k].push_back((unsigned)L[0] | ((unsigned)L[k] << 16)); }
+      if (L.size() > 1) { rec.push_back({{-(int)(L.size() - 1), L[0]}, &L}); }
    }
+   // Order: most further sources first, then by destination.  The destinations of phase k are then exactly the first
+   // n_k records, in the same order in every phase: entry i of every phase has the same destination, the thread that
+   // owns index i (i mod #threads) performs all additions onto it in program order, and the phases need no barrier
+   // between them.
+   std::sort(rec.begin(), rec.end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+   rec.erase(std::unique(rec.begin(), rec.end(), [](const auto &x, const auto &y) { return x.first.second == y.first.second; }),
+             rec.end());
    fold.assign(8, 0u);
    for (int k = 1; k <= PATCH_MAXEXTRA; k++)
    {
-      std::sort(ph[k].begin(), ph[k].end());
-      ph[k].erase(std::unique(ph[k].begin(), ph[k].end()), ph[k].end());
-      fold[k - 1] = (unsigned)ph[k].size();
-      fold.insert(fold.end(), ph[k].begin(), ph[k].end());
+      unsigned n = 0;
+      for (const auto &r : rec)
+      {
+         const std::vector<unsigned short> &L = *r.second;
+         if ((int)L.size() <= k) { break; }
+         fold.push_back((unsigned)L[0] | ((unsigned)L[k] << 16));
+         n++;
+      }
+      fold[k - 1] = n;
    }
    return true;
 }
@@ -352,14 +367,22 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          const int *R = I.prows.data() + I.prow_off[p];
          const std::vector<long> &keys = ifc_keys[p];
          // interior rows: slots follow the CSR rows; consecutive CSR positions merge into runs
+         // A run that starts at an odd CSR position on an even slot (or vice versa) is shifted by one dummy slot (no
+         // source, no store): the device writes aligned pairs of chunks (64 consecutive positions) with 16-byte stores.
          base.assign(D.nrows, 0);
          int s = 0;
          run_s.clear(); run_g.clear();
+         gpos.clear();
          for (int lr = 0; lr < D.nrow_int; lr++)
          {
             const int r = R[lr];
-            if (lr == 0 || R[lr - 1] + 1 != r) { run_s.push_back(s); run_g.push_back(I.rowptr[r]); }
+            if (lr == 0 || R[lr - 1] + 1 != r)
+            {
+               if ((I.rowptr[r] ^ s) & 1) { gpos.push_back(-1); s++; }
+               run_s.push_back(s); run_g.push_back(I.rowptr[r]);
+            }
             base[lr] = s;
+            for (int g = I.rowptr[r]; g < I.rowptr[r + 1]; g++) { gpos.push_back(g); }
             s += I.rowptr[r + 1] - I.rowptr[r];
          }
          // interface entries only this patch contributes to: final values, by CSR position
@@ -419,19 +442,17 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          if (!pack_sources(srcs, D.nslots, first, fold)) { ok = false; continue; }
          D.nvfold = (int)fold.size();
          // CSR position of every directly written slot, packed per chunk of 32 slots:
-         // {g0, g1 - split, split, -1}: slots [0,split) of the chunk go to g0 + lane, the rest to g1 + (lane - split);
-         // {0, 0, 0, k >= 0}:   irregular chunk, the k-th of the list irr[]: explicit positions over[32 k + lane]
+         // {g0, g1 - split, split, n}: slots [0,split) of the chunk go to g0 + lane, the rest to g1 + (lane - split);
+         // {g0, 0, 0, 64} + {0,0,0,0}: an (even, odd) pair of full chunks covering 64 consecutive positions, g0 even;
+         // {0, 0, 0, 0}: nothing to write here (padding, second chunk of a pair, or an irregular chunk: more than one
+         //               break or a dummy slot -> explicit positions over[] / sources isrc[], in chunk order)
          {
-            gpos.assign(D.nexc, 0);
-            for (int r = 0; r < D.nruns; r++)
-            {
-               for (int q = run_s[r]; q < run_s[r + 1]; q++) { gpos[q] = run_g[r] + (q - run_s[r]); }
-            }
+            gpos.resize(D.nexc, -1);
             for (int q = D.nint; q < D.nexc; q++) { gpos[q] = xg[q - D.nint]; }
-            // chunk table padded to a multiple of 32 chunks (dummy chunks write nothing) so that the
-            // device loop needs no bounds checks; d[3] = number of lanes of the chunk that store
-            const int nchunk = ((D.nexc + 31) / 32 + 31) / 32 * 32;
-            chunks.assign((size_t)4 * nchunk, 0);
+            // chunk table padded to an even number of chunks (the device works on pairs);
+            // d[3] = number of lanes of the chunk that store
+            const int nchunk = ((D.nexc + 31) / 32 + 1) / 2 * 2;
+            chunks.assign((size_t)4 * (nchunk + 2), 0); // + one all-zero pair: target of out-of-range pair indices
             over.clear();
             isrc.clear();
             for (int c = 0; c < nchunk; c++)
@@ -442,6 +463,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
                {
                   if (gpos[b0 + q] != gpos[b0 + q - 1] + 1) { breaks++; if (breaks == 1) { split = q; } }
                }
+               for (int q = 0; q < n; q++) { if (gpos[b0 + q] < 0) { breaks = 2; } } // dummy slot: explicit positions
                int *d = &chunks[(size_t)4 * c];
                if (n == 0) { continue; }
                if (breaks <= 1)
@@ -460,13 +482,24 @@ bool patch_build_v(Integrator &I, PatchHost &H)
                   }
                }
             }
+            // pairs (2c, 2c+1) of full chunks covering 64 consecutive positions from an even one: {g0, 0, 0, 64}, {0,0,0,0}
+            for (int c = 0; c + 1 < nchunk; c += 2)
+            {
+               int *d = &chunks[(size_t)4 * c];
+               if (d[3] == 32 && d[2] == 32 && d[7] == 32 && d[6] == 32 && d[4] == d[0] + 32 && (d[0] & 1) == 0)
+               {
+                  d[1] = d[2] = 0;
+                  d[3] = 64;
+                  d[4] = d[5] = d[6] = d[7] = 0;
+               }
+            }
             while ((over.size() / 32) % 8 != 0) // pad the irregular list to a multiple of 8 chunks
             {
                for (int q = 0; q < 32; q++) { over.push_back(-1); isrc.push_back(0); }
             }
             D.nchunk = nchunk;
             D.nirr = (int)over.size() / 32;
-            first.resize(std::max<size_t>(first.size(), (size_t)32 * nchunk), 0); // padded so that chunk loads stay in bounds
+            first.resize(std::max<size_t>(first.size(), (size_t)32 * (nchunk + 2)), 0); // padded so that chunk loads stay in bounds
          }
          D.nvsrc = (int)first.size();
          BlobWriter W;
@@ -603,7 +636,7 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
          const unsigned short *vsrc = (const unsigned short *)vb;
          const unsigned *vfold = (const unsigned *)(vb + patch_al16(2 * D.nvsrc));
          const int *chunks = (const int *)((const unsigned char *)vfold + patch_al16(4 * D.nvfold));
-         const unsigned short *isrc = (const unsigned short *)((const unsigned char *)chunks + patch_al16(16 * D.nchunk));
+         const unsigned short *isrc = (const unsigned short *)((const unsigned char *)chunks + patch_al16(16 * (D.nchunk + 2)));
          const int *over = (const int *)((const unsigned char *)isrc + patch_al16(64 * D.nirr));
          int base = 8;
          for (int ph = 0; ph < 8; ph++)
@@ -617,7 +650,12 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
             const int *d = chunks + 4 * c;
             for (int lane = 0; lane < 32; lane++)
             {
-               if (lane < d[3]) { v[((lane < d[2]) ? d[0] : d[1]) + lane] = sA[vsrc[c * 32 + lane]]; }
+               if (d[3] == 64) // aligned pair of chunks: lane writes the slots 2 lane, 2 lane + 1 (one 16-byte store)
+               {
+                  v[d[0] + 2 * lane] = sA[vsrc[c * 32 + 2 * lane]];
+                  v[d[0] + 2 * lane + 1] = sA[vsrc[c * 32 + 2 * lane + 1]];
+               }
+               else if (lane < d[3]) { v[((lane < d[2]) ? d[0] : d[1]) + lane] = sA[vsrc[c * 32 + lane]]; }
             }
          }
          for (int k = 0; k < D.nirr * 32; k++) { if (over[k] >= 0) { v[over[k]] = sA[isrc[k]]; } }

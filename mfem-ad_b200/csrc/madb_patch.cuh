@@ -71,19 +71,19 @@ template <int BAR, int NT> __device__ __forceinline__ void patch_bar()
 template <int BAR, int NT, int U>
 __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
                                             const bool wy, const bool wv, const int tid, double *__restrict__ y,
-                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage, const int diag = 0)
+                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage)
 {
-   static_assert(NT % 32 == 0 && 32 % ((NT / 32) * U) == 0, "chunk tables are padded to multiples of 32 chunks");
+   static_assert(NT % 32 == 0, "whole warps");
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
 #define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
    const int nrows = D.nrows, nrow_int = D.nrow_int, nexc = D.nexc, nslots = D.nslots;
    const int o_yfold = o_yb + patch_al16(2 * nrows);
    const int o_vfold = o_vb + patch_al16(2 * D.nvsrc);
    // ---- fold: add the further sources of every row / slot onto its first source, phase by phase -------
-   // (inside one phase every location occurs at most once, as a destination or as a source)
+   // (every location is the destination or a source of exactly one entry chain)
    {
       int ybase = 8, vbase = 8;
-      for (int ph = 0; ph < ((diag & 4) ? 0 : 8); ph++)
+      for (int ph = 0; ph < 8; ph++)
       {
          const int ny = wy ? *(const int *)(base + o_yfold + 4 * ph) : 0;
          const int nv = wv ? *(const int *)(base + o_vfold + 4 * ph) : 0;
@@ -114,8 +114,10 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
          }
          ybase += ny;
          vbase += nv;
-         patch_bar<BAR, NT>();
       }
+      // entry i of every phase has the same destination (pack_sources) and is handled by the same thread: one barrier
+      // after the last phase is enough
+      patch_bar<BAR, NT>();
    }
    // ---- rows of the residual -----------------------------------------------------------
    if (wy)
@@ -133,33 +135,62 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
    {
       constexpr int NW = NT / 32;
       const int o_chunk = o_vfold + patch_al16(4 * D.nvfold);
-      const int o_isrc = o_chunk + patch_al16(16 * D.nchunk);
+      const int o_isrc = o_chunk + patch_al16(16 * (D.nchunk + 2));
       const int o_over = o_isrc + patch_al16(64 * D.nirr);
       const unsigned short *vsrc = (const unsigned short *)(base + o_vb);
       const int lane = tid & 31, warp = tid >> 5;
-      // directly written slots: CSR positions from the chunk descriptors {g0, g1 - split, split, n}
-      // (consecutive lanes -> consecutive positions); the tables are padded, no bounds checks
+      // directly written slots: CSR positions from the chunk descriptors, one (even, odd) pair of chunks per warp and
+      // step.  {g0, 0, 0, 64}: the pair covers 64 consecutive positions from an even one: lane l gathers the slots
+      // 2l, 2l+1 and writes them with one 16-byte store; otherwise {g0, g1 - split, split, n} per chunk (consecutive
+      // lanes -> consecutive positions).
       {
-         const int4 *cp = (const int4 *)(base + o_chunk) + warp;
-         const unsigned short *vp = vsrc + warp * 32 + lane;
-         for (int c0 = 0; c0 < D.nchunk; c0 += NW * U)
+         constexpr int UP = U / 2; // pairs per batch
+         static_assert(U >= 2 && U % 2 == 0, "chunk pairs");
+         const bool al16 = (reinterpret_cast<size_t>(vals) & 15) == 0;
+         const int4 *cp = (const int4 *)(base + o_chunk);
+         const int nchunk = D.nchunk; // even; one all-zero pair is appended to the tables (index nchunk)
+         for (int c0 = 2 * warp; c0 < nchunk; c0 += 2 * NW * UP)
          {
-            int g[U];
-            unsigned idx[U];
-            double v[U];
+            int gA[UP], gB[UP];
+            unsigned iA[UP], iB[UP];
+            double vA[UP], vB[UP];
 #pragma unroll
-            for (int u = 0; u < U; u++)
+            for (int u = 0; u < UP; u++)
             {
-               const int4 d = cp[u * NW];
-               idx[u] = vp[u * NW * 32];
-               g[u] = (lane < d.w) ? ((lane < d.z) ? d.x : d.y) + lane : -1;
+               const int c = c0 + 2 * u * NW, ce = (c < nchunk) ? c : nchunk; // past the table: the zero pair (no branch)
+               const int4 dA = cp[ce], dB = cp[ce + 1];
+               const unsigned short *vp = vsrc + 32 * ce;
+               const bool pair = dA.w == 64;
+               iA[u] = vp[pair ? 2 * lane : lane];
+               iB[u] = vp[pair ? 2 * lane + 1 : 32 + lane];
+               const int ga = (lane < dA.w) ? ((lane < dA.z) ? dA.x : dA.y) + lane : -1;
+               gA[u] = pair ? dA.x + 2 * lane : ga;
+               gB[u] = pair ? -2 : ((lane < dB.w) ? ((lane < dB.z) ? dB.x : dB.y) + lane : -1);
             }
 #pragma unroll
-            for (int u = 0; u < U; u++) { v[u] = MADB_SA(idx[u]); }
+            for (int u = 0; u < UP; u++)
+            {
+               vA[u] = MADB_SA(iA[u]);
+               vB[u] = MADB_SA(iB[u]);
+            }
 #pragma unroll
-            for (int u = 0; u < U; u++) { if (g[u] >= 0 && !(diag & 2)) { vals[g[u]] = v[u]; } }
-            cp += NW * U;
-            vp += NW * U * 32;
+            for (int u = 0; u < UP; u++)
+            {
+               if (gB[u] == -2)
+               {
+                  if (al16) { *reinterpret_cast<double2 *>(vals + gA[u]) = make_double2(vA[u], vB[u]); }
+                  else
+                  {
+                     vals[gA[u]] = vA[u];
+                     vals[gA[u] + 1] = vB[u];
+                  }
+               }
+               else
+               {
+                  if (gA[u] >= 0) { vals[gA[u]] = vA[u]; }
+                  if (gB[u] >= 0) { vals[gB[u]] = vB[u]; }
+               }
+            }
          }
       }
          // irregular chunks: explicit positions (-1: none)
@@ -328,34 +359,22 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 // blob[w] (bulk-copy completion).  Patches are dealt round-robin: p = (it * gridDim + cta) * 2 + w.
 // ---------------------------------------------------------------------------------------------
 constexpr int WS_WRITER_WG = 2;                              // writer warpgroups without a loader (all drain the same patch together)
-// warpgroups: writers ([0, 2), or [0, 1) with a loader), the loader (if any), then the 2 compute warpgroups
-constexpr int WS_THREADS = 4 * PATCH_PE;
+constexpr int WS_THREADS = (WS_WRITER_WG + 2) * PATCH_PE;
 // Register split after setmaxnreg.  setmaxnreg only redistributes the CTA's own launch allocation (512 x 128 = 64 K
-// here), and the total must stay BELOW it: an exact fit deadlocks the increase.  (A 5-warpgroup CTA launches with
-// 640 x 96 registers; the compute warpgroups then get 184 each, which spills: measured 0.378 ms vs 0.326 ms.)
-constexpr int WS_REG_COMPUTE = 208, WS_REG_WRITER = 40;      // 2 compute + 2 writer warpgroups
-constexpr int WS_REG_WRITER1 = 56, WS_REG_LOADER = 32;       // 2 compute + 1 writer + 1 loader warpgroup
-static_assert(2 * PATCH_PE * WS_REG_COMPUTE + 2 * PATCH_PE * WS_REG_WRITER <= 65536 - 1024, "setmaxnreg budget");
-static_assert(2 * PATCH_PE * WS_REG_COMPUTE + PATCH_PE * (WS_REG_WRITER1 + WS_REG_LOADER) <= 65536 - 1024, "setmaxnreg budget");
+// registers here) and the total must stay BELOW it: an exact fit deadlocks the increase.
+constexpr int WS_REG_COMPUTE = 208, WS_REG_WRITER = 40;
+static_assert(2 * PATCH_PE * WS_REG_COMPUTE + WS_WRITER_WG * PATCH_PE * WS_REG_WRITER <= 65536 - 1024, "setmaxnreg budget");
 
-/// LOADER (sum-factorised 2-D path only): warpgroup 1 gathers the inputs of the next patch of either compute
-/// warpgroup (element->vertex map -> coordinates, element->dof map -> state) into shared memory while the compute
-/// warpgroups work; they never wait on global memory (ncu, r01: 32 % of their samples were long-scoreboard stalls of
-/// the two dependent loads of the gather, twice as many as without the concurrent CSR write-out).  Hand-off:
-/// in_full[w] (loader -> compute), in_empty[w] (compute -> loader, as soon as the inputs are in registers).
-template <class Func, class Cfg, bool UNROLLQ, bool LOADER>
+template <class Func, class Cfg, bool UNROLLQ>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constant__ AsmArgs<Func, Cfg> a,
                                                               const __grid_constant__ PatchDev P)
 {
    constexpr int MODE = MODE_RES | MODE_JAC;
    constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = PATCH_PE, LD = PATCH_LD;
    constexpr int SR_BYTES = patch_al16(NVD * LD * 8), SA_BYTES = patch_al16(NSYM * LD * 8);
-   constexpr int NWR = LOADER ? 1 : WS_WRITER_WG, NT_W = NWR * PE; // writer warpgroups / threads
-   constexpr int WG_C0 = 2;                                        // first compute warpgroup
-   constexpr int NIN = 8 + NVD, IN_BYTES = NIN * PE * 8;           // staged inputs of one patch: [NIN][PE]
-   static_assert(!LOADER || use_sf2d<Func, Cfg, MODE>(), "the loader stages the inputs of the sum-factorised 2-D path");
+   constexpr int NT_W = WS_WRITER_WG * PE, WG_C0 = WS_WRITER_WG; // writer threads, first compute warpgroup
    extern __shared__ __align__(16) unsigned char smraw[];
-   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blob[2], bar_in_full[2], bar_in_empty[2];
+   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blob[2];
    __shared__ PatchDesc Dd[2];
    // warpgroup index, made warp-uniform for the compiler (uniform registers instead of spilled vector registers)
    const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), tid = threadIdx.x & (PE - 1);
@@ -368,8 +387,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          mbar_init(&bar_full[k], PE);
          mbar_init(&bar_empty[k], NT_W);
          mbar_init(&bar_blob[k], 1);
-         mbar_init(&bar_in_full[k], PE / 2);
-         mbar_init(&bar_in_empty[k], PE);
       }
    }
    __syncthreads();
@@ -380,7 +397,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
       asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_COMPUTE));
       const int w = wg - WG_C0;
       unsigned char *base = smraw + (size_t)w * wg_bytes;
-      const double *in = (const double *)(smraw + 2 * (size_t)wg_bytes + (size_t)w * IN_BYTES) + tid;
       for (int it = 0;; it++)
       {
          const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
@@ -391,16 +407,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          const unsigned par = (it & 1) ^ 1; // parity of "the writer has drained the previous patch of this buffer"
          if constexpr (use_sf2d<Func, Cfg, MODE>())
          {
-            if constexpr (LOADER) { mbar_wait(&bar_in_full[w], it & 1); }
             if (valid)
             {
-               element_compute_sf2d<Func, Cfg, MODE, LOADER>(
-                  a, t, r, [&](int k, double v) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = v; }, in, PE,
-                  [&]()
-                  {
-                     // the inputs are in registers: the loader may fetch those of the next patch
-                     if constexpr (LOADER) { mbar_arrive(&bar_in_empty[w]); }
-                  },
+               element_compute_sf2d<Func, Cfg, MODE>(
+                  a, t, r, [&](int k, double v) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = v; },
                   [&]()
                   {
                      // the element vector is final: wait for the buffer and store it before the matrix phase
@@ -409,10 +419,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
 #pragma unroll
                      for (int i = 0; i < NVD; i++) { *(double *)(base + 8 * (i * LD + tid)) = r[i]; }
                   });
-            }
-            else
-            {
-               if constexpr (LOADER) { mbar_arrive(&bar_in_empty[w]); }
             }
          }
          else
@@ -431,64 +437,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          mbar_arrive(&bar_full[w]);
       }
    }
-   else if (LOADER && wg == NWR)
-   {
-      // ================= loader warpgroup =================
-      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_LOADER));
-      if constexpr (LOADER)
-      {
-         // warps 0,1 serve compute warpgroup 0, warps 2,3 serve warpgroup 1 (independent loops: no coupling between
-         // the two); every thread gathers the inputs of two elements
-         const int w = __shfl_sync(0xffffffffu, tid >> 6, 0), ltid = tid & 63;
-         double *dst0 = (double *)(smraw + 2 * (size_t)wg_bytes + (size_t)w * IN_BYTES);
-         for (int it = 0;; it++)
-         {
-            const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
-            if (p >= P.npatch) { break; }
-            mbar_wait(&bar_in_empty[w], (it & 1) ^ 1); // the compute warpgroup has read the previous inputs
-#pragma unroll 1
-            for (int h = 0; h < 2; h++)
-            {
-               const int l = ltid + 64 * h, t = p * PE + l;
-               double *dst = dst0 + l;
-               if (t < a.end)
-               {
-                  int n[4];
-#pragma unroll
-                  for (int k = 0; k < 4; k++) { n[k] = __ldg(a.e2n + (size_t)k * a.stride + t); }
-                  double2 c[4];
-#pragma unroll
-                  for (int k = 0; k < 4; k++) { c[k] = __ldg((const double2 *)a.coords + n[k]); }
-#pragma unroll
-                  for (int k = 0; k < 4; k++)
-                  {
-                     dst[(2 * k) * PE] = c[k].x;
-                     dst[(2 * k + 1) * PE] = c[k].y;
-                  }
-                  constexpr int CH = 5; // dof values in chunks (register budget)
-#pragma unroll
-                  for (int i0 = 0; i0 < NVD; i0 += CH)
-                  {
-                     int idx[CH];
-                     double xv[CH];
-#pragma unroll
-                     for (int i = 0; i < CH; i++) { if (i0 + i < NVD) { idx[i] = __ldg(a.vmap + (size_t)(i0 + i) * a.stride + t) & 0x7fffffff; } }
-#pragma unroll
-                     for (int i = 0; i < CH; i++) { if (i0 + i < NVD) { xv[i] = a.x[idx[i]]; } }
-#pragma unroll
-                     for (int i = 0; i < CH; i++) { if (i0 + i < NVD) { dst[(8 + i0 + i) * PE] = xv[i]; } }
-                  }
-               }
-            }
-            mbar_arrive(&bar_in_full[w]);
-         }
-      }
-   }
    else
    {
       // ================= writer warpgroup(s) =================
-      if constexpr (LOADER) { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_WRITER1)); }
-      else { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_WRITER)); }
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_WRITER));
       const int wtid = threadIdx.x; // 0..NT_W-1
       auto prefetch = [&](int w, int p)
       {
@@ -523,8 +475,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
             unsigned char *base = smraw + (size_t)w * wg_bytes;
             mbar_wait(&bar_blob[w], it & 1); // maps and descriptor (Dd[w], stable until the next prefetch) have landed
             mbar_wait(&bar_full[w], it & 1); // the compute warpgroup has staged the patch
-            if (!((a.write_vals >> 1) & 1))
-            patch_drain<1, NT_W, (NT_W == 128) ? 4 : 32 / (NT_W / 32)>(base, o_sa, o_yb, o_vb, Dd[w], wy, true, wtid, a.y, a.vals, P.ystage, P.vstage, a.write_vals >> 1);
+            patch_drain<1, NT_W, 32 / (NT_W / 32)>(base, o_sa, o_yb, o_vb, Dd[w], wy, true, wtid, a.y, a.vals, P.ystage, P.vstage);
             mbar_arrive(&bar_empty[w]);
             // all writer threads are done with the maps of this buffer: fetch those of its next patch
             patch_bar<1, NT_W>();
@@ -603,40 +554,20 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       static const bool use_ws = getenv("MADB_PATCH_WS") ? atoi(getenv("MADB_PATCH_WS")) != 0 : true;
       if (wv && use_ws)
       {
-         constexpr bool SF = use_sf2d<Func, Cfg, MODE>();
+         auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
          const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yblob + P.max_vblob) + 16;
-         const int in_bytes = SF ? 2 * (8 + Cfg::NVD) * PATCH_PE * 8 : 0;
-         static const bool want_loader = getenv("MADB_WS_LOADER") ? atoi(getenv("MADB_WS_LOADER")) != 0 : true;
          if (nsm == 0) { cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
-         const bool loader = SF && want_loader && ws_bytes + in_bytes <= 226 * 1024;
-         const int bytes = ws_bytes + (loader ? in_bytes : 0);
-         if (bytes <= 226 * 1024)
+         if (ws_bytes <= 226 * 1024)
          {
-            static int ws_set2_dev[64] = {0};
-            int &set = loader ? ws_set2_dev[dev] : ws_smem_set;
-            const int grid = std::min(nsm, (P.npatch + 1) / 2);
-            static const int diag = getenv("MADB_DIAG") ? atoi(getenv("MADB_DIAG")) : 0;
-            const_cast<AsmArgs<Func, Cfg> &>(a).write_vals = 1 | (diag << 1);
-            cudaError_t e = cudaSuccess;
-            if constexpr (SF)
+            if (ws_bytes > ws_smem_set)
             {
-               if (loader)
-               {
-                  auto kws = k_patch_ws<Func, Cfg, UNROLLQ, true>;
-                  if (bytes > set) { e = cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); set = bytes; }
-                  if (e != cudaSuccess) { return (int)e; }
-                  kws<<<grid, WS_THREADS, bytes, L.stream>>>(a, P);
-                  done = true;
-               }
-            }
-            if (!done)
-            {
-               auto kws = k_patch_ws<Func, Cfg, UNROLLQ, false>;
-               if (bytes > set) { e = cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); set = bytes; }
+               const cudaError_t e = cudaFuncSetAttribute(kws, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_bytes);
                if (e != cudaSuccess) { return (int)e; }
-               kws<<<grid, WS_THREADS, bytes, L.stream>>>(a, P);
-               done = true;
+               ws_smem_set = ws_bytes;
             }
+            const int grid = std::min(nsm, (P.npatch + 1) / 2);
+            kws<<<grid, WS_THREADS, ws_bytes, L.stream>>>(a, P);
+            done = true;
          }
       }
    }
