@@ -58,10 +58,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 }
 
 /// barrier of the NT threads draining one patch: the whole CTA (BAR = 0) or the writer warps (named barrier BAR)
-template <int BAR, int NT> __device__ __forceinline__ void patch_bar()
+template <int BAR, int NT> __device__ __forceinline__ void patch_bar(const int id = BAR)
 {
    if constexpr (BAR == 0) { __syncthreads(); }
-   else { asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory"); }
+   else { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 }
 
 /// Fold + gather + write-out of one staged patch by NT threads (tid = 0..NT-1).
@@ -71,7 +71,7 @@ template <int BAR, int NT> __device__ __forceinline__ void patch_bar()
 template <int BAR, int NT, int U>
 __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
                                             const bool wy, const bool wv, const int tid, double *__restrict__ y,
-                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage)
+                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage, const int bar_id = BAR)
 {
    static_assert(NT % 32 == 0, "whole warps");
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
@@ -117,7 +117,7 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
       }
       // entry i of every phase has the same destination (pack_sources) and is handled by the same thread: one barrier
       // after the last phase is enough
-      patch_bar<BAR, NT>();
+      patch_bar<BAR, NT>(bar_id);
    }
    // ---- rows of the residual -----------------------------------------------------------
    if (wy)
@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
       for (int k = 0; k < 2; k++)
       {
          mbar_init(&bar_full[k], PE);
-         mbar_init(&bar_empty[k], NT_W);
+         mbar_init(&bar_empty[k], PE);
          mbar_init(&bar_blob[k], 1);
       }
    }
@@ -441,7 +441,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
    {
       // ================= writer warpgroup(s) =================
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_WRITER));
-      const int wtid = threadIdx.x; // 0..NT_W-1
+      // writer warpgroup ww drains the patches of compute warpgroup ww (own named barrier): the two write-outs run
+      // concurrently and the compute warpgroups are not coupled through a common drain order
+      const int ww = wg, wtid = tid; // 0..PE-1
       auto prefetch = [&](int w, int p)
       {
          // one thread: descriptor to shared memory, then the bulk copies of the patch's maps
@@ -454,35 +456,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          if (yb) { bulk_g2s(mb, P.yblob + (size_t)Dd[w].yblob_off * 16, yb, &bar_blob[w]); }
          if (vb) { bulk_g2s(mb + P.max_yblob, P.vblob + (size_t)Dd[w].vblob_off * 16, vb, &bar_blob[w]); }
       };
-      if (wtid == 0)
       {
-         for (int w = 0; w < 2; w++)
-         {
-            const int p0 = (int)blockIdx.x * 2 + w;
-            if (p0 < P.npatch) { prefetch(w, p0); }
-         }
+         const int p0 = (int)blockIdx.x * 2 + ww;
+         if (wtid == 0 && p0 < P.npatch) { prefetch(ww, p0); }
       }
       const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_vb = o_yb + P.max_yblob;
+      unsigned char *base = smraw + (size_t)ww * wg_bytes;
       for (int it = 0;; it++)
       {
-         bool any = false;
-#pragma unroll 1
-         for (int w = 0; w < 2; w++)
-         {
-            const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
-            if (p >= P.npatch) { continue; }
-            any = true;
-            unsigned char *base = smraw + (size_t)w * wg_bytes;
-            mbar_wait(&bar_blob[w], it & 1); // maps and descriptor (Dd[w], stable until the next prefetch) have landed
-            mbar_wait(&bar_full[w], it & 1); // the compute warpgroup has staged the patch
-            patch_drain<1, NT_W, 32 / (NT_W / 32)>(base, o_sa, o_yb, o_vb, Dd[w], wy, true, wtid, a.y, a.vals, P.ystage, P.vstage);
-            mbar_arrive(&bar_empty[w]);
-            // all writer threads are done with the maps of this buffer: fetch those of its next patch
-            patch_bar<1, NT_W>();
-            const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
-            if (wtid == 0 && pn < P.npatch) { prefetch(w, pn); }
-         }
-         if (!any) { break; }
+         const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + ww;
+         if (p >= P.npatch) { break; }
+         mbar_wait(&bar_blob[ww], it & 1); // maps and descriptor (Dd[ww], stable until the next prefetch) have landed
+         mbar_wait(&bar_full[ww], it & 1); // the compute warpgroup has staged the patch
+         patch_drain<1, PE, 4>(base, o_sa, o_yb, o_vb, Dd[ww], wy, true, wtid, a.y, a.vals, P.ystage, P.vstage, 1 + ww);
+         mbar_arrive(&bar_empty[ww]);
+         // all threads of this warpgroup are done with the maps of the buffer: fetch those of its next patch
+         patch_bar<1, PE>(1 + ww);
+         const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + ww;
+         if (wtid == 0 && pn < P.npatch) { prefetch(ww, pn); }
       }
    }
 }
