@@ -343,10 +343,17 @@ def main():
     ap.add_argument("--n", type=int, default=1000, help="elements per direction per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 themselves (NCCL prints
+    # its version banner there) are sent to stderr; the line is written to the original descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
