@@ -14,6 +14,7 @@ using PGObsFD = PGFunctional<ObstacleEnergy<2>, FermiDiracEntropy, 0>;
 using LamPGObsFD = LambdaPGFunctional<ObstacleEnergy<2>, FermiDiracEntropy, 0>;
 
 MADB_EVAL_INSTANCE("ex0", Ex0Function)
+MADB_EVAL_INSTANCE("sqrtprobe", SqrtProbe)
 MADB_EVAL_INSTANCE("minsurf", MinS2)
 MADB_EVAL_INSTANCE("shannon", ShannonEntropy)
 MADB_EVAL_INSTANCE("fermidirac", FermiDiracEntropy)

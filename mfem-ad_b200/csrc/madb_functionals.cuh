@@ -29,6 +29,16 @@ struct Ex0Function
    }
 };
 
+// Probe of the AD square root (a user-body building block; mfem's dual sqrt: value sqrt(a), derivative 0.5/sqrt(a)):
+// f = sqrt(x0) x1.  The device sqrt is branch-free (madb_ad.cuh); the probe pins its results at 0, denormal, tiny,
+// huge and negative arguments against the IEEE results of the reference's formula (tests/test_gpu_latent.py).
+struct SqrtProbe
+{
+   static constexpr int N_INPUT = 2, N_PARAM = 0, N_QPRM = 0;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *) const { return sqrt(x[0]) * x[1]; }
+};
+
 // ex0.cpp:23-35  F = (sin(x0 x1), cos(x0 x1 x2))   (ADVectorFunction, AD_VEC_IMPL)
 struct Ex0VectorFunction
 {

@@ -62,3 +62,26 @@ def test_ex4_mapped_primal_coefficient(ctx):
     ref = of.coefficient(psi, 1)
     assert np.max(np.abs(grd - ref)) <= 1e-13
     assert grd.min() > 0.0 and grd.max() < 0.5
+
+
+def test_ad_sqrt_edge_cases(ctx):
+    """The device AD square root is branch-free (MUFU seed + Newton steps, csrc/madb_ad.cuh); it must reproduce the
+    reference's dual sqrt (value sqrt(a), f' = 0.5/sqrt(a), f'' = -0.5 f'/a) to rounding for regular arguments and
+    its IEEE results (0 / inf / -inf / NaN) at 0, at denormal, tiny and huge arguments and for negative ones."""
+    import mfem_ad_b200 as M
+    f = M.Functional(ctx, "sqrtprobe")  # f = sqrt(x0) * x1
+    x0 = np.array([0.0, 5e-324, 1e-320, 1e-300, 3e-291, 1e-200, 0.3, 1.0, 7.0, 1e200, 7e289, 1e300, 1.7e308, -1.0])
+    x1 = np.full_like(x0, 1.5)
+    v, g, h = f.eval(np.stack([x0, x1], axis=1))
+    with np.errstate(all="ignore"):
+        s = np.sqrt(x0)
+        f1 = 0.5 / s
+        f2 = -0.5 * f1 / x0
+        ev, eg0, eg1, eh00, eh01 = s * x1, f1 * x1, s, f2 * x1, f1
+    for got, exp in ((v, ev), (g[:, 0], eg0), (g[:, 1], eg1), (h[:, 0, 0], eh00), (h[:, 0, 1], eh01), (h[:, 1, 0], eh01)):
+        fin = np.isfinite(exp)
+        assert np.array_equal(np.isnan(got), np.isnan(exp)), (got, exp)
+        assert np.array_equal(got[np.isinf(exp)], exp[np.isinf(exp)]), (got, exp)
+        # finite results: to rounding (the second derivative of tiny arguments overflows in both formulas)
+        assert np.allclose(got[fin], exp[fin], rtol=4e-16 * 8, atol=0.0), (got[fin], exp[fin])
+    assert np.all(h[:, 1, 1][x0 > 0] == 0.0)
