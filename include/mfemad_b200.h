@@ -159,7 +159,8 @@ int madb_integrator_patch_stats(madb_integrator *I, int64_t *out);
 /* Host-only self test of the patch-assembly maps (no CUDA device needed): builds the maps for one H1 space of the
  * given order / vdim on the given mesh, assembles integer-valued element vectors and matrices directly and through
  * an emulation of the kernels' use of the maps, and returns the largest difference (must be 0).
- * stats[0..5]: patches, interface dofs, interface matrix entries, staged matrix partials, largest map blob (bytes), nnz. */
+ * stats[0..7]: patches, interface dofs, interface matrix entries, staged matrix partials, largest map blob (bytes), nnz,
+ * CSR entries written as aligned pairs of chunks (16-byte stores), reserved (0). */
 int madb_patch_selftest(int dim, int ne, const int32_t *e2n, int nnodes, const double *coords, int order, int vdim,
                         int ordering, int ndofs, const int32_t *e2l, double *max_err, int64_t *stats);
 

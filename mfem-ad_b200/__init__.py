@@ -344,11 +344,11 @@ def patch_selftest(mesh, space):
     """Host-only check of the patch-assembly maps (madb_patch_selftest): returns (max_err, stats dict)."""
     e2n, coords, e2l = _i32(mesh["e2n"]), _f64(mesh["coords"]), _i32(space["e2l"])
     err = C.c_double()
-    st = (C.c_int64 * 6)()
+    st = (C.c_int64 * 8)()
     _check(lib().madb_patch_selftest(mesh["dim"], e2n.shape[0], e2n.ctypes.data, coords.shape[0], coords.ctypes.data,
                                      space["order"], space.get("vdim", 1), space.get("ordering", BYNODES), space["ndofs"],
                                      e2l.ctypes.data, C.byref(err), st))
-    keys = ("patches", "ifc_dofs", "ifc_entries", "staged_vals", "max_blob_bytes", "nnz")
+    keys = ("patches", "ifc_dofs", "ifc_entries", "staged_vals", "max_blob_bytes", "nnz", "paired_entries")
     return err.value, dict(zip(keys, [int(v) for v in st]))
 
 

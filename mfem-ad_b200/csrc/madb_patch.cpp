@@ -598,6 +598,7 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
    }
    // emulation of the kernels
    std::vector<double> ystage(std::max<long>(HY.stage_size, 1), -555.0), vstage(std::max<long>(HV.stage_size, 1), -555.0);
+   long npaired = 0; // CSR entries written through the 16-byte path
    std::vector<double> sR((size_t)nvd * ld), sA((size_t)nsym * ld);
    for (int p = 0; p < np; p++)
    {
@@ -652,6 +653,7 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
             {
                if (d[3] == 64) // aligned pair of chunks: lane writes the slots 2 lane, 2 lane + 1 (one 16-byte store)
                {
+                  if (lane == 0) { npaired += 64; }
                   v[d[0] + 2 * lane] = sA[vsrc[c * 32 + 2 * lane]];
                   v[d[0] + 2 * lane + 1] = sA[vsrc[c * 32 + 2 * lane + 1]];
                }
@@ -691,6 +693,8 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
       stats[3] = HV.stage_size;
       stats[4] = I.max_vblob;
       stats[5] = nnz;
+      stats[6] = npaired;
+      stats[7] = 0;
    }
    return 0;
 }

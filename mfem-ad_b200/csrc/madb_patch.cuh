@@ -8,10 +8,11 @@
 //   2. the element vector / upper-triangular element matrix is staged in shared memory
 //      ([entry][element], padded leading dimension); the sum-factorised path streams its entries there
 //   3. fold: the further sources of every row / CSR entry ("slot") are added onto its first source, phase by
-//      phase (ascending element order); then every slot is read from its first source and written once,
-//      coalesced: interior rows straight to y / the CSR values (chunk descriptors: 32 consecutive slots ->
-//      CSR positions), entries of interface rows only this patch touches through explicit positions,
-//      entries shared with other patches to a staging buffer
+//      phase (ascending element order; the same thread owns a destination in every phase, one barrier at the
+//      end); then every slot is read from its first source and written once, coalesced: interior rows straight
+//      to y / the CSR values (chunk descriptors: an aligned pair of chunks = 64 consecutive CSR positions with
+//      16-byte stores, otherwise 32 consecutive slots -> CSR positions), entries of interface rows only this
+//      patch touches through explicit positions, entries shared with other patches to a staging buffer
 //   4. k_ifc_reduce adds the staged partial rows / entries in ascending patch order.
 // Two kernels: k_patch (one CTA per patch) and k_patch_ws (persistent, warp-specialised: compute warpgroups
 // and writer warpgroups overlap steps 1-2 and 3 of consecutive patches; fused residual + Jacobian).
@@ -349,16 +350,18 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised persistent variant (fused residual + Jacobian): one CTA per SM, three warpgroups.
-//   warpgroups 1,2 (224 registers/thread after setmaxnreg): element computation, patch after patch;
-//                  each streams its element vectors / matrices into its own shared-memory buffer
-//   warpgroup 0    (64 registers/thread): folds, gathers and writes the rows of the finished patches
-//                  of both compute warpgroups while those are already working on their next patch;
-//                  it also prefetches the gather maps of the next patch with cp.async.bulk.
+// Warp-specialised persistent variant (fused residual + Jacobian): one CTA per SM, four warpgroups.
+//   warpgroups 2,3 (208 registers/thread after setmaxnreg): element computation, patch after patch;
+//                  each stores its element vectors (before the matrix phase) and streams its element
+//                  matrices into its own shared-memory buffer
+//   warpgroups 0,1 (40 registers/thread): writer warpgroup w folds, gathers and writes the rows of the
+//                  finished patches of compute warpgroup w while that one is already working on its next
+//                  patch (independent drains, own named barrier); it also prefetches the gather maps of the
+//                  next patch with cp.async.bulk.
 // Hand-off through mbarriers: full[w] (compute -> writer), empty[w] (writer -> compute),
 // blob[w] (bulk-copy completion).  Patches are dealt round-robin: p = (it * gridDim + cta) * 2 + w.
 // ---------------------------------------------------------------------------------------------
-constexpr int WS_WRITER_WG = 2;                              // writer warpgroups without a loader (all drain the same patch together)
+constexpr int WS_WRITER_WG = 2;                              // writer warpgroups: one per compute warpgroup
 constexpr int WS_THREADS = (WS_WRITER_WG + 2) * PATCH_PE;
 // Register split after setmaxnreg.  setmaxnreg only redistributes the CTA's own launch allocation (512 x 128 = 64 K
 // registers here) and the total must stay BELOW it: an exact fit deadlocks the increase.
@@ -372,7 +375,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
    constexpr int MODE = MODE_RES | MODE_JAC;
    constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = PATCH_PE, LD = PATCH_LD;
    constexpr int SR_BYTES = patch_al16(NVD * LD * 8), SA_BYTES = patch_al16(NSYM * LD * 8);
-   constexpr int NT_W = WS_WRITER_WG * PE, WG_C0 = WS_WRITER_WG; // writer threads, first compute warpgroup
+   constexpr int WG_C0 = WS_WRITER_WG; // first compute warpgroup
+   static_assert(WS_WRITER_WG == 2, "writer warpgroup w serves compute warpgroup w");
    extern __shared__ __align__(16) unsigned char smraw[];
    __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blob[2];
    __shared__ PatchDesc Dd[2];

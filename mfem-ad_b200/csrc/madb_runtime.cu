@@ -952,9 +952,9 @@ extern "C"
       Space s;
       s.ctx = nullptr; s.mesh = &m; s.basis = BASIS_H1; s.order = order; s.vdim = vdim; s.ordering = ordering; s.ndofs = ndofs;
       s.e2l.assign(e2l, e2l + (size_t)ne * s.nd_el());
-      long st[6] = {0, 0, 0, 0, 0, 0};
+      long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const int rc = patch_selftest(m, s, max_err, st);
-      if (stats) { for (int k = 0; k < 6; k++) { stats[k] = st[k]; } }
+      if (stats) { for (int k = 0; k < 8; k++) { stats[k] = st[k]; } }
       return rc;
    }
 
