@@ -148,6 +148,15 @@ int madb_unpack_multi(madb_ctx *ctx, int n, const int32_t *src4, const int32_t *
  * quad_order < 0 selects the default 2*max_order+2 (src/_ad_intg.hpp:99-105, :298-313). */
 int madb_integrator_create(madb_ctx *ctx, int nfields, madb_space *const *spaces, const int *modes,
                            const int *roles, madb_functional *f, int quad_order, madb_integrator **out);
+/* Same with flags.  MADB_INTEG_BLOCK: treat the integrator as ADBlockNonlinearFormIntegrator even with one input
+ * space.  It matters for ONE vector space with MADB_VECTOR only: without the flag the Jacobian reproduces the
+ * arithmetic of ADNonlinearFormIntegrator<...|VECTOR>::AssembleElementGrad as written (src/ad_intg.hpp:283-326:
+ * contiguous windows of Hx, untransposed mirror blocks; it equals the intended B H B^T only for special Hessians,
+ * e.g. LinearElasticityEnergy with lambda == mu as in ex3.cpp:58 -- SURVEY H1); with the flag the index-consistent
+ * contraction of the block integrator (src/ad_intg.hpp:700-727) is used.  Residual and energy are the same in both. */
+enum { MADB_INTEG_BLOCK = 1 };
+int madb_integrator_create_ex(madb_ctx *ctx, int nfields, madb_space *const *spaces, const int *modes,
+                              const int *roles, madb_functional *f, int quad_order, int flags, madb_integrator **out);
 int madb_integrator_destroy(madb_integrator *I);
 
 /* sizes: total dofs of the concatenated input blocks, quadrature points per element */
@@ -194,6 +203,21 @@ int madb_integrator_assemble(madb_integrator *I, const double *x, double *y, dou
  * (src/ad_native.hpp:267-323; ex4.cpp:124-128,200: the latent->primal map grad E*(psi) as a
  * QuadratureFunction).  value [ne*nq] and/or grad [ne*nq*n_input] (may be NULL), layout [e][q][.] */
 int madb_integrator_coefficient(madb_integrator *I, const double *x, double *value, double *grad);
+/* DifferentiableCoefficient::Hessian().Eval (HessianCoefficient, src/ad_native.hpp:300-323) at the rule's points:
+ * value [ne*nq], grad [ne*nq*n], hess [ne*nq*n*n] (symmetric; any output may be NULL). */
+int madb_integrator_coefficient_hessian(madb_integrator *I, const double *x, double *value, double *grad, double *hess);
+/* ParametrizedFunctional::ParamGradient::Eval (src/mmto.hpp:54-70, src/mmto.cpp:4-38) at the rule's points for an
+ * integrator whose INPUT field is the design and whose PARAM field is the state ("designcompliance" kinds):
+ * J [ne*nq*param_dim], value [ne*nq] = F (may be NULL).
+ *   MADB_PARAMGRAD_AS_WRITTEN  the reference's result: slot i of the evaluator is overwritten with df_i/drho_j while the
+ *                              other parameter functions keep their values (:25-37), i.e. dF/drho_j + (m-1) F
+ *   MADB_PARAMGRAD_DERIVATIVE  the derivative dF/drho_j itself (corrected variant) */
+enum { MADB_PARAMGRAD_AS_WRITTEN = 0, MADB_PARAMGRAD_DERIVATIVE = 1 };
+int madb_integrator_param_gradient(madb_integrator *I, const double *design, double *value, double *J, int variant);
+/* Physical coordinates of the rule's points, xyz [ne*nq*dim] (host or device pointer).  Evaluator sources of Coefficient /
+ * VectorCoefficient / MatrixCoefficient type (src/ad_native.hpp:56-61; Eval at (Tr, ip), src/ad_native.cpp:132-165) are
+ * host callbacks: sample them at these points and pass the result with madb_integrator_set_param_qf. */
+int madb_integrator_qpoint_coords(madb_integrator *I, double *xyz);
 /* matrix-free Jacobian action y = J(x) v (no reference equivalent; config 3) */
 int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y);
 

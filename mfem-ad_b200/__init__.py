@@ -23,6 +23,8 @@ QVALUE, VALUE, GRAD, DIV, CURL, HESSIAN, VECTOR, VECFE = (1 << i for i in range(
 BASIS_H1, BASIS_L2 = 0, 1
 BYNODES, BYVDIM = 0, 1
 ROLE_INPUT, ROLE_PARAM = 0, 1
+INTEG_BLOCK = 1
+PARAMGRAD_AS_WRITTEN, PARAMGRAD_DERIVATIVE = 0, 1
 
 _lib = None
 
@@ -62,7 +64,11 @@ def lib():
         L.madb_unpack_multi.argtypes = [vp, C.c_int, ip, ip, dp, dp, C.c_int]
         L.madb_lvpp_update.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_double)]
         L.madb_integrator_create.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, pp]
+        L.madb_integrator_create_ex.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, C.c_int, pp]
         L.madb_integrator_destroy.argtypes = [vp]
+        L.madb_integrator_coefficient_hessian.argtypes = [vp, dp, dp, dp, dp]
+        L.madb_integrator_param_gradient.argtypes = [vp, dp, dp, dp, C.c_int]
+        L.madb_integrator_qpoint_coords.argtypes = [vp, dp]
         L.madb_integrator_sizes.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.madb_integrator_patch_stats.argtypes = [vp, C.POINTER(C.c_int64)]
         L.madb_vecfunction_eval.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
@@ -211,7 +217,10 @@ class Integrator:
 
     fields: list of (Space, mode[, role]); input fields are the blocks of x in order."""
 
-    def __init__(self, ctx, fields, functional, quad_order=-1):
+    def __init__(self, ctx, fields, functional, quad_order=-1, block=False):
+        """block=True: ADBlockNonlinearFormIntegrator semantics even with one input space (MADB_INTEG_BLOCK): only
+        matters for one VECTOR space, whose Jacobian otherwise follows the reference's single-space arithmetic
+        (src/ad_intg.hpp:310-326)."""
         self.ctx, self.fn = ctx, functional
         self.fields = [(f[0], f[1], f[2] if len(f) > 2 else ROLE_INPUT) for f in fields]
         n = len(self.fields)
@@ -219,8 +228,8 @@ class Integrator:
         modes = _i32([f[1] for f in self.fields])
         roles = _i32([f[2] for f in self.fields])
         h = C.c_void_p()
-        _check(lib().madb_integrator_create(ctx.h, n, sp, modes.ctypes.data, roles.ctypes.data, functional.h,
-                                            quad_order, C.byref(h)))
+        _check(lib().madb_integrator_create_ex(ctx.h, n, sp, modes.ctypes.data, roles.ctypes.data, functional.h,
+                                               quad_order, INTEG_BLOCK if block else 0, C.byref(h)))
         self.h = h
         nt, nq, nc = C.c_int64(), C.c_int(), C.c_int()
         _check(lib().madb_integrator_sizes(h, C.byref(nt), C.byref(nq), C.byref(nc)))
@@ -310,6 +319,48 @@ class Integrator:
         grd = np.empty((ne, self.nq_el, n_in)) if want_grad else None
         _check(lib().madb_integrator_coefficient(self.h, _ptr(x), _ptr(val), _ptr(grd)))
         return val, grd
+
+    def _n_in(self):
+        return sum((1 if m & VALUE else 0) + (s.mesh.dim if m & GRAD else 0) for s, m, r in self.fields if r == ROLE_INPUT
+                   for _ in range(s.desc.get("vdim", 1)))
+
+    def coefficient_hessian(self, x):
+        """f, grad f and the Hessian at every quadrature point (HessianCoefficient, src/ad_native.hpp:300-323)."""
+        x = _f64(x)
+        ne, n = self.fields[0][0].mesh.ne, self._n_in()
+        val, grd, hes = np.empty((ne, self.nq_el)), np.empty((ne, self.nq_el, n)), np.empty((ne, self.nq_el, n, n))
+        _check(lib().madb_integrator_coefficient_hessian(self.h, _ptr(x), _ptr(val), _ptr(grd), _ptr(hes)))
+        return val, grd, hes
+
+    def param_gradient(self, design, variant=PARAMGRAD_AS_WRITTEN):
+        """ParametrizedFunctional::ParamGradient::Eval at the points (src/mmto.cpp:4-38): (F [ne,nq], J [ne,nq,param_dim]);
+        variant PARAMGRAD_AS_WRITTEN reproduces the reference, PARAMGRAD_DERIVATIVE is dF/drho."""
+        design = _f64(design)
+        ne, n = self.fields[0][0].mesh.ne, self._n_in()
+        val, J = np.empty((ne, self.nq_el)), np.empty((ne, self.nq_el, n))
+        _check(lib().madb_integrator_param_gradient(self.h, _ptr(design), _ptr(val), _ptr(J), variant))
+        return val, J
+
+    def qpoint_coords(self):
+        """Physical coordinates of the rule's points [ne, nq, dim] (where Coefficient-type parameters are sampled)."""
+        mesh = self.fields[0][0].mesh
+        xyz = np.empty((mesh.ne, self.nq_el, mesh.dim))
+        _check(lib().madb_integrator_qpoint_coords(self.h, xyz.ctypes.data))
+        return xyz
+
+    def set_param_coefficient(self, *callbacks):
+        """Evaluator sources of Coefficient / VectorCoefficient / MatrixCoefficient type (src/ad_native.hpp:56-61):
+        host callbacks f(xyz[npts, dim]) -> [npts] or [npts, k], sampled at the rule's points and handed over as one
+        QuadratureFunction (columns in the order given)."""
+        xyz = self.qpoint_coords()
+        pts = xyz.reshape(-1, xyz.shape[-1])
+        cols = []
+        for cb in callbacks:
+            v = np.asarray(cb(pts), dtype=np.float64)
+            cols.append(v.reshape(pts.shape[0], -1))
+        qf = np.concatenate(cols, axis=1).reshape(xyz.shape[0], xyz.shape[1], -1)
+        self.set_param_qf(qf)
+        return qf
 
     def coefficient_device(self, x, value=None, grad=None):
         """Same on device buffers (torch tensors); value [ne*nq], grad [ne*nq*n] or None."""

@@ -35,3 +35,11 @@ using LagDM = LagrangianOf<DiffusionEnergy<2, 0>, MinS2, -1>;
 using ALDM = ALFunctionalOf<DiffusionEnergy<2, 0>, MinS2, -1>;
 MADB_EVAL_INSTANCE("lagrangian:-1[diffusion:0,minsurf]", LagDM)
 MADB_EVAL_INSTANCE("al:-1[diffusion:0,minsurf]", ALDM)
+
+using HellQ2 = HellingerEntropy<2, true>;
+MADB_EVAL_INSTANCE("hellingerq", HellQ2)
+MADB_EVAL_INSTANCE("mass", MassEnergy<1>)
+using DiffK4e = DiffusionEnergy<2, 4>;
+MADB_EVAL_INSTANCE("diffusion:4", DiffK4e)
+using DiffMass1e = DiffEnergy<MassEnergy<1>>;
+MADB_EVAL_INSTANCE("diff[mass]", DiffMass1e)

@@ -17,6 +17,7 @@ using CfgDesign = Config<2, 3, Field<2, 5, EV_VALUE>, Field<2, 2, EV_GRAD, ROLE_
 using CfgLatent = Config<2, 3, Field<2, 5, EV_VALUE>>;
 // quadrature loop NOT unrolled: unrolled, the kernel is 13.8 k instructions (220 KB) and instruction-cache bound (2x slower)
 MADB_INSTANCE("paramcompliance[simp,simp]", State, CfgState, false)
+MADB_INSTANCE_REFVEC("paramcompliance[simp,simp]", State, CfgState, false) // single-space arithmetic as written
 MADB_INSTANCE("designcompliance[simp,simp]", Design, CfgDesign, false)
 MADB_INSTANCE("simplex", Simplex5, CfgLatent, false)
 

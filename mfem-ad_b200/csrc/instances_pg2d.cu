@@ -22,3 +22,6 @@ MADB_INSTANCE("pg:0[obstacle,fermidirac]", PGObs, Ex4o2, false)
 // ex5 -o 2: H1 p2 x (H1 p1)^2, rule order 6 -> 4x4
 using Ex5o2 = Config<2, 4, Field<3, 1, EV_GRAD>, Field<2, 2, EV_VALUE>, Field<2, 2, EV_VALUE, ROLE_PARAM>>;
 MADB_INSTANCE("pg:0[gradobstacle,hellinger]", PGGrad, Ex5o2, false)
+// ex5.cpp:114-117: the Hellinger bound as a spatial coefficient -> a quadrature-function parameter of the entropy
+using PGGradQ = PGFunctional<GradientObstacleEnergy<2>, HellingerEntropy<2, true>, 0>;
+MADB_INSTANCE("pg:0[gradobstacle,hellingerq]", PGGradQ, Ex5o2, false)

@@ -8,3 +8,6 @@ using V1 = Config<2, 3, Field<2, 2, EV_GRAD>>; // order 1
 using V2 = Config<2, 4, Field<3, 2, EV_GRAD>>; // order 2
 MADB_INSTANCE("elasticity", Elast2, V1, true)
 MADB_INSTANCE("elasticity", Elast2, V2, false)
+// reference arithmetic of the single-space VECTOR integrator: the default for one vector space
+MADB_INSTANCE_REFVEC("elasticity", Elast2, V1, true)
+MADB_INSTANCE_REFVEC("elasticity", Elast2, V2, false)

@@ -453,6 +453,27 @@ template <int DIM, class FL, class FM> struct DesignComplianceOf
    FL fl;
    FM fm;
    MADB_HD void load(const double *p) { fl.load(p); fm.load(p + FL::N_PARAM); }
+   static constexpr bool HAS_PARAM_GRADIENT = true;
+   /// ParametrizedFunctional::ParamGradient::Eval exactly as written (src/mmto.cpp:25-37): for every parameter
+   /// function f_i and design component j, slot i of the evaluator is overwritten with df_i/drho_j while the other
+   /// slots keep their VALUES, and the parent is re-evaluated: J[j] = sum_i parent(state; ..., df_i/drho_j, ...).
+   /// For this parent (linear in lambda, mu) that is dF/drho_j + (m-1) F, m = 2.
+   MADB_HD void param_gradient_as_written(const double *rho, const double *gradu, double *J) const
+   {
+      using T1 = AD<N_INPUT, 1>;
+      T1 r[N_INPUT];
+#pragma unroll
+      for (int m = 0; m < N_INPUT; m++) { r[m] = ad_seed<N_INPUT, 1>(rho[m], m); }
+      const T1 lam = fl(r, (const double *)nullptr), mu = fm(r, (const double *)nullptr);
+#pragma unroll
+      for (int j = 0; j < N_INPUT; j++)
+      {
+         double acc = 0.0;                                                       // J = 0.0 (:9)
+         acc += LinearElasticityEnergy<DIM>::body(gradu, lam.g[j], mu.v);       // slot 0 <- dlambda/drho_j (:32-33)
+         acc += LinearElasticityEnergy<DIM>::body(gradu, lam.v, mu.g[j]);       // slot 1 <- dmu/drho_j
+         J[j] = acc;
+      }
+   }
    template <class T> MADB_HD T operator()(const T *rho, const double *gradu) const
    {
       const T lambda = fl(rho, (const double *)nullptr), mu = fm(rho, (const double *)nullptr);
@@ -471,6 +492,52 @@ template <int DIM, class FL, class FM> struct DesignComplianceOf
          }
       }
       return (0.5 * div * div) * lambda + h1 * mu;
+   }
+};
+
+// ---------------------------------------------------------------------------
+// Single-space VECTOR integrator, reference arithmetic.
+// ADNonlinearFormIntegrator<...|VECTOR>::AssembleElementGrad (src/ad_intg.hpp:283-326) views the n x n Hessian
+// (n = SD*VD, x index s + SD*c) as Hs[SD x VD*SD*VD] (:292), forms Hx = allshapes*Hs (:312) and takes CONTIGUOUS
+// windows Hx + (c*VD + r)*SD*dof as if they held the (c, r) block (:318); the (c, r) part is added untransposed at
+// (r, c) as well (:320-324).  In index terms: block (c, r), r <= c, of the element matrix is B G B^T with
+//     G(t, s1) = H[s1 + SD*c1][s2 + SD*c2],   k = (c*VD + r)*SD + t,  c1 = k % VD,  s2 = (k / VD) % SD,  c2 = k / (VD*SD),
+// which is the intended H[(t,c)][(s1,r)] only for special H (LinearElasticityEnergy with lambda == mu).  The wrapper
+// applies exactly this permutation to the second derivatives of F's result, so that the index-consistent contraction
+// of the kernels reproduces the reference's element matrix.  The packed symmetric storage keeps the (a <= b) half:
+// for the energies the reference uses with this integrator (LinearElasticityEnergy, ParametrizedCompliance) the
+// permuted matrix is symmetric for any lambda, mu (checked against the oracle's literal emulation in the tests).
+// Value and gradient (energy, residual) are untouched.
+// ---------------------------------------------------------------------------
+template <class F, int SD, int VD> struct RefVectorOf
+{
+   static_assert(F::N_INPUT == SD * VD, "single vector space: n_input = shapedim * vdim");
+   static constexpr int N_INPUT = F::N_INPUT, N_PARAM = F::N_PARAM, N_QPRM = F::N_QPRM;
+   F f;
+   MADB_HD void load(const double *p) { f.load(p); }
+   template <class T> MADB_HD T operator()(const T *x, const double *qp) const
+   {
+      const T r = f(x, qp);
+      if constexpr (ad_traits<T>::order >= 2)
+      {
+         constexpr int N = N_INPUT;
+         T out = r;
+#pragma unroll
+         for (int a = 0; a < N; a++)
+         {
+#pragma unroll
+            for (int b = a; b < N; b++)
+            {
+               const int ca = a / SD, t = a % SD, cb = b / SD, s1 = b % SD; // ca <= cb
+               // block (ca, cb) is the untransposed copy of block (c, r) = (cb, ca) (:320-324); ca == cb: the block itself
+               const int k = (cb * VD + ca) * SD + t;
+               const int c1 = k % VD, s2 = (k / VD) % SD, c2 = k / (VD * SD);
+               out.setH(hidx<N>(a, b), r.H(symidx_h<N>(s1 + SD * c1, s2 + SD * c2)));
+            }
+         }
+         return out;
+      }
+      else { return r; }
    }
 };
 

@@ -94,6 +94,8 @@ struct LaunchCtx
    double *y, *vals, *energy;
    const int *perm;        // sorted position -> element (MODE_COEF output order)
    double *cvalue, *cgrad; // MODE_COEF outputs [e][q], [e][q][n]
+   double *chess;          // MODE_COEF output [e][q][n][n] (null: not wanted)
+   int coef_variant;       // 1: cgrad = ParamGradient::Eval as written (src/mmto.cpp:25-37)
    int write_y, write_vals;
    const double *fparams; // host
    // host tables, laid out exactly as madb::Tables<Cfg>
@@ -112,6 +114,7 @@ struct KernelOps
    int map_aos = 0;          // element maps stored [t][k] instead of [k][stride]
    int matrix_free_only = 0; // no assembled Jacobian (use grad_mult)
    int patch_ok = 0;         // patch-assembly kernels are compiled for this configuration
+   int has_param_gradient = 0; // the functional implements ParamGradient::Eval as written (MODE_COEF variant 1)
 };
 
 std::map<std::string, KernelOps> &registry();
@@ -207,7 +210,7 @@ struct Integrator
    // device data
    int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
    int *d_rowptr = nullptr, *d_colidx = nullptr, *d_perm = nullptr;
-   double *d_cvalue = nullptr, *d_cgrad = nullptr;
+   double *d_cvalue = nullptr, *d_cgrad = nullptr, *d_chess = nullptr;
    double *d_energy = nullptr, *d_esum = nullptr;
    double *d_x = nullptr, *d_v = nullptr, *d_v2 = nullptr, *d_y = nullptr, *d_vals = nullptr; // staging for host callers
    std::vector<double *> d_pstage;                                           // staging of parameter fields

@@ -49,9 +49,19 @@ template <class Func, class Cfg> struct AsmArgs
    double *energy; // [stride] per-element energies (sorted order)
    const int *perm; // sorted position -> element
    double *cvalue, *cgrad; // MODE_COEF: value [e][q] and gradient [e][q][N] at the points
+   double *chess;          // MODE_COEF: Hessian [e][q][N][N] (HessianCoefficient, src/ad_native.hpp:300-323)
+   int coef_variant;       // MODE_COEF: 1 = cgrad is ParamGradient::Eval as written (src/mmto.cpp:25-37)
    double fparams[Func::N_PARAM > 0 ? Func::N_PARAM : 1];
    Tables<Cfg> tab;
    typename Sf2dTabFor<Cfg>::type sf; // 1-D tables of the sum-factorised 2-D path (empty otherwise)
+};
+
+/// functionals that implement ParamGradient::Eval as written provide param_gradient_as_written(x, qp, J)
+template <class F, class = void> struct has_param_gradient : std::false_type
+{
+};
+template <class F> struct has_param_gradient<F, std::void_t<decltype(F::HAS_PARAM_GRADIENT)>> : std::true_type
+{
 };
 
 template <int DIM> MADB_HD void invert(const double (&J)[DIM][DIM], double (&Ji)[DIM][DIM], double &det)
@@ -195,12 +205,49 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables
    {
       // DifferentiableCoefficient::Eval / Gradient().Eval at the point (src/ad_native.hpp:272-283,315-317):
       // value and gradient of f w.r.t. its inputs, stored as quadrature functions [e][q][.]
+      const size_t pt = (size_t)a.perm[t] * Cfg::NQ + q;
+      if constexpr (has_param_gradient<Func>::value)
+      {
+         if (a.coef_variant == 1)
+         {
+            // ParametrizedFunctional::ParamGradient::Eval as written (src/mmto.cpp:25-37)
+            double J[N];
+            f.param_gradient_as_written(xin, qp, J);
+            if (a.cvalue) { a.cvalue[pt] = f(xin, qp); }
+            if (a.cgrad)
+            {
+#pragma unroll
+               for (int m = 0; m < N; m++) { a.cgrad[pt * N + m] = J[m]; }
+            }
+            return;
+         }
+      }
+      if (a.chess)
+      {
+         using T2 = AD<N, 2>;
+         T2 xs[N];
+#pragma unroll
+         for (int m = 0; m < N; m++) { xs[m] = ad_seed<N, 2>(xin[m], m); }
+         const T2 res = f(xs, qp);
+         if (a.cvalue) { a.cvalue[pt] = res.v; }
+         if (a.cgrad)
+         {
+#pragma unroll
+            for (int m = 0; m < N; m++) { a.cgrad[pt * N + m] = res.g[m]; }
+         }
+#pragma unroll
+         for (int m = 0; m < N; m++)
+         {
+#pragma unroll
+            for (int n = 0; n < N; n++) { a.chess[(pt * N + m) * N + n] = res.hess(m, n); }
+         }
+         return;
+      }
       using T = AD<N, 1>;
       T xs[N];
 #pragma unroll
       for (int m = 0; m < N; m++) { xs[m] = ad_seed<N, 1>(xin[m], m); }
       const T res = f(xs, qp);
-      const size_t pt = (size_t)a.perm[t] * Cfg::NQ + q;
       if (a.cvalue) { a.cvalue[pt] = res.v; }
       if (a.cgrad)
       {

@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(NQ *NQ *NEB) k_sumfac3d(const __grid_constant_
 template <class Func, int ND, int NQ> int launch_sumfac3d(const LaunchCtx &L, int mode)
 {
    constexpr int NEB = (128 / (NQ * NQ) > 0) ? 128 / (NQ * NQ) : 1;
-   static Sf3Args<Func, ND, NQ> a;
+   static thread_local Sf3Args<Func, ND, NQ> a;
    if (mode & MODE_JAC) { return -2; }
    a.e2n = L.e2n; a.coords = L.coords; a.vmap = L.vmap;
    a.x = L.x; a.v = L.v; a.y = L.y; a.energy = L.energy;

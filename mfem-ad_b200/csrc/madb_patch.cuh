@@ -22,6 +22,7 @@
 #include "madb_kernels.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 namespace madb
 {
@@ -424,6 +425,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
                      for (int i = 0; i < NVD; i++) { *(double *)(base + 8 * (i * LD + tid)) = r[i]; }
                   });
             }
+            // threads past the end of the last patch take part in the hand-off like the others: without this wait their
+            // arrival on `full` would be counted in the previous, still open phase and the writers could start early
+            else { mbar_wait(&bar_empty[w], par); }
          }
          else
          {
@@ -524,7 +528,10 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
 {
    const PatchDev &P = *L.patch;
    // dynamic shared-memory limits are per device and per kernel: remember what was set on each device
+   // (several host threads may drive contexts on different devices: the bookkeeping is guarded)
    static int smem_set_dev[64] = {0}, ws_smem_set_dev[64] = {0}, nsm_dev[64] = {0};
+   static std::mutex attr_mutex;
+   std::lock_guard<std::mutex> attr_lock(attr_mutex);
    int dev = 0;
    cudaGetDevice(&dev);
    dev &= 63;

@@ -26,7 +26,7 @@ template <class Cfg> std::string config_key()
 template <class Func, class Cfg> AsmArgs<Func, Cfg> &fill_args(const LaunchCtx &L)
 {
    using Args = AsmArgs<Func, Cfg>;
-   static Args a; // ~tens of KB: keep off the stack; calls are single-threaded per context
+   static thread_local Args a; // ~tens of KB: keep off the stack; one block per host thread (one thread drives a context)
    a.stride = L.stride;
    a.write_y = L.write_y;
    a.write_vals = L.write_vals;
@@ -45,6 +45,8 @@ template <class Func, class Cfg> AsmArgs<Func, Cfg> &fill_args(const LaunchCtx &
    a.perm = L.perm;
    a.cvalue = L.cvalue;
    a.cgrad = L.cgrad;
+   a.chess = L.chess;
+   a.coef_variant = L.coef_variant;
    for (int i = 0; i < Func::N_PARAM; i++) { a.fparams[i] = L.fparams[i]; }
    std::memcpy(a.tab.phi, L.phi, sizeof(a.tab.phi));
    std::memcpy(a.tab.dphi, L.dphi, sizeof(a.tab.dphi));
@@ -105,6 +107,7 @@ template <class Func, class Cfg, bool UNROLLQ> KernelOps make_ops()
    o.map_aos = 0;
    o.matrix_free_only = 0;
    o.patch_ok = patch_eligible(Cfg::NVD) ? 1 : 0;
+   o.has_param_gradient = has_param_gradient<Func>::value ? 1 : 0;
    o.launch = &launch_impl<Func, Cfg, UNROLLQ>;
    o.n_input = Cfg::N_INPUT;
    o.n_fparam = Func::N_PARAM;
@@ -125,5 +128,14 @@ template <class Func, class Cfg, bool UNROLLQ> KernelOps make_ops()
 #define MADB_INSTANCE(KIND, FUNC, CFG, UNROLLQ)                                                         \
    static ::madb::Registrar MADB_CAT(madb_reg_, __COUNTER__)(std::string(KIND) + "|" + ::madb::config_key<CFG>(), \
                                                              ::madb::make_ops<FUNC, CFG, UNROLLQ>());
+
+/// Single vector space with ADEval::VECTOR: the variant that reproduces the reference's single-space
+/// AssembleElementGrad arithmetic (src/ad_intg.hpp:310-326, RefVectorOf in madb_functionals.cuh), registered under the
+/// same kind with the key suffix "|refvec".  madb_integrator_create selects it for one-input-space VECTOR integrators
+/// unless MADB_INTEG_BLOCK asks for the index-consistent (ADBlockNonlinearFormIntegrator) contraction.
+#define MADB_INSTANCE_REFVEC(KIND, FUNC, CFG, UNROLLQ)                                                             \
+   static ::madb::Registrar MADB_CAT(madb_regrv_, __COUNTER__)(                                                    \
+      std::string(KIND) + "|" + ::madb::config_key<CFG>() + "|refvec",                                             \
+      ::madb::make_ops<::madb::RefVectorOf<FUNC, CFG::template sd<0>(), CFG::template field<0>::VDIM>, CFG, UNROLLQ>());
 
 } // namespace madb

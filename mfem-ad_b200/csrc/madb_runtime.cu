@@ -57,7 +57,7 @@ void Functional::flat_params(std::vector<double> &out) const
 Integrator::~Integrator()
 {
    cudaFree(d_e2n); cudaFree(d_vmap); cudaFree(d_pmap); cudaFree(d_e2csr);
-   cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_perm); cudaFree(d_cvalue); cudaFree(d_cgrad); cudaFree(d_energy); cudaFree(d_esum);
+   cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_perm); cudaFree(d_cvalue); cudaFree(d_cgrad); cudaFree(d_chess); cudaFree(d_energy); cudaFree(d_esum);
    cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
    if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
@@ -458,7 +458,7 @@ static int stage_out_begin(Integrator &I, double *p, size_t n, double **buf, dou
 }
 
 static int run(Integrator &I, int mode, const double *x, const double *v, double *y, double *vals, double *energy,
-               double *cvalue = nullptr, double *cgrad = nullptr)
+               double *cvalue = nullptr, double *cgrad = nullptr, double *chess = nullptr, int coef_variant = 0)
 {
    CUDA_OK(cudaSetDevice(I.ctx->device));
    const size_t N = (size_t)I.ntotal;
@@ -531,14 +531,16 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
       }
       L.energy = I.d_energy;
    }
-   double *dcv = nullptr, *dcg = nullptr;
+   double *dcv = nullptr, *dcg = nullptr, *dch = nullptr;
    const size_t npts = (size_t)I.ne * I.nq;
    if (mode == MODE_COEF)
    {
       L.perm = I.d_perm;
       if (cvalue) { if (stage_out_begin(I, cvalue, npts, &I.d_cvalue, &dcv)) { return 2; } }
       if (cgrad) { if (stage_out_begin(I, cgrad, npts * I.ops.n_input, &I.d_cgrad, &dcg)) { return 2; } }
-      L.cvalue = dcv; L.cgrad = dcg;
+      if (chess) { if (stage_out_begin(I, chess, npts * I.ops.n_input * I.ops.n_input, &I.d_chess, &dch)) { return 2; } }
+      L.cvalue = dcv; L.cgrad = dcg; L.chess = dch;
+      L.coef_variant = coef_variant;
    }
    const int rc = I.ops.launch(L, mode);
    if (rc != 0) { set_error(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
@@ -554,6 +556,7 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    {
       if (cvalue && dcv != cvalue) { CUDA_OK(cudaMemcpyAsync(cvalue, dcv, npts * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); }
       if (cgrad && dcg != cgrad) { CUDA_OK(cudaMemcpyAsync(cgrad, dcg, npts * I.ops.n_input * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); }
+      if (chess && dch != chess) { CUDA_OK(cudaMemcpyAsync(chess, dch, npts * I.ops.n_input * I.ops.n_input * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); }
       CUDA_OK(cudaStreamSynchronize(L.stream));
       return 0;
    }
@@ -794,6 +797,7 @@ extern "C"
       entropy->flat_params(fp);
       if ((int)fp.size() != it->second.n_fparam) { set_error("entropy '" + key + "': wrong number of parameters"); return 1; }
       fp.push_back(0.0);
+      if (!u || !psi || !psik || !w) { set_error("madb_dofpg_nodal: u, psi, psik and the nodal weights w are required (zeros for w reproduce the reference, SURVEY H7)"); return 1; }
       Staged su, sp, sk, sw, ru, rp, dp, du;
       if (su.in(u, n) || sp.in(psi, n) || sk.in(psik, n) || sw.in(w, n) || ru.out(r_u, n) || rp.out(r_psi, n) ||
           dp.out(d_pp, n) || du.out(d_up, n))
@@ -865,6 +869,11 @@ extern "C"
    int madb_integrator_create(madb_ctx *ctx, int nfields, madb_space *const *spaces, const int *modes,
                               const int *roles, madb_functional *f, int quad_order, madb_integrator **out)
    {
+      return madb_integrator_create_ex(ctx, nfields, spaces, modes, roles, f, quad_order, 0, out);
+   }
+   int madb_integrator_create_ex(madb_ctx *ctx, int nfields, madb_space *const *spaces, const int *modes,
+                                 const int *roles, madb_functional *f, int quad_order, int flags, madb_integrator **out)
+   {
       if (nfields < 1 || nfields > 8 || !spaces || !modes || !f) { set_error("madb_integrator_create: bad arguments"); return 1; }
       CUDA_OK(cudaSetDevice(ctx->device));
       madb_integrator *I = new madb_integrator;
@@ -905,6 +914,25 @@ extern "C"
       {
          key += "|" + std::to_string(fd.space->order + 1) + "." + std::to_string(fd.space->vdim) + "." +
                 std::to_string((int)(fd.mode & (EV_VALUE | EV_GRAD))) + "." + std::to_string(fd.role);
+      }
+      // One vector space with ADEval::VECTOR = ADNonlinearFormIntegrator<...|VECTOR>: the reference's single-space
+      // arithmetic (src/ad_intg.hpp:310-326) unless the caller asks for the block integrator's
+      // index-consistent contraction (ADBlockNonlinearFormIntegrator, :700-727).
+      {
+         int ninput = 0;
+         const FieldDesc *fin = nullptr;
+         for (const FieldDesc &fd : I->fields) { if (fd.role == ROLE_INPUT) { ninput++; fin = &fd; } }
+         if (ninput == 1 && (fin->mode & EV_VECTOR) && fin->space->vdim > 1 && !(flags & MADB_INTEG_BLOCK))
+         {
+            if (registry().find(key + "|refvec") == registry().end())
+            {
+               set_error("the reference's single-space VECTOR arithmetic (src/ad_intg.hpp:310-326) is not compiled for '" + key +
+                         "': add MADB_INSTANCE_REFVEC, or pass MADB_INTEG_BLOCK for the index-consistent block contraction");
+               delete I;
+               return 1;
+            }
+            key += "|refvec";
+         }
       }
       I->key = key;
       auto it = registry().find(key);
@@ -1090,6 +1118,51 @@ extern "C"
    {
       if (I->ops.map_aos) { set_error("madb_integrator_coefficient: not available for the sum-factorised kernels"); return 1; }
       return run(*I, MODE_COEF, x, nullptr, nullptr, nullptr, nullptr, value, grad);
+   }
+   int madb_integrator_coefficient_hessian(madb_integrator *I, const double *x, double *value, double *grad, double *hess)
+   {
+      if (I->ops.map_aos) { set_error("madb_integrator_coefficient_hessian: not available for the sum-factorised kernels"); return 1; }
+      return run(*I, MODE_COEF, x, nullptr, nullptr, nullptr, nullptr, value, grad, hess);
+   }
+   int madb_integrator_param_gradient(madb_integrator *I, const double *design, double *value, double *J, int variant)
+   {
+      if (I->ops.map_aos) { set_error("madb_integrator_param_gradient: not available for the sum-factorised kernels"); return 1; }
+      if (variant != MADB_PARAMGRAD_AS_WRITTEN && variant != MADB_PARAMGRAD_DERIVATIVE) { set_error("madb_integrator_param_gradient: unknown variant"); return 1; }
+      if (variant == MADB_PARAMGRAD_AS_WRITTEN && !I->ops.has_param_gradient)
+      {
+         set_error("madb_integrator_param_gradient: functional '" + I->fn->key() + "' does not implement ParamGradient::Eval as written");
+         return 1;
+      }
+      return run(*I, MODE_COEF, design, nullptr, nullptr, nullptr, nullptr, value, J, nullptr, variant == MADB_PARAMGRAD_AS_WRITTEN ? 1 : 0);
+   }
+   int madb_integrator_qpoint_coords(madb_integrator *I, double *xyz)
+   {
+      // physical coordinates of the rule's points, [e][q][dim]: where Coefficient-type Evaluator sources
+      // (src/ad_native.hpp:56-61, src/ad_native.cpp:132-165) are sampled before they are handed over as a
+      // QuadratureFunction (madb_integrator_set_param_qf)
+      const Mesh &M = *I->mesh;
+      const int dim = M.dim, ngn = 1 << dim, nq = I->nq, nq1 = I->nq1d;
+      std::vector<double> out((size_t)I->ne * nq * dim);
+      for (int e = 0; e < I->ne; e++)
+      {
+         for (int q = 0; q < nq; q++)
+         {
+            double xi[3] = {0, 0, 0};
+            int r = q;
+            for (int d = 0; d < dim; d++) { xi[d] = I->xq1d[r % nq1]; r /= nq1; }
+            double *o = &out[((size_t)e * nq + q) * dim];
+            for (int d = 0; d < dim; d++) { o[d] = 0.0; }
+            for (int k = 0; k < ngn; k++)
+            {
+               double N = 1.0;
+               for (int d = 0; d < dim; d++) { N *= ((k >> d) & 1) ? xi[d] : 1.0 - xi[d]; }
+               const double *X = &M.coords[(size_t)M.e2n[(size_t)e * ngn + k] * dim];
+               for (int d = 0; d < dim; d++) { o[d] += N * X[d]; }
+            }
+         }
+      }
+      CUDA_OK(cudaMemcpy(xyz, out.data(), out.size() * sizeof(double), cudaMemcpyDefault));
+      return 0;
    }
    int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y)
    {

@@ -144,6 +144,15 @@ class SharedDofExchange:
                                torch.empty(max(sum(rcount), 1), dtype=torch.float64, device=self.device))
         scount, rcount, sidx, dst, src4, sbuf, rbuf = self._bufs[key]
         ns, nr = sum(scount), sum(rcount)
+        if vec.is_cuda and self.ctx is not None and torch.cuda.current_stream(self.device).cuda_stream != self.ctx.stream:
+            # pack / unpack run on the context's (non-blocking) stream, NCCL on torch's current stream: make them the
+            # same stream for the duration of the exchange, ordered after the work already queued by the caller
+            ext = torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+            ext.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(ext):
+                self._exchange(vec, send, recv, add, tag)
+            torch.cuda.current_stream(self.device).wait_stream(ext)
+            return
         if ns:
             self._pack(vec, sidx, sbuf[:ns])
         dist.all_to_all_single(rbuf[:nr], sbuf[:ns], rcount, scount, group=self.group)

@@ -39,15 +39,29 @@ class FSpec:
         import mfem_ad_b200 as M
         ch = [c.madb(ctx) for c in self.children]
         ip = list(self.iparams)
-        return M.Functional(ctx, self.kind, params=self.params, iparams=ip, children=ch)
+        kind = self.kind
+        if kind == "hellinger" and self.qoff >= 0:
+            kind = "hellingerq"  # the bound is a per-point parameter (ex5.cpp:114-117)
+        if kind == "diffusion" and self.qoff >= 0:
+            kind = "diffusionq"
+        return M.Functional(ctx, kind, params=self.params, iparams=ip, children=ch)
 
 
 def minsurf(dim, eps=0.5):
     return FSpec("minsurf", dim, [eps])
 
 
-def diffusion(dim, K=()):
+def diffusion(dim, K=(), qoff=-1, kdim=None):
+    """DiffusionEnergy (src/ad_native.hpp:421-481): K constant (none / scalar / diagonal / full, column-major), or read
+    from the per-point parameters at qoff (kdim entries)."""
+    if qoff >= 0:
+        return FSpec("diffusion", dim, [], [kdim], qoff=qoff)
     return FSpec("diffusion", dim, list(K), [len(K)])
+
+
+def diff(energy, qoff=0):
+    """DiffEnergy (src/ad_native.hpp:483-525): energy(x - target), target = per-point parameters at qoff."""
+    return FSpec("diff", energy.n_input, [], [], [energy], qoff=qoff)
 
 
 def mass(n):
@@ -117,8 +131,9 @@ def make_pair(ctx, mesh, spaces, fspec, quad_order=-1, params=(), ess=(), block=
     gm = M.Mesh(ctx, mesh)
     gs = [M.Space(ctx, gm, s) for s in spaces]
     gf = fspec.madb(ctx)
+    # block=None: the reference's choice (one space -> ADNonlinearFormIntegrator, several -> the block integrator)
     gi = M.Integrator(ctx, [(gs[i], spaces[i]["mode"], spaces[i].get("role", 0)) for i in range(len(spaces))], gf,
-                      quad_order=quad_order)
+                      quad_order=quad_order, block=bool(block))
     if len(ess):
         gi.set_essential(ess)
     gi._keepalive = (gm, gs, gf)

@@ -136,3 +136,73 @@ def test_config5_block_full_size(ctx):
     assert abs(K - K.T).max() <= 1e-13 * np.max(np.abs(v))
     y2, v2 = gi.assemble(x)
     assert np.array_equal(y2, y) and np.array_equal(v2, v)
+
+
+def test_config4_full_size(ctx):
+    """Config 4: 1072x1072 Q1 quads, displacement (vdim 2) + 5-component latent psi per node
+    (8,059,303 dofs): softmax latent->primal map, SIMP lambda(rho), mu(rho), ParametrizedCompliance state block
+    (the reference's single-space VECTOR arithmetic) and ParamGradient as written, against the oracle
+    on a corner sub-mesh; symmetry / determinism on the whole mesh."""
+    import mfem_ad_b200 as M
+    import scipy.sparse as sp
+    n, m = 1072, 8
+    E = [1e-3, 0.25, 0.5, 0.75, 1.0]
+    mesh = G.cartesian_mesh((n, n))
+    disp = G.h1_space(mesh, 1, vdim=2, mode=O.GRAD | O.VECTOR)
+    lat = G.h1_space(mesh, 1, vdim=5, mode=O.VALUE | O.VECTOR)
+    nd = lat["ndofs"]
+    assert nd == 1151329 and 7 * nd == 8059303
+    psi = np.random.default_rng(99).normal(0, 1, 5 * nd)
+    # latent -> primal map on the device (pointwise kernel), against numpy's softmax
+    _, g, _ = S.simplex(5, 1.0).madb(ctx).eval(psi.reshape(5, nd).T.copy())
+    p5 = psi.reshape(5, nd)
+    ex_ = np.exp(p5 - p5.max(axis=0))
+    rho = (ex_ / ex_.sum(axis=0)).reshape(-1)
+    assert np.max(np.abs(g.T.reshape(-1) - rho)) <= 1e-15
+    lam_fs, mu_fs = S.simp(E, 3.0), S.simp([0.5 * e for e in E], 3.0)
+    gm = M.Mesh(ctx, mesh)
+    gd, gl = M.Space(ctx, gm, disp), M.Space(ctx, gm, lat)
+    fn = M.Functional(ctx, "paramcompliance", children=[lam_fs.madb(ctx), mu_fs.madb(ctx)])
+    gi = M.Integrator(ctx, [(gd, O.GRAD | O.VECTOR), (gl, O.VALUE | O.VECTOR, M.ROLE_PARAM)], fn)
+    gi.set_param_field(1, rho)
+    x = np.random.default_rng(5).uniform(-1, 1, 2 * nd)
+    y, v = gi.assemble(x)
+    rp, ci = gi.pattern()
+    assert rp[-1] == 41396356  # BASELINE.md config 4 nnz
+    # corner sub-mesh
+    sub = G.cartesian_mesh((m, m), lengths=(m / n, m / n))
+    sdisp = G.h1_space(sub, 1, vdim=2, mode=O.GRAD | O.VECTOR)
+    slat = G.h1_space(sub, 1, vdim=5, mode=O.VALUE | O.VECTOR)
+    big1, inner1 = _sub_dofs(n, m, 1, 2)
+    bigd = np.concatenate([c * nd + big1 for c in range(2)])
+    bigl = np.concatenate([c * nd + big1 for c in range(5)])
+    inner = np.concatenate([inner1, inner1])
+    rq = O.OracleForm(sub, [slat], S.simplex(5).oracle()).inputs_at_qpts(rho[bigl])
+    lo, mo = lam_fs.oracle(), mu_fs.oracle()
+    qf = np.array([[[lo.value(r), mo.value(r)] for r in re] for re in rq])
+    of = O.OracleForm(sub, [sdisp], S.FSpec("paramcompliance", 4, qoff=0).oracle(),
+                      params=[dict(type=O.PRM_QF, size=2, data=qf)], block=0)
+    ys = of.mult(x[bigd])
+    rps, cis, vs = of.grad(x[bigd])
+    assert S.csr_rel_err(y[bigd][inner], ys[inner]) <= TOL
+    K = sp.csr_matrix((v, ci, rp), shape=(x.size,) * 2)
+    Ks = sp.csr_matrix((vs, cis, rps), shape=(bigd.size,) * 2)
+    rows = np.nonzero(inner)[0]
+    assert np.max(np.abs(K[bigd[rows]][:, bigd].toarray() - Ks[rows].toarray())) <= TOL * np.max(np.abs(vs))
+    assert abs(K - K.T).max() <= 1e-13 * np.max(np.abs(v))
+    y2, v2 = gi.assemble(x)
+    assert np.array_equal(y2, y) and np.array_equal(v2, v)
+    del K, v, v2
+    # ParamGradient as written (src/mmto.cpp:25-37) at the points of the sub-mesh elements
+    fnd = M.Functional(ctx, "designcompliance", children=[lam_fs.madb(ctx), mu_fs.madb(ctx)])
+    gdes = M.Integrator(ctx, [(gl, O.VALUE | O.VECTOR), (gd, O.GRAD, M.ROLE_PARAM)], fnd)
+    gdes.set_param_field(1, x)
+    _, J = gdes.param_gradient(rho)
+    F = O.Functional()
+    il = lam_fs._add(F)
+    im = mu_fs._add(F)
+    S.FSpec("paramcompliance", 4, qoff=4)._add(F)
+    ofd = O.OracleForm(sub, [slat], F, params=[dict(type=O.PRM_GF_GRAD, size=4, data=x[bigd], space=sdisp)])
+    J_ref = ofd.mmto_param_gradient(rho[bigl], [il, im])
+    ey, ex = np.divmod(np.arange(m * m), m)
+    assert np.max(np.abs(J[ey * n + ex] - J_ref)) <= TOL * np.max(np.abs(J_ref))

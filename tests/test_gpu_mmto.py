@@ -59,26 +59,32 @@ def test_parametrized_compliance_state_block(ctx):
     lo, mo = lam_fs.oracle(), mu_fs.oracle()
     qf = np.array([[[lo.value(r), mo.value(r)] for r in re] for re in rq])
     fo = S.FSpec("paramcompliance", 4, qoff=0)
-    of = O.OracleForm(mesh, [disp], fo.oracle(), params=[dict(type=O.PRM_QF, size=2, data=qf)], block=1)
     import mfem_ad_b200 as M
     gm = M.Mesh(ctx, mesh)
     gd, gl = M.Space(ctx, gm, disp), M.Space(ctx, gm, lat)
     fn = M.Functional(ctx, "paramcompliance", children=[lam_fs.madb(ctx), mu_fs.madb(ctx)])
-    gi = M.Integrator(ctx, [(gd, O.GRAD | O.VECTOR), (gl, O.VALUE | O.VECTOR, M.ROLE_PARAM)], fn)
-    gi.set_param_field(1, rho)
     x = np.random.default_rng(5).uniform(-1, 1, 2 * disp["ndofs"])
-    assert S.csr_rel_err(gi.mult(x), of.mult(x)) <= TOL
-    rp, ci, v = of.grad(x)
-    rpg, cig = gi.pattern()
-    assert np.array_equal(rp, rpg) and np.array_equal(ci, cig)
-    assert S.csr_rel_err(gi.grad(x), v) <= TOL
-    assert abs(gi.energy(x) - of.energy(x)) <= TOL * abs(of.energy(x))
+    vals = {}
+    # block=0: ADNonlinearFormIntegrator<GRAD|VECTOR> as written (the default of the library);
+    # block=1: the index-consistent contraction (MADB_INTEG_BLOCK)
+    for block in (0, 1):
+        of = O.OracleForm(mesh, [disp], fo.oracle(), params=[dict(type=O.PRM_QF, size=2, data=qf)], block=block)
+        gi = M.Integrator(ctx, [(gd, O.GRAD | O.VECTOR), (gl, O.VALUE | O.VECTOR, M.ROLE_PARAM)], fn, block=bool(block))
+        gi.set_param_field(1, rho)
+        assert S.csr_rel_err(gi.mult(x), of.mult(x)) <= TOL
+        rp, ci, v = of.grad(x)
+        rpg, cig = gi.pattern()
+        assert np.array_equal(rp, rpg) and np.array_equal(ci, cig)
+        vals[block] = gi.grad(x)
+        assert S.csr_rel_err(vals[block], v) <= TOL
+        assert abs(gi.energy(x) - of.energy(x)) <= TOL * abs(of.energy(x))
+    assert np.max(np.abs(vals[0] - vals[1])) > 1e-3 * np.max(np.abs(vals[1]))  # lambda(rho) != mu(rho): H1 shows
 
 
 def test_param_gradient(ctx):
     """ParametrizedFunctional::ParamGradient::Eval (src/mmto.cpp:4-38) as written: substituting df_i/drho_j
     into slot i while the other f's keep their values yields dF/drho_j + (m-1) F, m = 2.
-    The CUDA path returns F and the true dF/drho at the points; both variants follow."""
+    madb_integrator_param_gradient returns the reference's result by default, dF/drho on request."""
     mesh, disp, lat, psi = _setup()
     rho = _softmax_nodal(psi, lat["ndofs"])
     u = np.random.default_rng(6).uniform(-1, 1, 2 * disp["ndofs"])
@@ -95,8 +101,23 @@ def test_param_gradient(ctx):
     fn = M.Functional(ctx, "designcompliance", children=[lam_fs.madb(ctx), mu_fs.madb(ctx)])
     gi = M.Integrator(ctx, [(gl, O.VALUE | O.VECTOR), (gd, O.GRAD, M.ROLE_PARAM)], fn)
     gi.set_param_field(1, u)
-    val, grd = gi.coefficient(rho)
-    as_written = grd + (2 - 1) * val[..., None]
-    assert np.max(np.abs(as_written - J_ref)) <= TOL * np.max(np.abs(J_ref))
-    # corrected variant = finite differences of the oracle energy density w.r.t. rho at one point
-    assert np.all(np.isfinite(grd)) and np.max(np.abs(grd)) > 0
+    # the library's ParamGradient: as written by default (the reference's result), the derivative on request
+    val, J = gi.param_gradient(rho)
+    assert np.max(np.abs(J - J_ref)) <= TOL * np.max(np.abs(J_ref))
+    val2, dF = gi.param_gradient(rho, M.PARAMGRAD_DERIVATIVE)
+    assert np.max(np.abs(val2 - val)) <= 1e-14 * np.max(np.abs(val))
+    assert np.max(np.abs((dF + (2 - 1) * val[..., None]) - J_ref)) <= TOL * np.max(np.abs(J_ref))  # H6: dF/drho + (m-1) F
+    v3, g3 = gi.coefficient(rho)
+    assert np.array_equal(g3, dF)
+    # the derivative variant against central differences of F(rho) at one point
+    e, q = 3, 4
+    xin = of.inputs_at_qpts(rho)[e, q]
+    gq = O.OracleForm(mesh, [disp], S.FSpec("empty", 4).oracle()).inputs_at_qpts(u)[e, q]
+    lo, mo = lam_fs.oracle(), mu_fs.oracle()
+    par = S.FSpec("paramcompliance", 4, qoff=0).oracle()
+    Fr = lambda r: par.value(gq, [lo.value(r), mo.value(r)])
+    for j in range(5):
+        d = np.zeros(5)
+        d[j] = 1e-6
+        fd = (Fr(xin + d) - Fr(xin - d)) / 2e-6
+        assert abs(fd - dF[e, q, j]) <= 1e-7 * max(1.0, abs(fd))

@@ -21,7 +21,7 @@ def _state(mesh, s, seed=1234):
     return u + 0.1 * np.random.default_rng(seed).uniform(-1, 1, s["ndofs"])  # SURVEY 8d config 2 state
 
 
-def _compare(of, gi, x, energy=True):
+def _compare(of, gi, x, energy=True, action=True):
     y_ref = of.mult(x)
     rp, ci, v_ref = of.grad(x)
     y = gi.mult(x)
@@ -40,6 +40,8 @@ def _compare(of, gi, x, energy=True):
     if energy:
         e_ref = of.energy(x)
         assert abs(gi.energy(x) - e_ref) <= TOL * max(1.0, abs(e_ref))
+    if not action:
+        return
     # matrix-free action == assembled Jacobian
     import scipy.sparse as sp
     d = np.random.default_rng(4321).uniform(-1, 1, x.size)
@@ -329,16 +331,22 @@ def test_ex5_gradient_constraint_pg_block_on_quads(ctx):
 
 @pytest.mark.parametrize("p,ordering", [(1, 0), (2, 0), (1, 1)])
 def test_ex3_vector_elasticity(ctx, p, ordering):
-    """ex3.cpp:50-63: vector H1 space, GRAD|VECTOR, LinearElasticityEnergy.  The CUDA path implements the
-    index-consistent contraction (= the block integrator, src/ad_intg.hpp:700-727); it equals the
-    single-space code (src/ad_intg.hpp:310-326) exactly when lambda == mu (ex3's case), see SURVEY H1."""
+    """ex3.cpp:50-63: vector H1 space, GRAD|VECTOR, LinearElasticityEnergy.  Default = the reference's single-space
+    arithmetic as written (src/ad_intg.hpp:310-326: windows of Hx, untransposed mirror blocks -- SURVEY H1), for
+    lambda == mu (ex3) and for lambda != mu, where it differs O(1) from the index-consistent contraction of the block
+    integrator (src/ad_intg.hpp:700-727), which MADB_INTEG_BLOCK selects."""
     mesh = G.cartesian_mesh((4, 3), perturb=0.1)
     s = G.h1_space(mesh, p, vdim=2, ordering=ordering, mode=O.GRAD | O.VECTOR)
     x = _block_state(mesh, [s])
-    of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 1.0, 1.0), block=0)  # reference single-space arithmetic
+    of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 1.0, 1.0), block=0)  # ex3.cpp:58
     _compare(of, gi, x)
-    of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 2.0, 0.7), block=1)  # consistent variant, lambda != mu
-    _compare(of, gi, x)
+    of0, gi0 = S.make_pair(ctx, mesh, [s], S.elasticity(2, 2.0, 0.7), block=0)  # as written, lambda != mu
+    _compare(of0, gi0, x)
+    of1, gi1 = S.make_pair(ctx, mesh, [s], S.elasticity(2, 2.0, 0.7), block=1)  # consistent variant
+    _compare(of1, gi1, x)
+    v0, v1 = gi0.grad(x), gi1.grad(x)
+    assert np.max(np.abs(v0 - v1)) > 1e-2 * np.max(np.abs(v1))  # the two really are different matrices (H1)
+    assert np.array_equal(gi0.mult(x), gi1.mult(x))              # the residual is not affected
 
 
 @pytest.mark.parametrize("kind", ["diffusion", "minsurf"])
