@@ -922,7 +922,9 @@ extern "C"
          int ninput = 0;
          const FieldDesc *fin = nullptr;
          for (const FieldDesc &fd : I->fields) { if (fd.role == ROLE_INPUT) { ninput++; fin = &fd; } }
-         if (ninput == 1 && (fin->mode & EV_VECTOR) && fin->space->vdim > 1 && !(flags & MADB_INTEG_BLOCK))
+         // (with one shape slot per component -- VALUE only -- the windows of :318 coincide with the (c, r) blocks)
+         const int sd = fin ? ((fin->mode & EV_VALUE) ? 1 : 0) + ((fin->mode & EV_GRAD) ? I->mesh->dim : 0) : 0;
+         if (ninput == 1 && (fin->mode & EV_VECTOR) && fin->space->vdim > 1 && sd > 1 && !(flags & MADB_INTEG_BLOCK))
          {
             if (registry().find(key + "|refvec") == registry().end())
             {
