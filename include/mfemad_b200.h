@@ -173,6 +173,13 @@ int madb_integrator_patch_stats(madb_integrator *I, int64_t *out);
 int madb_patch_selftest(int dim, int ne, const int32_t *e2n, int nnodes, const double *coords, int order, int vdim,
                         int ordering, int ndofs, const int32_t *e2l, double *max_err, int64_t *stats);
 
+/* Same for the maps of the CSR-image kernel (shared-memory image of the patch's CSR rows written with bulk copies):
+ * tpe = threads per element (1, or 2 = the thread pair with the mirrored half-element, scalar 2-D spaces).
+ * stats[0..7]: patches, interface dofs, interface matrix entries, staged matrix partials, shared memory per work group
+ * (bytes), nnz, CSR entries written by bulk copies, bytes of maps and lists read per assembly. */
+int madb_patch_selftest_img(int dim, int ne, const int32_t *e2n, int nnodes, const double *coords, int order, int vdim,
+                            int ordering, int ndofs, const int32_t *e2l, int tpe, double *max_err, int64_t *stats);
+
 /* Device timing of the element kernel(s) of the last mult / assemble / grad_mult call: CUDA events on the
  * context stream around the dominant kernel (the interface reduction and essential-dof kernels excluded). */
 int madb_integrator_set_timing(madb_integrator *I, int on);

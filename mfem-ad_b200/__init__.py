@@ -74,6 +74,8 @@ def lib():
         L.madb_vecfunction_eval.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
         L.madb_patch_selftest.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, ip,
                                           C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+        L.madb_patch_selftest_img.argtypes = [C.c_int, C.c_int, ip, C.c_int, dp, C.c_int, C.c_int, C.c_int, C.c_int, ip, C.c_int,
+                                              C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.madb_integrator_set_timing.argtypes = [vp, C.c_int]
         L.madb_integrator_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double)]
         L.madb_integrator_set_param_field.argtypes = [vp, C.c_int, dp]
@@ -400,6 +402,18 @@ def patch_selftest(mesh, space):
                                      space["order"], space.get("vdim", 1), space.get("ordering", BYNODES), space["ndofs"],
                                      e2l.ctypes.data, C.byref(err), st))
     keys = ("patches", "ifc_dofs", "ifc_entries", "staged_vals", "max_blob_bytes", "nnz", "paired_entries")
+    return err.value, dict(zip(keys, [int(v) for v in st]))
+
+
+def patch_selftest_img(mesh, space, tpe):
+    """Host-only check of the CSR-image kernel's maps (madb_patch_selftest_img): returns (max_err, stats dict)."""
+    e2n, coords, e2l = _i32(mesh["e2n"]), _f64(mesh["coords"]), _i32(space["e2l"])
+    err = C.c_double()
+    st = (C.c_int64 * 8)()
+    _check(lib().madb_patch_selftest_img(mesh["dim"], e2n.shape[0], e2n.ctypes.data, coords.shape[0], coords.ctypes.data,
+                                         space["order"], space.get("vdim", 1), space.get("ordering", BYNODES), space["ndofs"],
+                                         e2l.ctypes.data, tpe, C.byref(err), st))
+    keys = ("patches", "ifc_dofs", "ifc_entries", "staged_vals", "smem_per_group", "nnz", "bulk_entries", "map_bytes")
     return err.value, dict(zip(keys, [int(v) for v in st]))
 
 

@@ -69,6 +69,40 @@ struct IfcListDev // interface reduction lists of one side (see k_ifc_reduce)
    const double *stage;
    double *out;
 };
+// ---- CSR-image patch kernel (k_patch_img, madb_patch_img.cuh) -------------------------------------------------
+// The threads of a patch scatter their element-matrix entries straight into a shared-memory IMAGE of the patch's part
+// of the CSR value array (first source of a slot -> the slot; further sources -> private "extras" slots, folded onto
+// the slot in ascending element order afterwards); the image is then written with bulk copies (cp.async.bulk
+// shared -> global), one per run of consecutive CSR positions: no per-entry instructions on the write-out path.
+// Image layout (doubles): [interior rows in CSR order, runs padded so that image and CSR positions have the same
+// parity (16-byte alignment of the bulk copies)] [entries of interface rows only this patch contributes to]
+// [entries shared with other patches: contiguous, even start and count -> one bulk copy to the staging buffer]
+// [2 trash slots] [extras].  The y image: [local rows][1 trash][extras].
+struct ImgDesc
+{
+   int ne, nrows, nrow_int, ystage_off;
+   int mblob_off, mblob_bytes; // the patch's blob (one bulk copy to shared memory): mblob + 16*mblob_off
+   int o_vmap, o_ymap, o_lists; // byte offsets of the scatter maps and of the lists inside the blob
+   int nvfold, nyfold;         // fold lists: 8 phase counts + (dst | src << 16) words
+   int nruns, nexcl;
+   int sh0, nsh;               // shared interface entries: image range (even start, even count)
+   int stage_off;              // vstage[stage_off + k] <- image[sh0 + k]
+   int nvslots, nyslots;       // image sizes incl. trash and extras
+   int pad[2];
+};
+// Blob of a patch: ImgDesc | vmap u32 [NEV][PE][TPE] (slot(i,j) | slot(j,i) << 16 of the entry thread (l, h) keeps at
+// emission e) | ymap u16 [NEY][PE][TPE] | lists (ints, every section padded to a multiple of 4):
+//   vfold [nvfold] | yfold [nyfold] | runs [4*nruns] {image offset, CSR position, count, 0} | excl_gpos [nexcl]
+//   | excl_slot [u16 pairs, nexcl] | ylist [nrow_int]
+struct ImgDev
+{
+   const ImgDesc *desc;
+   const unsigned char *mblob;
+   int max_vslots, max_yslots, max_mblob; // shared-memory sizing (slots / bytes)
+   int nev, ney;                          // emissions per thread (matrix / vector)
+};
+constexpr int img_al4(int n) { return (n + 3) & ~3; }
+
 struct PatchDev
 {
    int npatch;
@@ -79,6 +113,7 @@ struct PatchDev
    // interface reductions: out[dst] = sum of the staged partials, ascending patch order
    int ny_ifc, nv_ifc; // entries (statistics)
    IfcListDev ylist, vlist;
+   ImgDev img; // CSR-image kernel (desc == null: not in use)
 };
 
 struct LaunchCtx
@@ -115,6 +150,9 @@ struct KernelOps
    int matrix_free_only = 0; // no assembled Jacobian (use grad_mult)
    int patch_ok = 0;         // patch-assembly kernels are compiled for this configuration
    int has_param_gradient = 0; // the functional implements ParamGradient::Eval as written (MODE_COEF variant 1)
+   int patch_pe = 0;           // elements per patch of this configuration (0: patch_pe(nvd))
+   int img_tpe = 0;            // CSR-image kernel: threads per element (0: kernel not compiled for this configuration)
+   int img_mirror_nd = 0;      // img_tpe == 2: thread 1 works on the element mirrored in its second direction (1-D dofs)
 };
 
 std::map<std::string, KernelOps> &registry();
@@ -232,6 +270,9 @@ struct Integrator
    PatchDev pdev {};
    PatchDesc *d_pdesc = nullptr;
    unsigned char *d_yblob = nullptr, *d_vblob = nullptr;
+   ImgDesc *d_idesc = nullptr; // CSR-image kernel maps
+   unsigned char *d_mblob = nullptr;
+   long img_map_bytes = 0; // statistics: scatter maps + lists (bytes read per assembly)
    double *d_ystage = nullptr, *d_vstage = nullptr;
    int *d_ifc[2][5] = {{nullptr, nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr, nullptr}}; // [side][src4, dst4, ptr, src, dst]
 
@@ -266,6 +307,16 @@ struct PatchHost // maps of one side (residual or matrix)
 void patch_order(Integrator &I);                      // fills I.perm (patch order) and I.pdesc[].ne
 bool patch_build_y(Integrator &I, PatchHost &H);       // needs I.perm; false: not representable
 bool patch_build_v(Integrator &I, PatchHost &H);       // needs the CSR pattern
+struct ImgHost // maps of the CSR-image kernel
+{
+   std::vector<ImgDesc> desc;
+   std::vector<unsigned char> mblob;
+   int max_vslots = 0, max_yslots = 0, max_mblob = 0, nev = 0, ney = 0;
+};
+/// emission schedule of the element threads: local (I, J) of kept matrix entry e, local I of kept vector entry e
+void img_schedule(int nvd, int tpe, int mirror_nd, std::vector<int> &vI, std::vector<int> &vJ, std::vector<int> &yI);
+bool patch_build_img(Integrator &I, PatchHost &H, ImgHost &IH); // needs the CSR pattern and patch_build_y
 int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats); // host-only emulation (CPU tests)
+int patch_selftest_img(Mesh &mesh, Space &space, int tpe, double *max_err, long *stats); // same for the CSR-image kernel
 
 } // namespace madb

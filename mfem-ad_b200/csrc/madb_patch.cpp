@@ -13,6 +13,7 @@
 //                   partials of each entry in ascending patch order (deterministic).
 // No atomics, no colouring: the summation order of every entry is fixed by the maps.
 #include "madb_host.hpp"
+#include "madb_pair_schedule.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -542,6 +543,333 @@ bool patch_build_v(Integrator &I, PatchHost &H)
    return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// CSR-image kernel (k_patch_img): scatter maps, fold lists, runs.  See ImgDesc in madb_host.hpp.
+// ---------------------------------------------------------------------------------------------
+void img_schedule(int nvd, int tpe, int mirror_nd, std::vector<int> &vI, std::vector<int> &vJ, std::vector<int> &yI)
+{
+   if (tpe == 1)
+   {
+      // one thread per element: all entries of the upper triangle in packed order k = b (b + 1) / 2 + a
+      const int nsym = nvd * (nvd + 1) / 2;
+      vI.resize(nsym); vJ.resize(nsym); yI.resize(nvd);
+      for (int b = 0; b < nvd; b++) { for (int a = 0; a <= b; a++) { vI[b * (b + 1) / 2 + a] = a; vJ[b * (b + 1) / 2 + a] = b; } }
+      for (int i = 0; i < nvd; i++) { yI[i] = i; }
+      return;
+   }
+   int nv = 0, ny = 0;
+   switch (mirror_nd)
+   {
+      case 2: nv = sf2d_pair_keep_v<2>(nullptr, nullptr); ny = sf2d_pair_keep_y<2>(nullptr); break;
+      case 3: nv = sf2d_pair_keep_v<3>(nullptr, nullptr); ny = sf2d_pair_keep_y<3>(nullptr); break;
+      case 4: nv = sf2d_pair_keep_v<4>(nullptr, nullptr); ny = sf2d_pair_keep_y<4>(nullptr); break;
+      case 5: nv = sf2d_pair_keep_v<5>(nullptr, nullptr); ny = sf2d_pair_keep_y<5>(nullptr); break;
+      default: vI.clear(); vJ.clear(); yI.clear(); return;
+   }
+   vI.resize(nv); vJ.resize(nv); yI.resize(ny);
+   switch (mirror_nd)
+   {
+      case 2: sf2d_pair_keep_v<2>(vI.data(), vJ.data()); sf2d_pair_keep_y<2>(yI.data()); break;
+      case 3: sf2d_pair_keep_v<3>(vI.data(), vJ.data()); sf2d_pair_keep_y<3>(yI.data()); break;
+      case 4: sf2d_pair_keep_v<4>(vI.data(), vJ.data()); sf2d_pair_keep_y<4>(yI.data()); break;
+      default: sf2d_pair_keep_v<5>(vI.data(), vJ.data()); sf2d_pair_keep_y<5>(yI.data()); break;
+   }
+}
+
+namespace
+{
+// fold list of one side: per destination the extras in ascending element order -> 8 phase counts + (dst | src << 16)
+// words; records sorted by (number of extras descending, destination), so that entry i of every phase has the same
+// destination and is handled by the same thread (no barrier between the phases)
+bool pack_folds(std::vector<std::pair<int, std::vector<int>>> &rec, std::vector<int> &out)
+{
+   std::sort(rec.begin(), rec.end(), [](const auto &a, const auto &b)
+   {
+      if (a.second.size() != b.second.size()) { return a.second.size() > b.second.size(); }
+      return a.first < b.first;
+   });
+   out.assign(8, 0);
+   if (!rec.empty() && rec.front().second.size() > 8) { return false; }
+   for (int k = 1; k <= 8; k++)
+   {
+      int n = 0;
+      for (const auto &r : rec)
+      {
+         if ((int)r.second.size() < k) { break; }
+         out.push_back((int)((unsigned)r.first | ((unsigned)r.second[k - 1] << 16)));
+         n++;
+      }
+      out[k - 1] = n;
+   }
+   return true;
+}
+void pad4(std::vector<int> &v) { while (v.size() % 4) { v.push_back(0); } }
+} // namespace
+
+bool patch_build_img(Integrator &I, PatchHost &H, ImgHost &IH)
+{
+   const int nvd = I.nvd, pe = I.pe, np = (int)I.pdesc.size(), tpe = I.ops.img_tpe, mnd = I.ops.img_mirror_nd;
+   std::vector<int> eI, eJ, eY;
+   img_schedule(nvd, tpe, mnd, eI, eJ, eY);
+   const int nev = (int)eI.size(), ney = (int)eY.size();
+   if (nev == 0) { set_error("patch_build_img: no emission schedule for this configuration"); return false; }
+   auto mir = [&](int i, int h) { return (h && tpe == 2) ? (mnd - 1 - i / mnd) * mnd + i % mnd : i; };
+   IH.nev = nev; IH.ney = ney;
+   IH.desc.assign(np, ImgDesc());
+   std::vector<std::vector<unsigned char>> mblobs(np);
+   std::vector<std::vector<int>> gdatas(np);
+   std::vector<std::vector<int>> shared_gpos(np);
+   // interface entries of every patch, number of contributing patches per CSR position (as in patch_build_v)
+   std::vector<std::vector<long>> ifc_keys(np);
+   std::vector<std::vector<int>> ifc_gpos(np);
+   parallel_for_p(np, 64, [&](long b, long e)
+   {
+      std::vector<int> vd;
+      for (long p = b; p < e; p++)
+      {
+         const PatchDesc &D = I.pdesc[p];
+         const int lo = (int)p * pe;
+         const int *R = I.prows.data() + I.prow_off[p];
+         std::vector<long> &keys = ifc_keys[p];
+         keys.clear();
+         for (int l = 0; l < D.ne; l++)
+         {
+            build_vdofs(I, I.perm[lo + l], vd);
+            for (int i = 0; i < nvd; i++)
+            {
+               const int lr = (int)(std::lower_bound(R + D.nrow_int, R + D.nrows, vd[i]) - R);
+               if (lr < D.nrows && R[lr] == vd[i])
+               {
+                  for (int j = 0; j < nvd; j++) { keys.push_back(((long)lr << 32) | (unsigned)vd[j]); }
+               }
+            }
+         }
+         std::sort(keys.begin(), keys.end());
+         keys.erase(std::unique(keys.begin(), keys.end()), keys.end());
+         ifc_gpos[p].resize(keys.size());
+         for (size_t k = 0; k < keys.size(); k++)
+         {
+            const int r = R[(int)(keys[k] >> 32)], c = (int)(keys[k] & 0xffffffff);
+            const int *cb = I.colidx.data() + I.rowptr[r], *ce = I.colidx.data() + I.rowptr[r + 1];
+            ifc_gpos[p][k] = (int)(std::lower_bound(cb, ce, c) - I.colidx.data());
+         }
+      }
+   });
+   std::vector<unsigned char> cnt(I.colidx.size(), 0);
+   for (int p = 0; p < np; p++) { for (int g : ifc_gpos[p]) { if (cnt[g] < 255) { cnt[g]++; } } }
+
+   bool ok = true;
+   parallel_for_p(np, 64, [&](long b, long e)
+   {
+      std::vector<int> vd, base, keyslot, vfold, yfold, runs, xgpos, xslot, scnt, ycnt;
+      std::vector<std::pair<int, int>> excl;
+      std::vector<unsigned> word; // [l][k] scatter word of sym entry k of element l
+      std::vector<unsigned short> yword;
+      std::vector<std::pair<int, std::vector<int>>> vrec, yrec;
+      std::vector<int> recof; // slot -> record index (or -1)
+      for (long p = b; p < e; p++)
+      {
+         const PatchDesc &D = I.pdesc[p];
+         ImgDesc &G = IH.desc[p];
+         std::memset(&G, 0, sizeof(G));
+         const int lo = (int)p * pe;
+         const int *R = I.prows.data() + I.prow_off[p];
+         const std::vector<long> &keys = ifc_keys[p];
+         // ---- image layout ------------------------------------------------------------------------------
+         base.assign(D.nrows, 0);
+         runs.clear();
+         int s = 0;
+         for (int lr = 0; lr < D.nrow_int; lr++)
+         {
+            const int r = R[lr];
+            if (lr == 0 || R[lr - 1] + 1 != r)
+            {
+               if ((I.rowptr[r] ^ s) & 1) { s++; } // same parity of image slot and CSR position
+               runs.push_back(s); runs.push_back(I.rowptr[r]); runs.push_back(0); runs.push_back(0);
+            }
+            base[lr] = s;
+            s += I.rowptr[r + 1] - I.rowptr[r];
+            runs[runs.size() - 2] += I.rowptr[r + 1] - I.rowptr[r];
+         }
+         excl.clear();
+         keyslot.assign(keys.size(), -1);
+         for (size_t k = 0; k < keys.size(); k++) { if (cnt[ifc_gpos[p][k]] == 1) { excl.emplace_back(ifc_gpos[p][k], (int)k); } }
+         std::sort(excl.begin(), excl.end());
+         xgpos.clear(); xslot.clear();
+         for (size_t k = 0; k < excl.size(); k++)
+         {
+            keyslot[excl[k].second] = s;
+            xgpos.push_back(excl[k].first);
+            xslot.push_back(s);
+            s++;
+         }
+         if (s & 1) { s++; }
+         const int sh0 = s;
+         shared_gpos[p].clear();
+         for (size_t k = 0; k < keys.size(); k++)
+         {
+            if (keyslot[k] < 0)
+            {
+               keyslot[k] = s++;
+               shared_gpos[p].push_back(ifc_gpos[p][k]);
+            }
+         }
+         if (s & 1) { s++; } // pad slot: copied to a staging position nobody reads
+         const int nsh = s - sh0;
+         const int trash = s;
+         s += 2;
+         int xnext = s; // extras
+         // ---- sources: first source -> the slot, further sources -> extras + fold ----------------------------
+         const int nsym = nvd * (nvd + 1) / 2;
+         word.assign((size_t)pe * nsym, (unsigned)trash | ((unsigned)trash << 16));
+         scnt.assign(xnext, 0);
+         recof.assign(xnext, -1);
+         vrec.clear();
+         const int ytrash = D.nrows;
+         int ynext = D.nrows + 1;
+         yword.assign((size_t)pe * nvd, (unsigned short)ytrash);
+         ycnt.assign(D.nrows, 0);
+         yrec.clear();
+         std::vector<int> yrecof(D.nrows, -1), lrow(nvd), rbeg(nvd);
+         for (int l = 0; l < D.ne; l++)
+         {
+            build_vdofs(I, I.perm[lo + l], vd);
+            for (int i = 0; i < nvd; i++)
+            {
+               int lr = (int)(std::lower_bound(R, R + D.nrow_int, vd[i]) - R);
+               const bool interior = lr < D.nrow_int && R[lr] == vd[i];
+               if (!interior) { lr = (int)(std::lower_bound(R + D.nrow_int, R + D.nrows, vd[i]) - R); }
+               lrow[i] = interior ? lr : -1 - lr;
+               // element vector
+               if (ycnt[lr]++ == 0) { yword[(size_t)l * nvd + i] = (unsigned short)lr; }
+               else
+               {
+                  if (yrecof[lr] < 0) { yrecof[lr] = (int)yrec.size(); yrec.push_back({lr, {}}); }
+                  yrec[yrecof[lr]].second.push_back(ynext);
+                  yword[(size_t)l * nvd + i] = (unsigned short)ynext++;
+               }
+            }
+            auto slot_of = [&](int i, int j)
+            {
+               if (lrow[i] >= 0)
+               {
+                  const int r = vd[i];
+                  const int *cb = I.colidx.data() + I.rowptr[r], *ce = I.colidx.data() + I.rowptr[r + 1];
+                  return base[lrow[i]] + (int)(std::lower_bound(cb, ce, vd[j]) - cb);
+               }
+               const long key = ((long)(-1 - lrow[i]) << 32) | (unsigned)vd[j];
+               return keyslot[std::lower_bound(keys.begin(), keys.end(), key) - keys.begin()];
+            };
+            for (int jb = 0; jb < nvd; jb++)
+            {
+               for (int ia = 0; ia <= jb; ia++)
+               {
+                  const int k = jb * (jb + 1) / 2 + ia;
+                  const int s1 = slot_of(ia, jb), s2 = slot_of(jb, ia);
+                  const int rank = scnt[s1]++;
+                  if (s2 != s1) { scnt[s2]++; }
+                  if (rank == 0) { word[(size_t)l * nsym + k] = (unsigned)s1 | ((unsigned)s2 << 16); }
+                  else
+                  {
+                     const int x = xnext++;
+                     word[(size_t)l * nsym + k] = (unsigned)x | ((unsigned)x << 16);
+                     for (int sdst : {s1, s2})
+                     {
+                        if (recof[sdst] < 0) { recof[sdst] = (int)vrec.size(); vrec.push_back({sdst, {}}); }
+                        vrec[recof[sdst]].second.push_back(x);
+                        if (s2 == s1) { break; }
+                     }
+                  }
+               }
+            }
+         }
+         if (xnext > 65535 || ynext > 65535) { ok = false; continue; }
+         if (!pack_folds(vrec, vfold) || !pack_folds(yrec, yfold)) { ok = false; continue; }
+         // ---- blobs ------------------------------------------------------------------------------------------
+         std::vector<int> &gd = gdatas[p];
+         gd.clear();
+         gd.insert(gd.end(), vfold.begin(), vfold.end()); pad4(gd);
+         gd.insert(gd.end(), yfold.begin(), yfold.end()); pad4(gd);
+         gd.insert(gd.end(), runs.begin(), runs.end()); pad4(gd);
+         gd.insert(gd.end(), xgpos.begin(), xgpos.end()); pad4(gd);
+         for (size_t k = 0; k < xslot.size(); k += 2)
+         {
+            gd.push_back((int)((unsigned)xslot[k] | ((k + 1 < xslot.size() ? (unsigned)xslot[k + 1] : 0u) << 16)));
+         }
+         pad4(gd);
+         gd.insert(gd.end(), R, R + D.nrow_int); pad4(gd);
+         // one blob per patch, fetched with one bulk copy: descriptor | scatter maps | lists
+         std::vector<unsigned char> &mb = mblobs[p];
+         const size_t vbytes = (size_t)nev * pe * tpe * 4, ybytes = (size_t)ney * pe * tpe * 2;
+         const size_t o_vmap = (sizeof(ImgDesc) + 15) & ~(size_t)15;
+         const size_t o_ymap = (o_vmap + vbytes + 15) & ~(size_t)15;
+         const size_t o_lists = (o_ymap + ybytes + 15) & ~(size_t)15;
+         mb.assign((o_lists + gd.size() * 4 + 15) & ~(size_t)15, 0);
+         std::memcpy(mb.data() + o_lists, gd.data(), gd.size() * 4);
+         unsigned *vm = (unsigned *)(mb.data() + o_vmap);
+         unsigned short *ym = (unsigned short *)(mb.data() + o_ymap);
+         for (int ee = 0; ee < nev; ee++)
+         {
+            for (int l = 0; l < pe; l++)
+            {
+               for (int h = 0; h < tpe; h++)
+               {
+                  const int a = mir(eI[ee], h), bb = mir(eJ[ee], h);
+                  const int lo_ = std::min(a, bb), hi_ = std::max(a, bb);
+                  vm[((size_t)ee * pe + l) * tpe + h] = word[(size_t)l * nsym + hi_ * (hi_ + 1) / 2 + lo_];
+               }
+            }
+         }
+         for (int ee = 0; ee < ney; ee++)
+         {
+            for (int l = 0; l < pe; l++)
+            {
+               for (int h = 0; h < tpe; h++) { ym[((size_t)ee * pe + l) * tpe + h] = yword[(size_t)l * nvd + mir(eY[ee], h)]; }
+            }
+         }
+         G.o_vmap = (int)o_vmap;
+         G.o_lists = (int)o_lists;
+         G.ne = D.ne; G.nrows = D.nrows; G.nrow_int = D.nrow_int; G.ystage_off = D.ystage_off;
+         G.mblob_bytes = (int)mb.size();
+         G.o_ymap = (int)o_ymap;
+         G.nvfold = (int)vfold.size(); G.nyfold = (int)yfold.size();
+         G.nruns = (int)runs.size() / 4; G.nexcl = (int)xgpos.size();
+         G.sh0 = sh0; G.nsh = nsh;
+         G.nvslots = xnext; G.nyslots = ynext;
+      }
+   });
+   if (!ok) { set_error("patch assembly (CSR image): a patch does not fit the 16-bit slot indices / 8 fold phases"); return false; }
+   long soff = 0, boff = 0;
+   IH.max_vslots = IH.max_yslots = IH.max_mblob = 0;
+   for (int p = 0; p < np; p++)
+   {
+      ImgDesc &G = IH.desc[p];
+      G.stage_off = (int)soff;
+      G.mblob_off = (int)(boff / 16);
+      soff += G.nsh;
+      boff += (long)mblobs[p].size();
+      IH.max_vslots = std::max(IH.max_vslots, G.nvslots);
+      IH.max_yslots = std::max(IH.max_yslots, G.nyslots);
+      IH.max_mblob = std::max(IH.max_mblob, G.mblob_bytes);
+   }
+   if (boff / 16 >= 0x7fffffffL) { set_error("patch assembly (CSR image): maps too large"); return false; }
+   H.stage_size = soff;
+   IH.mblob.resize(std::max<long>(boff, 16));
+   std::vector<std::pair<int, int>> tup;
+   for (int p = 0; p < np; p++)
+   {
+      const ImgDesc &G = IH.desc[p];
+      std::copy(mblobs[p].begin(), mblobs[p].end(), IH.mblob.begin() + (size_t)G.mblob_off * 16);
+      std::memcpy(IH.mblob.data() + (size_t)G.mblob_off * 16, &G, sizeof(ImgDesc)); // the blob starts with its descriptor
+      for (size_t k = 0; k < shared_gpos[p].size(); k++) { tup.emplace_back(shared_gpos[p][k], G.stage_off + (int)k); }
+   }
+   group_by_dst(tup, H);
+   I.img_map_bytes = boff;
+   I.have_patch_vals = true;
+   return true;
+}
+
 } // namespace madb
 
 // ---------------------------------------------------------------------------------------------
@@ -695,6 +1023,157 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
       stats[5] = nnz;
       stats[6] = npaired;
       stats[7] = 0;
+   }
+   return 0;
+}
+
+
+// Host-only emulation of k_patch_img (madb_patch_img.cuh) on integer-valued element data: scatter through the maps in
+// the emission order of the element threads (tpe = 2: the thread pair with the mirrored half-element), fold, runs with
+// the parity peeling of the bulk copies, exclusive / shared interface entries, interface reduction.
+int patch_selftest_img(Mesh &mesh, Space &space, int tpe, double *max_err, long *stats)
+{
+   Integrator I;
+   I.mesh = &mesh;
+   FieldDesc fd;
+   fd.space = &space;
+   fd.mode = 4; // GRAD
+   fd.role = 0;
+   I.fields.push_back(fd);
+   I.ne = mesh.ne;
+   I.nvd = space.nd_el() * space.vdim;
+   I.ndof_all = I.nvd;
+   I.ntotal = space.vsize();
+   I.goff.assign(1, 0);
+   if (patch_pe(I.nvd) != PATCH_PE) { set_error("patch_selftest_img: element matrix too large for the CSR-image kernel"); return 1; }
+   if (tpe != 1 && !(tpe == 2 && space.vdim == 1 && mesh.dim == 2)) { set_error("patch_selftest_img: thread pairs need a scalar 2-D space"); return 1; }
+   I.ops.img_tpe = tpe;
+   I.ops.img_mirror_nd = tpe == 2 ? space.order + 1 : 0;
+   I.pe = 128 / tpe;
+   I.use_patches = true;
+   patch_order(I);
+   if (I.pdesc.empty()) { set_error("patch_selftest_img: patch_order failed"); return 1; }
+   const int pe = I.pe, nvd = I.nvd, np = (int)I.pdesc.size();
+   I.stride = np * pe;
+   PatchHost HY, HV;
+   ImgHost IH;
+   if (!patch_build_y(I, HY)) { set_error("patch_selftest_img: patch_build_y failed"); return 1; }
+   build_pattern(I);
+   if (!I.have_pattern) { return 1; }
+   if (!patch_build_img(I, HV, IH)) { return 1; }
+   std::vector<int> eI, eJ, eY;
+   img_schedule(nvd, tpe, I.ops.img_mirror_nd, eI, eJ, eY);
+   const int nev = (int)eI.size(), ney = (int)eY.size(), mnd = I.ops.img_mirror_nd;
+   auto mir = [&](int i, int h) { return (h && tpe == 2) ? (mnd - 1 - i / mnd) * mnd + i % mnd : i; };
+   const long N = I.ntotal, nnz = (long)I.colidx.size();
+   auto rval = [](int e, int i) { return (double)((e * 7 + i * 3) % 11 - 5); };
+   auto aval = [](int e, int a, int b) { const int lo = std::min(a, b), hi = std::max(a, b); return (double)((e * 5 + lo * 13 + hi * 17) % 23 - 11); };
+   std::vector<double> y_ref(N, 0.0), v_ref(nnz, 0.0), y(N, -777.0), v(nnz, -777.0);
+   std::vector<int> vd;
+   for (int e = 0; e < I.ne; e++)
+   {
+      build_vdofs(I, e, vd);
+      for (int i = 0; i < nvd; i++)
+      {
+         y_ref[vd[i]] += rval(e, i);
+         const int *cb = I.colidx.data() + I.rowptr[vd[i]], *ce = I.colidx.data() + I.rowptr[vd[i] + 1];
+         for (int j = 0; j < nvd; j++) { v_ref[std::lower_bound(cb, ce, vd[j]) - I.colidx.data()] += aval(e, i, j); }
+      }
+   }
+   std::vector<double> ystage(std::max<long>(HY.stage_size, 1), -555.0), vstage(std::max<long>(HV.stage_size, 2), -555.0);
+   std::vector<double> img(IH.max_vslots), yimg(IH.max_yslots);
+   long nbulk = 0, nwritten = 0;
+   for (int p = 0; p < np; p++)
+   {
+      const ImgDesc &D = IH.desc[p];
+      std::fill(img.begin(), img.end(), 1e300);
+      std::fill(yimg.begin(), yimg.end(), 1e300);
+      const unsigned char *blob = IH.mblob.data() + (size_t)D.mblob_off * 16;
+      if (std::memcmp(blob, &D, sizeof(ImgDesc)) != 0) { set_error("patch_selftest_img: blob descriptor"); return 1; }
+      const unsigned *vm = (const unsigned *)(blob + D.o_vmap);
+      const unsigned short *ym = (const unsigned short *)(blob + D.o_ymap);
+      for (int l = 0; l < D.ne; l++)
+      {
+         const int e = I.perm[p * pe + l];
+         for (int h = 0; h < tpe; h++)
+         {
+            for (int ee = 0; ee < ney; ee++) { yimg[ym[((size_t)ee * pe + l) * tpe + h]] = rval(e, mir(eY[ee], h)); }
+            for (int ee = 0; ee < nev; ee++)
+            {
+               const unsigned w = vm[((size_t)ee * pe + l) * tpe + h];
+               const double val = aval(e, mir(eI[ee], h), mir(eJ[ee], h));
+               img[w & 0xffffu] = val;
+               img[w >> 16] = val;
+            }
+         }
+      }
+      const int *gd = (const int *)(blob + D.o_lists);
+      auto fold = [](const int *f, std::vector<double> &a)
+      {
+         int base = 8;
+         for (int ph = 0; ph < 8; ph++)
+         {
+            const int n = f[ph];
+            for (int i = 0; i < n; i++) { const unsigned w = (unsigned)f[base + i]; a[w & 0xffffu] += a[w >> 16]; }
+            base += n;
+         }
+      };
+      fold(gd, img);
+      fold(gd + img_al4(D.nvfold), yimg);
+      const int *runs = gd + img_al4(D.nvfold) + img_al4(D.nyfold);
+      const int *xg = runs + 4 * D.nruns;
+      const unsigned short *xs = (const unsigned short *)(xg + img_al4(D.nexcl));
+      const int *ylist = xg + img_al4(D.nexcl) + img_al4((D.nexcl + 1) / 2);
+      for (int r = 0; r < D.nruns; r++)
+      {
+         int so = runs[4 * r], g0 = runs[4 * r + 1], n = runs[4 * r + 2];
+         if ((so ^ g0) & 1) { set_error("patch_selftest_img: run parity"); return 1; }
+         nwritten += n;
+         if (g0 & 1) { v[g0] = img[so]; so++; g0++; n--; }
+         if (n & 1) { v[g0 + n - 1] = img[so + n - 1]; n--; }
+         for (int j = 0; j < n; j++) { v[g0 + j] = img[so + j]; }
+         nbulk += n;
+      }
+      if ((D.sh0 & 1) || (D.nsh & 1) || (D.stage_off & 1)) { set_error("patch_selftest_img: staging alignment"); return 1; }
+      for (int k = 0; k < D.nsh; k++) { vstage[D.stage_off + k] = img[D.sh0 + k]; }
+      for (int q = 0; q < D.nexcl; q++) { v[xg[q]] = img[xs[q]]; }
+      for (int lr = 0; lr < D.nrows; lr++)
+      {
+         if (lr < D.nrow_int) { y[ylist[lr]] = yimg[lr]; }
+         else { ystage[D.ystage_off + (lr - D.nrow_int)] = yimg[lr]; }
+      }
+   }
+   auto reduce = [](const PatchHost &H, const std::vector<double> &stage, std::vector<double> &out)
+   {
+      for (size_t i = 0; i < H.dst4.size(); i++)
+      {
+         double s = 0.0;
+         for (int k = 0; k < 4; k++) { if (H.src4[4 * i + k] >= 0) { s += stage[H.src4[4 * i + k]]; } }
+         out[H.dst4[i]] = s;
+      }
+      for (size_t i = 0; i < H.dst.size(); i++)
+      {
+         double s = 0.0;
+         for (int k = H.ptr[i]; k < H.ptr[i + 1]; k++) { s += stage[H.src[k]]; }
+         out[H.dst[i]] = s;
+      }
+   };
+   reduce(HY, ystage, y);
+   reduce(HV, vstage, v);
+   double err = 0.0;
+   for (long i = 0; i < N; i++) { err = std::max(err, std::fabs(y[i] - y_ref[i])); }
+   for (long i = 0; i < nnz; i++) { err = std::max(err, std::fabs(v[i] - v_ref[i])); }
+   *max_err = err;
+   if (stats)
+   {
+      stats[0] = np;
+      stats[1] = (long)HY.dst4.size() + (long)HY.dst.size();
+      stats[2] = (long)HV.dst4.size() + (long)HV.dst.size();
+      stats[3] = HV.stage_size;
+      stats[4] = (long)IH.max_vslots * 8 + (long)IH.max_yslots * 8 + IH.max_mblob; // shared memory per work group
+      stats[5] = nnz;
+      stats[6] = nbulk;           // CSR entries written by bulk copies
+      stats[7] = I.img_map_bytes; // bytes of maps + lists read per assembly
    }
    return 0;
 }

@@ -20,6 +20,7 @@
 //  without atomics and without order dependence.
 #pragma once
 #include "madb_kernels.cuh"
+#include "madb_sf2d_pair.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
@@ -279,10 +280,10 @@ __device__ __forceinline__ void patch_compute_stage(const AsmArgs<Func, Cfg> &a,
 
 /// One CTA per patch: PE = patch_pe(NVD) elements, NPART = element_parts threads per element.
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
-__global__ void __launch_bounds__(patch_pe(Cfg::NVD) * element_parts<Cfg, MODE>())
+__global__ void __launch_bounds__(patch_pe_of<Func, Cfg>() * element_parts<Cfg, MODE>())
    k_patch(const __grid_constant__ AsmArgs<Func, Cfg> a, const __grid_constant__ PatchDev P)
 {
-   constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = patch_pe(NVD), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
+   constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = patch_pe_of<Func, Cfg>(), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
    constexpr int NT = PE * NPART;
    constexpr bool HAS_Y = (MODE & (MODE_RES | MODE_ACT)) != 0, HAS_V = (MODE & MODE_JAC) != 0;
    constexpr int SR_BYTES = patch_al16(NVD * LD * 8), SA_BYTES = patch_al16(NSYM * LD * 8);
@@ -523,6 +524,12 @@ static __global__ void __launch_bounds__(256) k_ifc_reduce(const IfcList A, cons
    else { ifc_reduce_general(B, (blk - nb2) * 256 + t); }
 }
 
+/// does <functional, configuration> have the CSR-image kernel (madb_patch_img.cuh)? (element matrices of up to 10 dofs)
+/// (one thread per element: up to 8 dofs, so that two work groups of 128 elements fit in shared memory; the thread-pair
+/// variant of the sum-factorised 2-D path runs 64 elements per work group)
+template <class Func, class Cfg> constexpr bool img_eligible() { return sf2d_pair_ok<Func, Cfg>() || Cfg::NVD <= 8; }
+template <class Func, class Cfg, bool UNROLLQ> int launch_patch_img(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L); // madb_patch_img.cuh
+
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
 int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
 {
@@ -538,7 +545,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    int &smem_set = smem_set_dev[dev], &ws_smem_set = ws_smem_set_dev[dev], &nsm = nsm_dev[dev];
    auto kern = k_patch<Func, Cfg, MODE, UNROLLQ>;
    const bool wy = (MODE & (MODE_RES | MODE_ACT)) && L.write_y, wv = (MODE & MODE_JAC) && L.write_vals;
-   constexpr int PE = patch_pe(Cfg::NVD), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
+   constexpr int PE = patch_pe_of<Func, Cfg>(), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
    constexpr bool TAB_SMEM = !UNROLLQ && !use_sf2d<Func, Cfg, MODE>();
    const int smem_bytes = (wy ? patch_al16(Cfg::NVD * LD * 8) + P.max_yblob : 0) +
                           (wv ? patch_al16(Cfg::NSYM * LD * 8) + P.max_vblob : 0) + (TAB_SMEM ? (int)sizeof(Tables<Cfg>) : 0) + 16;
@@ -551,10 +558,19 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    }
    if (L.ev0) { cudaEventRecord(L.ev0, L.stream); }
    bool done = false;
+   if constexpr (MODE == (MODE_RES | MODE_JAC) && img_eligible<Func, Cfg>())
+   {
+      if (wv && P.img.desc)
+      {
+         const int rc = launch_patch_img<Func, Cfg, UNROLLQ>(a, L);
+         if (rc != 0) { return rc; }
+         done = true;
+      }
+   }
    if constexpr (MODE == (MODE_RES | MODE_JAC) && PE == PATCH_PE && NPART == 1)
    {
       static const bool use_ws = getenv("MADB_PATCH_WS") ? atoi(getenv("MADB_PATCH_WS")) != 0 : true;
-      if (wv && use_ws)
+      if (!done && wv && use_ws && P.vblob)
       {
          auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
          const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yblob + P.max_vblob) + 16;
@@ -573,7 +589,11 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
          }
       }
    }
-   if (!done) { kern<<<P.npatch, PE * NPART, smem_bytes, L.stream>>>(a, P); }
+   if (!done)
+   {
+      if (wv && !P.vblob) { return (int)cudaErrorInvalidValue; } // the gather maps of this path were not built
+      kern<<<P.npatch, PE * NPART, smem_bytes, L.stream>>>(a, P);
+   }
    (void)ws_smem_set;
    (void)nsm;
    if (L.ev1) { cudaEventRecord(L.ev1, L.stream); }

@@ -3,6 +3,7 @@
 #include "madb_host.hpp"
 #include "madb_kernels.cuh"
 #include "madb_patch.cuh"
+#include "madb_patch_img.cuh"
 
 #include <cstring>
 #include <string>
@@ -107,6 +108,9 @@ template <class Func, class Cfg, bool UNROLLQ> KernelOps make_ops()
    o.map_aos = 0;
    o.matrix_free_only = 0;
    o.patch_ok = patch_eligible(Cfg::NVD) ? 1 : 0;
+   o.patch_pe = patch_pe_of<Func, Cfg>();
+   o.img_tpe = img_eligible<Func, Cfg>() ? img_tpe<Func, Cfg>() : 0;
+   o.img_mirror_nd = (o.img_tpe == 2) ? Cfg::template field<0>::ND1D : 0;
    o.has_param_gradient = has_param_gradient<Func>::value ? 1 : 0;
    o.launch = &launch_impl<Func, Cfg, UNROLLQ>;
    o.n_input = Cfg::N_INPUT;

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace madb
 {
@@ -61,7 +62,7 @@ Integrator::~Integrator()
    cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
    if (ev0) { cudaEventDestroy(ev0); cudaEventDestroy(ev1); }
-   cudaFree(d_pdesc); cudaFree(d_yblob); cudaFree(d_vblob);
+   cudaFree(d_pdesc); cudaFree(d_yblob); cudaFree(d_vblob); cudaFree(d_idesc); cudaFree(d_mblob);
    cudaFree(d_ystage); cudaFree(d_vstage);
    for (int a = 0; a < 2; a++) { for (int b = 0; b < 5; b++) { cudaFree(d_ifc[a][b]); } }
 }
@@ -217,6 +218,8 @@ static void release_device_maps(Integrator &I)
    I.d_e2n = I.d_vmap = I.d_pmap = I.d_perm = I.d_e2csr = nullptr;
    I.d_pdesc = nullptr;
    I.d_yblob = I.d_vblob = nullptr;
+   cudaFree(I.d_idesc); cudaFree(I.d_mblob);
+   I.d_idesc = nullptr; I.d_mblob = nullptr;
    I.d_ystage = I.d_vstage = nullptr;
    I.d_rowptr = I.d_colidx = nullptr;
    for (int a = 0; a < 2; a++) { for (int b = 0; b < 5; b++) { cudaFree(I.d_ifc[a][b]); I.d_ifc[a][b] = nullptr; } }
@@ -251,7 +254,7 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
    I.use_patches = allow_patches && I.ops.patch_ok && !I.ops.map_aos && !getenv("MADB_NO_PATCH");
    if (I.use_patches)
    {
-      I.pe = patch_pe(I.nvd);
+      I.pe = I.ops.patch_pe > 0 ? I.ops.patch_pe : patch_pe(I.nvd);
       patch_order(I);
       if (I.pdesc.empty()) { I.use_patches = false; }
    }
@@ -413,9 +416,43 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
 
 static int ensure_pattern_device(Integrator &I)
 {
-   if (I.d_e2csr || I.d_vblob) { return 0; }
+   if (I.d_e2csr || I.d_vblob || I.d_idesc) { return 0; }
    build_pattern(I);
    if (!I.have_pattern) { return 1; }
+   // CSR-image kernel (k_patch_img): measured slower than the warp-specialised gather-map kernel on configs 2 and 4
+   // (profiles/r02_img_kernel.md), so it is opt-in: MADB_PATCH_IMG=1 for the one-thread-per-element variant (element
+   // matrices of up to 8 dofs), -DMADB_PAIR_KERNEL=1 at build time for the thread-pair variant (64-element patches)
+   static const bool img_on = getenv("MADB_PATCH_IMG") && atoi(getenv("MADB_PATCH_IMG")) == 1;
+   if (I.use_patches && (I.ops.img_tpe == 2 || (I.ops.img_tpe == 1 && img_on)))
+   {
+      PatchHost H;
+      ImgHost IH;
+      if (!patch_build_img(I, H, IH)) { return 1; }
+      if (upload(IH.desc, &I.d_idesc) || upload(IH.mblob, &I.d_mblob) ||
+          upload_ifc(H, I.d_ifc[1], I.pdev.vlist) || upload(I.rowptr, &I.d_rowptr) || upload(I.colidx, &I.d_colidx))
+      {
+         return 2;
+      }
+      CUDA_OK(cudaMalloc((void **)&I.d_vstage, std::max<size_t>(H.stage_size, 2) * sizeof(double)));
+      PatchDev &P = I.pdev;
+      P.vstage = I.d_vstage;
+      P.nv_ifc = (int)(H.dst.size() + H.dst4.size());
+      P.img.desc = I.d_idesc;
+      P.img.mblob = I.d_mblob;
+      P.img.max_vslots = IH.max_vslots;
+      P.img.max_yslots = IH.max_yslots;
+      P.img.max_mblob = IH.max_mblob;
+      P.img.nev = IH.nev;
+      P.img.ney = IH.ney;
+      for (size_t p = 0; p < I.pdesc.size(); p++)
+      {
+         // statistics (madb_integrator_patch_stats)
+         I.pdesc[p].nslots = IH.desc[p].sh0 + IH.desc[p].nsh;
+         I.pdesc[p].nexc = IH.desc[p].sh0;
+         I.pdesc[p].nruns = IH.desc[p].nruns;
+      }
+      return 0;
+   }
    if (I.use_patches)
    {
       PatchHost H;
@@ -984,6 +1021,23 @@ extern "C"
       s.e2l.assign(e2l, e2l + (size_t)ne * s.nd_el());
       long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
       const int rc = patch_selftest(m, s, max_err, st);
+      if (stats) { for (int k = 0; k < 8; k++) { stats[k] = st[k]; } }
+      return rc;
+   }
+
+   int madb_patch_selftest_img(int dim, int ne, const int32_t *e2n, int nnodes, const double *coords, int order, int vdim,
+                               int ordering, int ndofs, const int32_t *e2l, int tpe, double *max_err, int64_t *stats)
+   {
+      if (dim < 1 || dim > 3 || ne <= 0 || !e2n || !coords || !e2l || order < 1 || vdim < 1) { set_error("madb_patch_selftest_img: bad arguments"); return 1; }
+      Mesh m;
+      m.ctx = nullptr; m.dim = dim; m.ne = ne; m.geom_order = 1; m.nnodes = nnodes;
+      m.e2n.assign(e2n, e2n + (size_t)ne * (1 << dim));
+      m.coords.assign(coords, coords + (size_t)nnodes * dim);
+      Space s;
+      s.ctx = nullptr; s.mesh = &m; s.basis = BASIS_H1; s.order = order; s.vdim = vdim; s.ordering = ordering; s.ndofs = ndofs;
+      s.e2l.assign(e2l, e2l + (size_t)ne * s.nd_el());
+      long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const int rc = patch_selftest_img(m, s, tpe, max_err, st);
       if (stats) { for (int k = 0; k < 8; k++) { stats[k] = st[k]; } }
       return rc;
    }

@@ -22,62 +22,32 @@
 // sf2d_pair_keep_v / sf2d_pair_keep_y below, applying the mirror for thread 1.
 #pragma once
 #include "madb_kernels.cuh"
+#include "madb_pair_schedule.hpp"
 
 namespace madb
 {
-
-/// Walk of the kept matrix entries: for emission index e the LOCAL (I, J) the thread keeps (I = i2*ND + i1).
-/// Blocks (j1, i1 <= j1) in the order of the matrix phase; inside a block the (i2, j2) with (i2, j2) <= mirror in
-/// lexicographic order are kept.  Returns the number of kept entries; fills I[], J[] when non-null.
-template <int ND> MADB_HD constexpr int sf2d_pair_keep_v(int *Iout, int *Jout)
-{
-   int e = 0;
-   for (int j1 = 0; j1 < ND; j1++)
-   {
-      for (int i1 = 0; i1 <= j1; i1++)
-      {
-         for (int i2 = 0; i2 < ND; i2++)
-         {
-            for (int j2 = 0; j2 < ND; j2++)
-            {
-               if (i1 == j1 && i2 > j2) { continue; } // diagonal block: upper triangle only
-               // partner entry under the mirror: (ND-1-i2, ND-1-j2); in a diagonal block it is stored with sorted indices
-               int mi = ND - 1 - i2, mj = ND - 1 - j2;
-               if (i1 == j1 && mi > mj) { const int t = mi; mi = mj; mj = t; }
-               const bool keep = (i2 < mi) || (i2 == mi && j2 <= mj);
-               if (!keep) { continue; }
-               if (Iout) { Iout[e] = i2 * ND + i1; Jout[e] = j2 * ND + j1; }
-               e++;
-            }
-         }
-      }
-   }
-   return e;
-}
-/// Walk of the kept element-vector entries: rows i2 <= ND-1-i2.
-template <int ND> MADB_HD constexpr int sf2d_pair_keep_y(int *Iout)
-{
-   int e = 0;
-   for (int i2 = 0; 2 * i2 <= ND - 1; i2++)
-   {
-      for (int i1 = 0; i1 < ND; i1++)
-      {
-         if (Iout) { Iout[e] = i2 * ND + i1; }
-         e++;
-      }
-   }
-   return e;
-}
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ double shfl_xor1(double v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 
 /// configurations / functionals the pair kernel covers
+/// (compile with -DMADB_PAIR_KERNEL=1 to route these configurations through the thread-pair / CSR-image kernel; measured
+/// on config 2 it is slower than the warp-specialised kernel k_patch_ws -- profiles/r02_img_kernel.md -- so the default is off)
+#ifndef MADB_PAIR_KERNEL
+#define MADB_PAIR_KERNEL 0
+#endif
 template <class Func, class Cfg> constexpr bool sf2d_pair_ok()
 {
+#if MADB_PAIR_KERNEL
    if constexpr (sf2d_cfg<Cfg>()) { return Func::N_QPRM == 0 && Func::N_INPUT == 2 && (Cfg::NQ1D % 2) == 0; }
    else { return false; }
+#else
+   return false;
+#endif
 }
+
+/// elements per patch for <functional, configuration>: the pair kernel runs 64 elements per 128-thread work group
+template <class Func, class Cfg> constexpr int patch_pe_of() { return sf2d_pair_ok<Func, Cfg>() ? 64 : patch_pe(Cfg::NVD); }
 
 /// Fused residual + Jacobian of sorted element t by the thread pair (h = 0, 1).  ALL 32 lanes of the warp must call
 /// (shuffles); a lane without an element passes a valid t and ignores the sinks.
