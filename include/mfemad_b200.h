@@ -42,6 +42,8 @@ typedef struct madb_mesh madb_mesh;
 typedef struct madb_space madb_space;
 typedef struct madb_functional madb_functional;
 typedef struct madb_integrator madb_integrator;
+typedef struct madb_comm madb_comm;
+typedef struct madb_exchange madb_exchange;
 
 /* ADEval flags: src/_ad_intg.hpp:24-36 (same bit values) */
 enum
@@ -139,6 +141,32 @@ int madb_unpack(madb_ctx *ctx, int n, const int32_t *idx, const double *src, dou
  * (-1: none) added in that order (ascending peer rank: deterministic), on top of the old value if add != 0.
  * A dof shared by several ranks (a corner) has one destination entry with several sources. */
 int madb_unpack_multi(madb_ctx *ctx, int n, const int32_t *src4, const int32_t *dst_idx, const double *src, double *dst, int add);
+
+/* The same exchange behind the ABI for C++ / MFEM hosts: one process per GPU, NCCL send/recv between neighbouring
+ * ranks (ParMesh / ParFiniteElementSpace group communication, ex4.cpp:85,136 [MFEM-upstream]).
+ *   madb_comm_unique_id   rank 0 creates the 128-byte id and hands it to the other ranks (MPI_Bcast, a file, ...)
+ *   madb_comm_create      ncclCommInitRank on the context's device + a communication stream
+ *   madb_comm_allreduce_sum  global sums of up to 64 doubles (host or device pointer): Newton norms, the L1 change
+ *                         of lambda at ex4.cpp:205; same bits on every rank
+ *   madb_exchange_create  neighbour lists, peers in ascending rank order:
+ *        own_*   : per peer the LOCAL indices of dofs this rank owns and the peer holds a copy of
+ *        ghost_* : per peer the LOCAL indices of copies this rank holds of dofs the peer owns
+ *        (both sides list the dofs of a pair in the same order, e.g. ascending global id)
+ *   madb_exchange_begin(x, vec, reverse) / madb_exchange_end(x, vec, add): device vectors, asynchronous on the context
+ *        stream (pack kernel -> event -> ncclGroup{Send,Recv} on the communication stream -> event -> unpack kernel).
+ *        reverse = 0: P, owner -> copies (end with add = 0).  reverse = 1: P^T, copies -> owner (end with add = 1): the
+ *        values of one dof are added on the owner in ascending peer rank, independent of arrival order.
+ *        Work queued on the context stream between begin and end overlaps the transfer. */
+int madb_comm_unique_id(unsigned char *id128);
+int madb_comm_create(madb_ctx *ctx, const unsigned char *id128, int rank, int world, madb_comm **out);
+int madb_comm_destroy(madb_comm *c);
+int madb_comm_allreduce_sum(madb_comm *c, int n, double *values);
+int madb_exchange_create(madb_comm *c, int nown_peers, const int *own_peer, const int *own_count, const int32_t *own_idx,
+                         int nghost_peers, const int *ghost_peer, const int *ghost_count, const int32_t *ghost_idx,
+                         madb_exchange **out);
+int madb_exchange_destroy(madb_exchange *x);
+int madb_exchange_begin(madb_exchange *x, const double *vec, int reverse);
+int madb_exchange_end(madb_exchange *x, double *vec, int add);
 
 /* AD(Block)NonlinearFormIntegrator<modes...>(f, ir) attached to its form
  * (src/_ad_intg.hpp:71-155, :157-327).  fields: spaces[i] with ADEval modes[i];

@@ -62,6 +62,14 @@ def lib():
         L.madb_pack.argtypes = [vp, C.c_int, ip, dp, dp]
         L.madb_unpack.argtypes = [vp, C.c_int, ip, dp, dp, C.c_int]
         L.madb_unpack_multi.argtypes = [vp, C.c_int, ip, ip, dp, dp, C.c_int]
+        L.madb_comm_unique_id.argtypes = [C.c_char_p]
+        L.madb_comm_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, pp]
+        L.madb_comm_destroy.argtypes = [vp]
+        L.madb_comm_allreduce_sum.argtypes = [vp, C.c_int, dp]
+        L.madb_exchange_create.argtypes = [vp, C.c_int, ip, ip, ip, C.c_int, ip, ip, ip, pp]
+        L.madb_exchange_destroy.argtypes = [vp]
+        L.madb_exchange_begin.argtypes = [vp, dp, C.c_int]
+        L.madb_exchange_end.argtypes = [vp, dp, C.c_int]
         L.madb_lvpp_update.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, C.POINTER(C.c_double)]
         L.madb_integrator_create.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, pp]
         L.madb_integrator_create_ex.argtypes = [vp, C.c_int, pp, ip, ip, vp, C.c_int, C.c_int, pp]

@@ -176,3 +176,197 @@ class SharedDofExchange:
     def broadcast_from_owner(self, x):
         """P: every sharer's copy is overwritten with the owner's value."""
         self._exchange(x, self.recv_up, self.send_up, False, "down")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Overlapping element partition: owned elements + one layer of ghost elements (SURVEY 5 / 8e).
+# Every element that touches a dof owned by this rank is local, so the ROWS of owned dofs -- residual entries and
+# Jacobian rows, i.e. this rank's rows of P^T A P -- are complete after the local assembly and summed in the local,
+# fixed patch order; the only communication per assembly is P: owner -> copies for the state and the parameter
+# fields (HaloExchange.forward).  P^T (reverse) is available for vectors assembled on non-overlapping partitions.
+# ---------------------------------------------------------------------------------------------------------------
+def halo_lists(l2g, owner, rank, world, group=None):
+    """Neighbour lists of the exchange from the local->global map and the owner rank of every local dof:
+    own[r]  = local indices of dofs this rank owns and rank r holds a copy of,
+    ghost[r] = local indices of the copies this rank holds of dofs rank r owns; both in ascending global id."""
+    l2g = np.asarray(l2g, dtype=np.int64)
+    owner = np.asarray(owner, dtype=np.int64)
+    need = {}
+    for r in np.unique(owner):
+        r = int(r)
+        if r == rank:
+            continue
+        idx = np.nonzero(owner == r)[0]
+        idx = idx[np.argsort(l2g[idx], kind="stable")]
+        need[r] = idx
+    published = [None] * world
+    dist.all_gather_object(published, {r: l2g[idx] for r, idx in need.items()}, group=group)
+    order = np.argsort(l2g, kind="stable")
+    sorted_g = l2g[order]
+    own = {}
+    for r in range(world):
+        if r == rank or published[r] is None or rank not in published[r]:
+            continue
+        g = published[r][rank]
+        pos = np.searchsorted(sorted_g, g)
+        if np.any(pos >= sorted_g.size) or np.any(sorted_g[np.minimum(pos, sorted_g.size - 1)] != g):
+            raise ValueError("halo_lists: rank %d asks rank %d for dofs it does not hold" % (r, rank))
+        loc = order[pos]
+        if np.any(owner[loc] != rank):
+            raise ValueError("halo_lists: rank %d asks rank %d for dofs it does not own" % (r, rank))
+        own[r] = loc
+    return own, need
+
+
+class HaloExchange:
+    """P (forward: owner -> copies) and P^T (reverse: copies -> owner, added in ascending peer rank) for one local
+    vector.  CUDA tensors go through the C ABI (madb_exchange_*: pack kernel, ncclSend/ncclRecv group on a
+    communication stream, unpack kernel; asynchronous on the context stream); CPU tensors (gloo, the tests of the host
+    logic) through torch.distributed."""
+
+    def __init__(self, own, ghost, ctx=None, comm=None, group=None):
+        self.group, self.ctx, self.comm = group, ctx, comm
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.own = {int(r): np.asarray(v, dtype=np.int32) for r, v in sorted(own.items()) if len(v)}
+        self.ghost = {int(r): np.asarray(v, dtype=np.int32) for r, v in sorted(ghost.items()) if len(v)}
+        self.h = None
+        if comm is not None:
+            import ctypes as C
+            from . import lib, _check
+
+            def pack(d):
+                peers = np.array(sorted(d), dtype=np.int32)
+                counts = np.array([d[r].size for r in peers], dtype=np.int32)
+                idx = np.concatenate([d[r] for r in peers]).astype(np.int32) if peers.size else np.zeros(0, np.int32)
+                return peers, counts, np.ascontiguousarray(idx)
+            op, oc, oi = pack(self.own)
+            gp, gc, gi = pack(self.ghost)
+            h = C.c_void_p()
+            _check(lib().madb_exchange_create(comm.h, op.size, op.ctypes.data, oc.ctypes.data, oi.ctypes.data,
+                                              gp.size, gp.ctypes.data, gc.ctypes.data, gi.ctypes.data, C.byref(h)))
+            self.h = h
+
+    # ---- device path ----
+    def begin(self, vec, reverse=False):
+        from . import lib, _check
+        _check(lib().madb_exchange_begin(self.h, vec.data_ptr(), 1 if reverse else 0))
+
+    def end(self, vec, add=False):
+        from . import lib, _check
+        _check(lib().madb_exchange_end(self.h, vec.data_ptr(), 1 if add else 0))
+
+    # ---- both paths ----
+    def forward(self, x):
+        """P: the copies are overwritten with the owner's values."""
+        if x.is_cuda:
+            self.begin(x, False)
+            self.end(x, False)
+        else:
+            self._cpu(x, self.own, self.ghost, False)
+
+    def reverse(self, y):
+        """P^T: the owner's value becomes own + sum of the copies (ascending peer rank)."""
+        if y.is_cuda:
+            self.begin(y, True)
+            self.end(y, True)
+        else:
+            self._cpu(y, self.ghost, self.own, True)
+
+    def _cpu(self, vec, send, recv, add):
+        scount = [send[r].size if r in send else 0 for r in range(self.world)]
+        rcount = [recv[r].size if r in recv else 0 for r in range(self.world)]
+        sidx = np.concatenate([send[r] for r in sorted(send)]) if send else np.zeros(0, np.int64)
+        sbuf = vec[torch.from_numpy(sidx.astype(np.int64))].contiguous() if sum(scount) else torch.zeros(0, dtype=vec.dtype)
+        rbuf = torch.zeros(sum(rcount), dtype=vec.dtype)
+        dist.all_to_all_single(rbuf, sbuf, rcount, scount, group=self.group)
+        off = 0
+        for r in sorted(recv):  # ascending peer rank: fixed summation order
+            idx = torch.from_numpy(recv[r].astype(np.int64))
+            part = rbuf[off:off + recv[r].size]
+            if add:
+                vec[idx] = vec[idx] + part
+            else:
+                vec[idx] = part
+            off += recv[r].size
+
+    def __del__(self):
+        try:
+            if self.h is not None:
+                from . import lib
+                lib().madb_exchange_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Comm:
+    """NCCL communicator behind the C ABI (madb_comm_*); the unique id travels through torch.distributed here, a C++ host
+    would use MPI_Bcast."""
+
+    def __init__(self, ctx, group=None):
+        import ctypes as C
+        from . import lib, _check
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            _check(lib().madb_comm_unique_id(buf))
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        h = C.c_void_p()
+        _check(lib().madb_comm_create(ctx.h, box[0], rank, world, C.byref(h)))
+        self.h, self.ctx, self.rank, self.world = h, ctx, rank, world
+
+    def allreduce_sum(self, values):
+        from . import lib, _check
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _check(lib().madb_comm_allreduce_sum(self.h, v.size, v.ctypes.data))
+        return v
+
+    def __del__(self):
+        try:
+            from . import lib
+            lib().madb_comm_destroy(self.h)
+        except Exception:
+            pass
+
+
+def cartesian_block_ghost(rank, world, n, p_h1, p_l2=None, lengths=(1.0, 1.0)):
+    """This rank's n x n block of the (px*n) x (py*n) mesh plus one layer of ghost elements towards the higher ranks
+    (right / top), the order-p_h1 H1 space and (optionally) the order-p_l2 L2 space on it.
+
+    A dof is owned by the lowest rank whose OWN elements touch it: block (rx, ry) owns the dofs of its closed block
+    except those on its left / bottom edge when a lower neighbour exists; the ghost layer makes every element touching
+    an owned dof local.  Returns dict(mesh, h1, l2, l2g_h1, owner_h1, l2g_l2, owner_l2, owned_elements, px, py)."""
+    from . import meshgen as G
+    px, py = rank_grid(world)
+    rx, ry = rank % px, rank // px
+    gx, gy = (1 if rx < px - 1 else 0), (1 if ry < py - 1 else 0)
+    nx, ny = n + gx, n + gy
+    mesh = G.cartesian_mesh((nx, ny), lengths=(lengths[0] * nx / n, lengths[1] * ny / n))
+    mesh["coords"] = mesh["coords"] + np.array([rx * lengths[0], ry * lengths[1]])
+    h1 = G.h1_space(mesh, p_h1)
+    p = p_h1
+    ngx = nx * p + 1
+    NGX = px * n * p + 1
+    iy, ix = np.divmod(np.arange(h1["ndofs"], dtype=np.int64), ngx)
+    gix, giy = ix + rx * n * p, iy + ry * n * p
+    l2g_h1 = giy * NGX + gix
+
+    def block_owner(gi_, nb, last):  # block index of the lowest block touching global node index gi_ (block size nb*p)
+        b = gi_ // (n * p)
+        on_edge = (gi_ % (n * p) == 0) & (b > 0)
+        b = np.where(on_edge, b - 1, b)
+        return np.minimum(b, last)
+    owner_h1 = block_owner(giy, n, py - 1) * px + block_owner(gix, n, px - 1)
+    ey, ex = np.divmod(np.arange(nx * ny, dtype=np.int64), nx)
+    owned_el = (ex < n) & (ey < n)
+    owner_el = (np.minimum((ey + ry * n) // n, py - 1)) * px + np.minimum((ex + rx * n) // n, px - 1)
+    out = dict(mesh=mesh, h1=h1, l2g_h1=l2g_h1, owner_h1=owner_h1, owned_elements=owned_el, px=px, py=py, rx=rx, ry=ry,
+               owner_el=owner_el)
+    if p_l2 is not None:
+        l2 = G.l2_space(mesh, p_l2)
+        nd = (p_l2 + 1) ** 2
+        gel = (ey + ry * n) * (px * n) + (ex + rx * n)
+        out["l2"] = l2
+        out["l2g_l2"] = (gel[:, None] * nd + np.arange(nd)[None, :]).reshape(-1)
+        out["owner_l2"] = np.repeat(owner_el, nd)
+    return out
