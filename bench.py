@@ -30,10 +30,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 EPS = 0.5
 P = 2
-FP64_INSTR = 2514  # DFMA+DMUL+DADD executed per element by k_patch_ws<minsurf,Q2> (ncu smsp__sass_thread_inst_executed_op_d*)
+FP64_INSTR = 2278  # DFMA+DMUL+DADD executed per element by k_patch_ws<minsurf,Q2> (ncu smsp__sass_thread_inst_executed_op_d*, r02 v1)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_patch_ws launch of this workload (1000x1000),
-# ncu --set full capture summarised in profiles/r01_v2_k_patch_ws.md
-NCU_TRAFFIC_BYTES = {1000: 951191552}
+# ncu --set full capture summarised in profiles/r02_k_patch_ws.md (409.3 MB read + 535.8 MB written)
+NCU_TRAFFIC_BYTES = {1000: 945158400}
 
 
 def peaks():

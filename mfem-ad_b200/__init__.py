@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmadb.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("MADB_LIB", "libmadb.so"))  # MADB_LIB: a variant build (tools/variant.sh)
 
 QVALUE, VALUE, GRAD, DIV, CURL, HESSIAN, VECTOR, VECFE = (1 << i for i in range(8))
 BASIS_H1, BASIS_L2 = 0, 1

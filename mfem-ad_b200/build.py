@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libmadb.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
-         "-diag-suppress", "177,550,128"]
+         "-diag-suppress", "177,550,128"] + os.environ.get("MADB_CFLAGS", "").split()
 
 
 def _deps_newer(obj):

@@ -1,0 +1,18 @@
+// Fused-kernel instances: 2-D scalar spaces with ADEval::VALUE (split from instances_scalar2d.cu for build time).
+#include "madb_functionals.cuh"
+#include "madb_registry.cuh"
+using namespace madb;
+
+// MassEnergy (src/ad_native.hpp:413-420) and DiffEnergy (:483-525: energy(x - target), the target a per-point
+// parameter) on scalar spaces with ADEval::VALUE: L2 projection-type forms
+using Q1V = Config<2, 3, Field<2, 1, EV_VALUE>>;
+using Q2V = Config<2, 4, Field<3, 1, EV_VALUE>>;
+using Mass1 = MassEnergy<1>;
+using DiffMass1 = DiffEnergy<Mass1>;
+MADB_INSTANCE("mass", Mass1, Q1V, true)
+MADB_INSTANCE("mass", Mass1, Q2V, true)
+MADB_INSTANCE("diff[mass]", DiffMass1, Q1V, true)
+MADB_INSTANCE("diff[mass]", DiffMass1, Q2V, true)
+// the target as a GridFunction parameter of the same space (Evaluator GridFunction source)
+using Q2VP = Config<2, 4, Field<3, 1, EV_VALUE>, Field<3, 1, EV_VALUE, ROLE_PARAM>>;
+MADB_INSTANCE("diff[mass]", DiffMass1, Q2VP, true)

@@ -49,17 +49,29 @@ struct PatchDesc
    int vblob_off, vblob_bytes; // matrix-side maps: vblob + 16*vblob_off
    int nchunk, nirr;          // chunk descriptors (padded to a multiple of 32) / irregular chunks (multiple of 8)
    int nvsrc;                 // entries of vsrc (>= nslots, padded to 32*nchunk)
-   int pad[2];
+   int npair, ngen;           // work lists of the write-out: aligned pairs of chunks / general chunks (each + 1 dummy entry)
 };
 // Blob layouts (sections padded to 16 bytes, copied to shared memory with one bulk copy each):
-//   y blob: ysrc u16[nrows]  | yfold u32[nyfold] | ylist i32[nrow_int]
-//   v blob: vsrc u16[nvsrc] | vfold u32[nvfold] | chunk i32[4*nchunk] | isrc u16[32*nirr] | over i32[32*nirr]
-//           chunk c covers slots [32c, 32c+32) of the directly written slots [0,nexc):
-//           {g0, g1 - split, split, n}: lanes < n store; lane < split -> CSR position g0 + lane, else g1 + (lane - split);
-//           n = 0: nothing (padding, or an irregular chunk: its sources / explicit positions are isrc / over, -1 = none)
+//   y blob: ysrc u16[nrows]  | ylist i32[nrow_int] | yfold u32[nyfold]
+//   v blob: vsrc u16[nvsrc] | plist i32[2*(npair+1)] | glist i32[4*(ngen+1)] | isrc u16[32*nirr] | over i32[32*nirr] | vfold u32[nvfold]
+//           (gather part first, fold list last: k_patch_ws fetches the fold list of the next patch as soon as the fold of
+//           the current one is done and the gather part when its drain is complete; sizes: patch_yg_bytes / patch_vg_bytes)
+//           the directly written slots [0,nexc) are cut into chunks of 32 slots; a chunk is written through one of
+//           plist {g0, s0}: slots [s0, s0+64) (two full chunks) go to the 64 consecutive CSR positions from g0 (even):
+//                 lane l gathers the slots s0 + 2l, s0 + 2l + 1 and writes them with one 16-byte store; g0 = -1: nothing
+//           glist {g0, g1 - split, split, n | s0 << 8}: lanes < n store slot s0 + lane; lane < split -> CSR position
+//                 g0 + lane, else g1 + (lane - split); n = 0: nothing
+//           isrc / over: irregular chunks (more than one break or a dummy slot): sources / explicit positions, -1 = none
+//           (both lists end with one entry that stores nothing: the device clamps list indices instead of branching)
 // ysrc/vsrc: shared-memory location (entry * PATCH_LD + local element) of the first source of a row / slot.
 // fold lists: 8 counts (phases 1..8), then words (dst | src << 16): staged[dst] += staged[src], phase by phase;
 // phase k adds the k-th further source, so every row / slot is summed in ascending element order.
+inline constexpr int patch_yg_bytes(const PatchDesc &D) { return patch_al16(2 * D.nrows) + patch_al16(4 * D.nrow_int); }
+inline constexpr int patch_vg_bytes(const PatchDesc &D)
+{
+   return patch_al16(2 * D.nvsrc) + patch_al16(8 * (D.npair + 1)) + patch_al16(16 * (D.ngen + 1)) + patch_al16(64 * D.nirr) +
+          patch_al16(128 * D.nirr);
+}
 struct IfcListDev // interface reduction lists of one side (see k_ifc_reduce)
 {
    int n4, ng;
@@ -107,6 +119,7 @@ struct PatchDev
 {
    int npatch;
    int max_yblob, max_vblob; // bytes, shared-memory sizing
+   int max_yg, max_yf, max_vg, max_vf; // the same split in gather part / fold list (k_patch_ws prefetches them separately)
    const PatchDesc *desc;
    const unsigned char *yblob, *vblob;
    double *ystage, *vstage;
@@ -114,6 +127,8 @@ struct PatchDev
    int ny_ifc, nv_ifc; // entries (statistics)
    IfcListDev ylist, vlist;
    ImgDev img; // CSR-image kernel (desc == null: not in use)
+   int diag = 0; // MADB_DIAG (measurement only, results are wrong): 1 = writers skip the drain, 2 = compute warps skip the
+                 // element computation
 };
 
 struct LaunchCtx
@@ -141,6 +156,8 @@ struct LaunchCtx
    const PatchDev *patch; // non-null: patch assembly (elements in patch order)
    cudaEvent_t ev0, ev1;  // non-null: recorded around the element kernel(s) (madb_integrator_set_timing)
 };
+
+constexpr int MADB_RC_MIRROR = -77; // KernelOps::launch: 1-D tables without mirror symmetry on the sum-factorised path
 
 struct KernelOps
 {
@@ -266,6 +283,7 @@ struct Integrator
    std::vector<int> prows;      // concatenated local row lists (global dof ids), per patch [nrows]
    std::vector<int> prow_off;   // [npatch+1]
    int max_yblob = 0, max_vblob = 0;
+   int max_yg = 0, max_yf = 0, max_vg = 0, max_vf = 0;
    bool have_patch_vals = false;
    PatchDev pdev {};
    PatchDesc *d_pdesc = nullptr;

@@ -513,6 +513,9 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables
    }
 }
 
+#ifndef MADB_SF2D_FENCE
+#define MADB_SF2D_FENCE 1
+#endif
 /// Sum-factorised gather + quadrature loop (madb_sf2d.cuh) for 2-D scalar H1 fields with ADEval::GRAD.
 /// The element vector is returned in r; the entries of the upper triangle of the element matrix are handed
 /// to sink(k, value), k = symidx(I, J), one by one at the end (they never all live in registers: the
@@ -521,35 +524,47 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables
 struct NoHook
 {
    __device__ __forceinline__ void operator()() const {}
+   __device__ __forceinline__ void operator()(int) const {}
 };
-template <class Func, class Cfg, int MODE, class Sink, class HookPre = NoHook>
-__device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a, const int t,
-                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink,
-                                                     HookPre &&pre_matrix = HookPre())
+/// Inputs of one element of the sum-factorised 2-D path: vertex coordinates, dof values (and the direction of ACT)
+template <class Cfg, bool ACT> struct Sf2dIn
+{
+   static constexpr int ND = Cfg::template field<0>::ND1D;
+   double X[4][2];
+   double u[ND][ND], vd[ACT ? ND : 1][ACT ? ND : 1];
+};
+template <class Func, class Cfg, bool ACT>
+__device__ __forceinline__ void sf2d_gather(const AsmArgs<Func, Cfg> &a, const int t, Sf2dIn<Cfg, ACT> &in)
+{
+   constexpr int ND = Cfg::template field<0>::ND1D, NVD = Cfg::NVD;
+#pragma unroll
+   for (int k = 0; k < 4; k++)
+   {
+      const int n = a.e2n[(size_t)k * a.stride + t];
+      in.X[k][0] = a.coords[(size_t)n * 2];
+      in.X[k][1] = a.coords[(size_t)n * 2 + 1];
+   }
+#pragma unroll
+   for (int i = 0; i < NVD; i++)
+   {
+      const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
+      in.u[i / ND][i % ND] = a.x[idx];
+      if constexpr (ACT) { in.vd[i / ND][i % ND] = a.v[idx]; }
+   }
+}
+template <class Func, class Cfg, int MODE, class Sink, class HookPre = NoHook, class HookMid = NoHook>
+__device__ __forceinline__ void element_compute_sf2d_core(const AsmArgs<Func, Cfg> &a, const Sf2dIn<Cfg, (MODE & MODE_ACT) != 0> &in,
+                                                          double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink,
+                                                          HookPre &&pre_matrix = HookPre(), HookMid &&mid_matrix = HookMid())
 {
    constexpr int ND = Cfg::template field<0>::ND1D, NQ = Cfg::NQ1D, NVD = Cfg::NVD;
    constexpr bool RES = (MODE & MODE_RES) != 0, JAC = (MODE & MODE_JAC) != 0, ACT = (MODE & MODE_ACT) != 0;
    constexpr int ORDER = (JAC || ACT) ? 2 : 1;
    static_assert(Func::N_INPUT == 2 && Func::N_QPRM == 0, "sum-factorised 2-D path: scalar field, GRAD, no per-point parameters");
    const auto &T = a.sf;
-
-   // ---- gather ---------------------------------------------------------------------------
-   double X[4][2];
-   double u[ND][ND], vd[ACT ? ND : 1][ACT ? ND : 1];
-#pragma unroll
-   for (int k = 0; k < 4; k++)
-   {
-      const int n = a.e2n[(size_t)k * a.stride + t];
-      X[k][0] = a.coords[(size_t)n * 2];
-      X[k][1] = a.coords[(size_t)n * 2 + 1];
-   }
-#pragma unroll
-   for (int i = 0; i < NVD; i++)
-   {
-      const int idx = a.vmap[(size_t)i * a.stride + t] & 0x7fffffff;
-      u[i / ND][i % ND] = a.x[idx];
-      if constexpr (ACT) { vd[i / ND][i % ND] = a.v[idx]; }
-   }
+   const auto &X = in.X;
+   const auto &u = in.u;
+   const auto &vd = in.vd;
    Func f;
    f.load(a.fparams);
 
@@ -713,23 +728,80 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
 #pragma unroll
          for (int i1 = 0; i1 <= j1; i1++)
          {
-            ZD T00[NQ], T01[NQ], T10[NQ], T11[NQ]; // per q2: sum_q1 (1-D products)[q1][i1][j1] H^ab(q2,q1)
-#pragma unroll
-            for (int q2 = 0; q2 < NQ; q2++)
+            // Scheduling fence between two (i1, j1) blocks: left alone, ptxas hoists the q1-contractions of the later
+            // blocks above the emission of the earlier ones and spills about 50 registers per element.  The stores of
+            // the previous block stay above the fence ("memory"), the pulled-back Hessians are "redefined" by it.
+            mid_matrix(j1 * (j1 + 1) / 2 + i1); // k_patch_ws: loads of the next element are issued between two blocks
+            if (MADB_SF2D_FENCE && (i1 + j1) > 0)
             {
-               ZD s00 {0.0, true}, s01 {0.0, true}, s10 {0.0, true}, s11 {0.0, true};
 #pragma unroll
-               for (int q1 = 0; q1 < NQ; q1++)
+               for (int q2 = 0; q2 < NQ; q2++)
                {
-                  s00 = zfmac(H00[q2][q1], T.GG[q1][i1][j1], s00);
-                  s01 = zfmac(H01[q2][q1], T.BG[q1][j1][i1], s01); // G[q1][i1] B[q1][j1]
-                  if (i1 != j1) { s10 = zfmac(H01[q2][q1], T.BG[q1][i1][j1], s10); } // G[q1][j1] B[q1][i1]
-                  s11 = zfmac(H11[q2][q1], T.BB[q1][i1][j1], s11);
+#pragma unroll
+                  for (int q1 = 0; q1 < NQ; q1++)
+                  {
+                     if (!H00[q2][q1].z) { asm volatile("" : "+d"(H00[q2][q1].v)::"memory"); }
+                     if (!H01[q2][q1].z) { asm volatile("" : "+d"(H01[q2][q1].v)::"memory"); }
+                     if (!H11[q2][q1].z) { asm volatile("" : "+d"(H11[q2][q1].v)::"memory"); }
+                  }
                }
-               T00[q2] = s00;
-               T01[q2] = s01;
-               T10[q2] = (i1 != j1) ? s10 : s01;
-               T11[q2] = s11;
+            }
+            // per q2: Tab = sum_q1 (1-D products)[q1][i1][j1] H^ab(q2,q1); kept as even / odd parts over q2 (mirror
+            // q2' = NQ-1-q2): P multiplies the symmetrised tables, M the antisymmetrised ones; T01 / T10 multiply
+            // B G products, which change sign under the mirror (madb_sf2d.cuh)
+            constexpr int NQH = (NQ + 1) / 2;
+            ZD P00[NQH], P01[NQH], P10[NQH], P11[NQH], M00[NQH], M01[NQH], M10[NQH], M11[NQH];
+#pragma unroll
+            for (int q = 0; q < NQH; q++)
+            {
+               ZD t00[2], t01[2], t10[2], t11[2];
+#pragma unroll
+               for (int h = 0; h < 2; h++)
+               {
+                  const int q2 = h ? NQ - 1 - q : q;
+                  ZD s00 {0.0, true}, s01 {0.0, true}, s10 {0.0, true}, s11 {0.0, true};
+                  if (h == 0 || q2 != q)
+                  {
+#pragma unroll
+                     for (int q1 = 0; q1 < NQ; q1++)
+                     {
+                        s00 = zfmac(H00[q2][q1], T.GG[q1][i1][j1], s00);
+                        s01 = zfmac(H01[q2][q1], T.BG[q1][j1][i1], s01); // G[q1][i1] B[q1][j1]
+                        if (i1 != j1) { s10 = zfmac(H01[q2][q1], T.BG[q1][i1][j1], s10); } // G[q1][j1] B[q1][i1]
+                        s11 = zfmac(H11[q2][q1], T.BB[q1][i1][j1], s11);
+                     }
+                  }
+                  t00[h] = s00;
+                  t01[h] = s01;
+                  t10[h] = (i1 != j1) ? s10 : s01;
+                  t11[h] = s11;
+               }
+               if (q == NQ - 1 - q)
+               {
+                  P00[q] = M00[q] = t00[0];
+                  P01[q] = M01[q] = t01[0];
+                  P10[q] = M10[q] = t10[0];
+                  P11[q] = M11[q] = t11[0];
+               }
+               else
+               {
+                  P00[q] = zadd(t00[0], t00[1]);
+                  M00[q] = zsub(t00[0], t00[1]);
+                  P11[q] = zadd(t11[0], t11[1]);
+                  M11[q] = zsub(t11[0], t11[1]);
+                  P01[q] = zsub(t01[0], t01[1]);
+                  M01[q] = zadd(t01[0], t01[1]);
+                  if (i1 != j1)
+                  {
+                     P10[q] = zsub(t10[0], t10[1]);
+                     M10[q] = zadd(t10[0], t10[1]);
+                  }
+                  else
+                  {
+                     P10[q] = P01[q];
+                     M10[q] = M01[q];
+                  }
+               }
             }
 #pragma unroll
             for (int i2 = 0; i2 < ND; i2++)
@@ -738,23 +810,58 @@ __device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a
                for (int j2 = 0; j2 < ND; j2++)
                {
                   if (i1 == j1 && i2 > j2) { continue; }
-                  // entry (I, J), I = (i2, i1), J = (j2, j1)
-                  double v = 0.0;
-#pragma unroll
-                  for (int q2 = 0; q2 < NQ; q2++)
+                  // entry (I, J), I = (i2, i1), J = (j2, j1), and its mirror partner (i2', j2') (for i1 == j1 the block
+                  // is symmetric and the partner is stored as its transpose when i2' > j2')
+                  int pi = ND - 1 - i2, pj = ND - 1 - j2;
+                  if (i1 == j1 && pi > pj)
                   {
-                     zacc(v, T00[q2], T.BB[q2][i2][j2]);
-                     zacc(v, T01[q2], T.BG[q2][i2][j2]);
-                     zacc(v, T10[q2], T.BG[q2][j2][i2]);
-                     zacc(v, T11[q2], T.GG[q2][i2][j2]);
+                     const int tmp = pi;
+                     pi = pj;
+                     pj = tmp;
+                  }
+                  const int lin = i2 * ND + j2, plin = pi * ND + pj;
+                  if (plin < lin) { continue; } // emitted together with its partner
+                  double se = 0.0;
+#pragma unroll
+                  for (int q = 0; q < NQH; q++)
+                  {
+                     zacc(se, P00[q], T.BBs[q][i2][j2]);
+                     zacc(se, P01[q], T.BGs[q][i2][j2]);
+                     zacc(se, P10[q], T.BGs[q][j2][i2]);
+                     zacc(se, P11[q], T.GGs[q][i2][j2]);
                   }
                   const int I = i2 * ND + i1, J = j2 * ND + j1;
-                  sink(symidx(I, J), v);
+                  if (plin == lin) { sink(symidx(I, J), se); }
+                  else
+                  {
+                     double so = 0.0;
+#pragma unroll
+                     for (int q = 0; q < NQH; q++)
+                     {
+                        zacc(so, M00[q], T.BBd[q][i2][j2]);
+                        zacc(so, M01[q], T.BGd[q][i2][j2]);
+                        zacc(so, M10[q], T.BGd[q][j2][i2]);
+                        zacc(so, M11[q], T.GGd[q][i2][j2]);
+                     }
+                     sink(symidx(I, J), se + so);
+                     sink(symidx(pi * ND + i1, pj * ND + j1), se - so);
+                  }
                }
             }
          }
       }
    }
+}
+
+/// gather + computation of sorted element t
+template <class Func, class Cfg, int MODE, class Sink, class HookPre = NoHook>
+__device__ __forceinline__ void element_compute_sf2d(const AsmArgs<Func, Cfg> &a, const int t,
+                                                     double (&r)[(MODE & (MODE_RES | MODE_ACT)) ? Cfg::NVD : 1], Sink &&sink,
+                                                     HookPre &&pre_matrix = HookPre())
+{
+   Sf2dIn<Cfg, (MODE & MODE_ACT) != 0> in;
+   sf2d_gather<Func, Cfg, (MODE & MODE_ACT) != 0>(a, t, in);
+   element_compute_sf2d_core<Func, Cfg, MODE>(a, in, r, sink, pre_matrix);
 }
 
 /// does <functional, configuration, mode> take the sum-factorised 2-D path?

@@ -264,14 +264,14 @@ bool patch_build_y(Integrator &I, PatchHost &H)
          ylist.assign(R.begin(), R.begin() + D.nrow_int);
          BlobWriter W;
          W.section(first, first.size());
-         W.section(fold, fold.size());
          W.section(ylist, ylist.size());
+         W.section(fold, fold.size());
          blobs[p].swap(W.b);
       }
    });
    if (!ok) { return false; }
    long soff = 0, boff = 0;
-   I.max_yblob = 0;
+   I.max_yblob = I.max_yg = I.max_yf = 0;
    for (int p = 0; p < np; p++)
    {
       PatchDesc &D = I.pdesc[p];
@@ -282,6 +282,8 @@ bool patch_build_y(Integrator &I, PatchHost &H)
       boff += (long)blobs[p].size();
       I.prow_off[p + 1] = I.prow_off[p] + D.nrows;
       I.max_yblob = std::max(I.max_yblob, D.yblob_bytes);
+      I.max_yg = std::max(I.max_yg, patch_yg_bytes(D));
+      I.max_yf = std::max(I.max_yf, patch_al16(4 * D.nyfold));
    }
    H.stage_size = soff;
    H.blob.resize(std::max<long>(boff, 16));
@@ -355,7 +357,7 @@ bool patch_build_v(Integrator &I, PatchHost &H)
    bool ok = true;
    parallel_for_p(np, 64, [&](long b, long e)
    {
-      std::vector<int> vd, base, run_s, run_g, keyslot, xg, gpos, chunks, over;
+      std::vector<int> vd, base, run_s, run_g, keyslot, xg, gpos, chunks, over, plist, glist;
       std::vector<unsigned short> isrc;
       std::vector<std::pair<int, int>> excl; // (CSR position, key index)
       std::vector<std::vector<unsigned short>> srcs;
@@ -498,6 +500,25 @@ bool patch_build_v(Integrator &I, PatchHost &H)
             {
                for (int q = 0; q < 32; q++) { over.push_back(-1); isrc.push_back(0); }
             }
+            // the two work lists of the device: aligned pairs {g0, first slot} and general chunks
+            // {g0, g1 - split, split, n | first slot << 8}; each ends with one entry that stores nothing (the device
+            // clamps out-of-range list indices onto it instead of branching)
+            plist.clear();
+            glist.clear();
+            for (int c = 0; c < nchunk; c++)
+            {
+               const int *d = &chunks[(size_t)4 * c];
+               if (d[3] == 64) { plist.push_back(d[0]); plist.push_back(32 * c); }
+               else if (d[3] > 0)
+               {
+                  glist.push_back(d[0]); glist.push_back(d[1]); glist.push_back(d[2]);
+                  glist.push_back(d[3] | ((32 * c) << 8));
+               }
+            }
+            D.npair = (int)plist.size() / 2;
+            D.ngen = (int)glist.size() / 4;
+            plist.push_back(-1); plist.push_back(0);
+            for (int q = 0; q < 4; q++) { glist.push_back(0); }
             D.nchunk = nchunk;
             D.nirr = (int)over.size() / 32;
             first.resize(std::max<size_t>(first.size(), (size_t)32 * (nchunk + 2)), 0); // padded so that chunk loads stay in bounds
@@ -505,16 +526,17 @@ bool patch_build_v(Integrator &I, PatchHost &H)
          D.nvsrc = (int)first.size();
          BlobWriter W;
          W.section(first, first.size());
-         W.section(fold, fold.size());
-         W.section(chunks, chunks.size());
+         W.section(plist, plist.size());
+         W.section(glist, glist.size());
          W.section(isrc, isrc.size());
          W.section(over, over.size());
+         W.section(fold, fold.size());
          blobs[p].swap(W.b);
       }
    });
    if (!ok) { set_error("patch assembly: a matrix entry has more than 8 contributing elements in one patch"); return false; }
    long soff = 0, boff = 0;
-   I.max_vblob = 0;
+   I.max_vblob = I.max_vg = I.max_vf = 0;
    for (int p = 0; p < np; p++)
    {
       PatchDesc &D = I.pdesc[p];
@@ -524,6 +546,8 @@ bool patch_build_v(Integrator &I, PatchHost &H)
       soff += D.nslots - D.nexc;
       boff += (long)blobs[p].size();
       I.max_vblob = std::max(I.max_vblob, D.vblob_bytes);
+      I.max_vg = std::max(I.max_vg, patch_vg_bytes(D));
+      I.max_vf = std::max(I.max_vf, patch_al16(4 * D.nvfold));
    }
    if (boff / 16 >= 0x7fffffffL) { set_error("patch assembly: maps too large"); return false; }
    H.stage_size = soff;
@@ -943,8 +967,8 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
       {
          const unsigned char *yb = HY.blob.data() + (size_t)D.yblob_off * 16;
          const unsigned short *ysrc = (const unsigned short *)yb;
-         const unsigned *yfold = (const unsigned *)(yb + patch_al16(2 * D.nrows));
-         const int *ylist = (const int *)((const unsigned char *)yfold + patch_al16(4 * D.nyfold));
+         const int *ylist = (const int *)(yb + patch_al16(2 * D.nrows));
+         const unsigned *yfold = (const unsigned *)(yb + patch_yg_bytes(D));
          int base = 8;
          for (int ph = 0; ph < 8; ph++)
          {
@@ -963,9 +987,10 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
       {
          const unsigned char *vb = HV.blob.data() + (size_t)D.vblob_off * 16;
          const unsigned short *vsrc = (const unsigned short *)vb;
-         const unsigned *vfold = (const unsigned *)(vb + patch_al16(2 * D.nvsrc));
-         const int *chunks = (const int *)((const unsigned char *)vfold + patch_al16(4 * D.nvfold));
-         const unsigned short *isrc = (const unsigned short *)((const unsigned char *)chunks + patch_al16(16 * (D.nchunk + 2)));
+         const unsigned *vfold = (const unsigned *)(vb + patch_vg_bytes(D));
+         const int *plist = (const int *)(vb + patch_al16(2 * D.nvsrc));
+         const int *glist = (const int *)((const unsigned char *)plist + patch_al16(8 * (D.npair + 1)));
+         const unsigned short *isrc = (const unsigned short *)((const unsigned char *)glist + patch_al16(16 * (D.ngen + 1)));
          const int *over = (const int *)((const unsigned char *)isrc + patch_al16(64 * D.nirr));
          int base = 8;
          for (int ph = 0; ph < 8; ph++)
@@ -974,19 +999,19 @@ int patch_selftest(Mesh &mesh, Space &space, double *max_err, long *stats)
             for (int i = 0; i < n; i++) { const unsigned w = vfold[base + i]; sA[w & 0xffffu] += sA[w >> 16]; }
             base += n;
          }
-         for (int c = 0; c < D.nchunk; c++)
+         // aligned pairs of chunks: lane writes the slots 2 lane, 2 lane + 1 (one 16-byte store)
+         for (int k = 0; k <= D.npair; k++)
          {
-            const int *d = chunks + 4 * c;
-            for (int lane = 0; lane < 32; lane++)
-            {
-               if (d[3] == 64) // aligned pair of chunks: lane writes the slots 2 lane, 2 lane + 1 (one 16-byte store)
-               {
-                  if (lane == 0) { npaired += 64; }
-                  v[d[0] + 2 * lane] = sA[vsrc[c * 32 + 2 * lane]];
-                  v[d[0] + 2 * lane + 1] = sA[vsrc[c * 32 + 2 * lane + 1]];
-               }
-               else if (lane < d[3]) { v[((lane < d[2]) ? d[0] : d[1]) + lane] = sA[vsrc[c * 32 + lane]]; }
-            }
+            const int g0 = plist[2 * k], s0 = plist[2 * k + 1];
+            if (g0 < 0) { continue; }
+            npaired += 64;
+            for (int q = 0; q < 64; q++) { v[g0 + q] = sA[vsrc[s0 + q]]; }
+         }
+         for (int k = 0; k <= D.ngen; k++)
+         {
+            const int *d = glist + 4 * k;
+            const int n = d[3] & 0xff, s0 = d[3] >> 8;
+            for (int lane = 0; lane < n; lane++) { v[((lane < d[2]) ? d[0] : d[1]) + lane] = sA[vsrc[s0 + lane]]; }
          }
          for (int k = 0; k < D.nirr * 32; k++) { if (over[k] >= 0) { v[over[k]] = sA[isrc[k]]; } }
          for (int s = D.nexc; s < D.nslots; s++) { vstage[D.stage_off + (s - D.nexc)] = sA[vsrc[s]]; }

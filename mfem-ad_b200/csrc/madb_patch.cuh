@@ -71,17 +71,23 @@ template <int BAR, int NT> __device__ __forceinline__ void patch_bar(const int i
 /// base: shared memory of the patch: element vectors at 0, element matrices at o_sa, y maps at o_yb, matrix maps at o_vb.
 /// Every loop is written in batches of U independent iterations (all index loads, then all value loads, then
 /// all stores): the chains are shared-memory-latency bound, and only a few warps work on a patch.
-template <int BAR, int NT, int U>
-__device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_vb, const PatchDesc &D,
-                                            const bool wy, const bool wv, const int tid, double *__restrict__ y,
-                                            double *__restrict__ vals, double *__restrict__ ystage, double *__restrict__ vstage, const int bar_id = BAR)
+/// o_yb / o_vb: gather parts of the maps, o_yfold / o_vfold: fold lists (byte offsets into base).  after_fold() runs in
+/// every thread right after the barrier that ends the fold phase: the fold lists are dead from there on (k_patch_ws
+/// fetches those of the next patch and waits for the gather part of this one there).
+struct NoAfterFold
+{
+   __device__ __forceinline__ void operator()() const {}
+};
+template <int BAR, int NT, int U, class AfterFold = NoAfterFold>
+__device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa, const int o_yb, const int o_yfold, const int o_vb,
+                                            const int o_vfold, const PatchDesc &D, const bool wy, const bool wv, const int tid,
+                                            double *__restrict__ y, double *__restrict__ vals, double *__restrict__ ystage,
+                                            double *__restrict__ vstage, const int bar_id = BAR, AfterFold &&after_fold = AfterFold())
 {
    static_assert(NT % 32 == 0, "whole warps");
 #define MADB_SR(i) (*(double *)(base + 8 * (i)))
 #define MADB_SA(i) (*(double *)(base + o_sa + 8 * (i)))
    const int nrows = D.nrows, nrow_int = D.nrow_int, nexc = D.nexc, nslots = D.nslots;
-   const int o_yfold = o_yb + patch_al16(2 * nrows);
-   const int o_vfold = o_vb + patch_al16(2 * D.nvsrc);
    // ---- fold: add the further sources of every row / slot onto its first source, phase by phase -------
    // (every location is the destination or a source of exactly one entry chain)
    {
@@ -121,11 +127,12 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
       // entry i of every phase has the same destination (pack_sources) and is handled by the same thread: one barrier
       // after the last phase is enough
       patch_bar<BAR, NT>(bar_id);
+      after_fold();
    }
    // ---- rows of the residual -----------------------------------------------------------
    if (wy)
    {
-      const int o_ylist = o_yfold + patch_al16(4 * D.nyfold);
+      const int o_ylist = o_yb + patch_al16(2 * nrows);
       for (int lr = tid; lr < nrows; lr += NT)
       {
          const double v = MADB_SR(*(const unsigned short *)(base + o_yb + 2 * lr));
@@ -137,63 +144,76 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
    if (wv)
    {
       constexpr int NW = NT / 32;
-      const int o_chunk = o_vfold + patch_al16(4 * D.nvfold);
-      const int o_isrc = o_chunk + patch_al16(16 * (D.nchunk + 2));
+      const int o_plist = o_vb + patch_al16(2 * D.nvsrc);
+      const int o_glist = o_plist + patch_al16(8 * (D.npair + 1));
+      const int o_isrc = o_glist + patch_al16(16 * (D.ngen + 1));
       const int o_over = o_isrc + patch_al16(64 * D.nirr);
       const unsigned short *vsrc = (const unsigned short *)(base + o_vb);
       const int lane = tid & 31, warp = tid >> 5;
-      // directly written slots: CSR positions from the chunk descriptors, one (even, odd) pair of chunks per warp and
-      // step.  {g0, 0, 0, 64}: the pair covers 64 consecutive positions from an even one: lane l gathers the slots
-      // 2l, 2l+1 and writes them with one 16-byte store; otherwise {g0, g1 - split, split, n} per chunk (consecutive
-      // lanes -> consecutive positions).
+      // directly written slots, two work lists (layout: madb_host.hpp).  Aligned pairs of chunks first: 64 consecutive
+      // CSR positions from an even one, lane l gathers the slots 2l, 2l+1 (one 32-bit load of the two source indices)
+      // and writes them with one 16-byte store.  No selects, no branches: about 12 instructions per 64 entries.
       {
-         constexpr int UP = U / 2; // pairs per batch
-         static_assert(U >= 2 && U % 2 == 0, "chunk pairs");
+         constexpr int UP = (U >= 4) ? 4 : 2; // pairs per batch
          const bool al16 = (reinterpret_cast<size_t>(vals) & 15) == 0;
-         const int4 *cp = (const int4 *)(base + o_chunk);
-         const int nchunk = D.nchunk; // even; one all-zero pair is appended to the tables (index nchunk)
-         for (int c0 = 2 * warp; c0 < nchunk; c0 += 2 * NW * UP)
+         const int2 *pl = (const int2 *)(base + o_plist);
+         const int npair = D.npair;
+         for (int k0 = warp; k0 < npair; k0 += NW * UP)
          {
-            int gA[UP], gB[UP];
-            unsigned iA[UP], iB[UP];
+            int g[UP];
+            unsigned ix[UP];
             double vA[UP], vB[UP];
 #pragma unroll
             for (int u = 0; u < UP; u++)
             {
-               const int c = c0 + 2 * u * NW, ce = (c < nchunk) ? c : nchunk; // past the table: the zero pair (no branch)
-               const int4 dA = cp[ce], dB = cp[ce + 1];
-               const unsigned short *vp = vsrc + 32 * ce;
-               const bool pair = dA.w == 64;
-               iA[u] = vp[pair ? 2 * lane : lane];
-               iB[u] = vp[pair ? 2 * lane + 1 : 32 + lane];
-               const int ga = (lane < dA.w) ? ((lane < dA.z) ? dA.x : dA.y) + lane : -1;
-               gA[u] = pair ? dA.x + 2 * lane : ga;
-               gB[u] = pair ? -2 : ((lane < dB.w) ? ((lane < dB.z) ? dB.x : dB.y) + lane : -1);
+               const int k = k0 + u * NW;
+               const int2 e = pl[(k < npair) ? k : npair]; // past the list: the entry that stores nothing
+               g[u] = e.x;
+               ix[u] = *(const unsigned *)(vsrc + e.y + 2 * lane);
             }
 #pragma unroll
             for (int u = 0; u < UP; u++)
             {
-               vA[u] = MADB_SA(iA[u]);
-               vB[u] = MADB_SA(iB[u]);
+               vA[u] = MADB_SA(ix[u] & 0xffffu);
+               vB[u] = MADB_SA(ix[u] >> 16);
             }
 #pragma unroll
             for (int u = 0; u < UP; u++)
             {
-               if (gB[u] == -2)
+               if (g[u] >= 0)
                {
-                  if (al16) { *reinterpret_cast<double2 *>(vals + gA[u]) = make_double2(vA[u], vB[u]); }
+                  double *dst = vals + g[u] + 2 * lane;
+                  if (al16) { *reinterpret_cast<double2 *>(dst) = make_double2(vA[u], vB[u]); }
                   else
                   {
-                     vals[gA[u]] = vA[u];
-                     vals[gA[u] + 1] = vB[u];
+                     dst[0] = vA[u];
+                     dst[1] = vB[u];
                   }
                }
-               else
-               {
-                  if (gA[u] >= 0) { vals[gA[u]] = vA[u]; }
-                  if (gB[u] >= 0) { vals[gB[u]] = vB[u]; }
-               }
             }
+         }
+      }
+      // general chunks {g0, g1 - split, split, n | first slot << 8}: consecutive lanes -> consecutive positions, one break
+      {
+         const int4 *gl = (const int4 *)(base + o_glist);
+         const int ngen = D.ngen;
+         for (int k0 = warp; k0 < ngen; k0 += NW * U)
+         {
+            int gp[U];
+            unsigned ix[U];
+            double v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++)
+            {
+               const int k = k0 + u * NW;
+               const int4 d = gl[(k < ngen) ? k : ngen];
+               ix[u] = vsrc[(d.w >> 8) + lane];
+               gp[u] = (lane < (d.w & 0xff)) ? ((lane < d.z) ? d.x : d.y) + lane : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) { v[u] = MADB_SA(ix[u]); }
+#pragma unroll
+            for (int u = 0; u < U; u++) { if (gp[u] >= 0) { vals[gp[u]] = v[u]; } }
          }
       }
          // irregular chunks: explicit positions (-1: none)
@@ -343,8 +363,53 @@ __global__ void __launch_bounds__(patch_pe_of<Func, Cfg>() * element_parts<Cfg, 
    __syncthreads();
    mbar_wait(&mbar, 0);
    constexpr int NW = NT / 32, U = (32 / NW < 8) ? 32 / NW : 8;
-   patch_drain<0, NT, U>(smraw, o_sa, o_yb, o_vb, D, wy, wv, tid, a.y, a.vals, P.ystage, P.vstage);
+   patch_drain<0, NT, U>(smraw, o_sa, o_yb, o_yb + patch_yg_bytes(D), o_vb, o_vb + patch_vg_bytes(D), D, wy, wv, tid, a.y, a.vals,
+                         P.ystage, P.vstage);
 }
+
+// loads of the prefetch: volatile asm keeps them where they are written (between two blocks of the matrix phase)
+__device__ __forceinline__ int ldg_nc_s32(const int *p)
+{
+   int v;
+   asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+   return v;
+}
+__device__ __forceinline__ double ldg_nc_f64(const double *p)
+{
+   double v;
+   asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+   return v;
+}
+__device__ __forceinline__ void ldg_nc_f64x2(const double *p, double &v0, double &v1)
+{
+   asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "l"(p));
+}
+/// Basic-block boundary ptxas cannot remove (the stride is never negative, which it cannot know).  ptxas schedules
+/// inside basic blocks and sinks loads whose results are needed late to the end of theirs: without the boundaries the
+/// map loads and the value loads of the prefetch end up next to each other at the end of the matrix phase.
+__device__ __forceinline__ void bb_break(const int never_negative)
+{
+   for (int k = never_negative; k < 0; k++) { __nanosleep(1); }
+}
+#ifndef MADB_WS_JOINT
+#define MADB_WS_JOINT 0 // 1: both writer warpgroups drain one buffer at a time; 0: writer warpgroup w serves compute warpgroup w
+                        // (measured on config 2, profiles/r02_k_patch_ws.md: 0.309 ms joint, 0.269 ms separate)
+#endif
+#ifndef MADB_WS_PREFETCH
+#define MADB_WS_PREFETCH 0 // register prefetch of the next element's inputs during the matrix phase: the compute warpgroups alone
+                           // gain 10 % (0.223 -> 0.200 ms), the full kernel loses (0.269 -> 0.321 ms): ptxas spills the
+                           // prefetched values right after the loads, which stalls the warp until they land
+#endif
+#ifndef MADB_WS_PREFETCH_AT
+#define MADB_WS_PREFETCH_AT 2 // block of the matrix phase (0..5 for order 2) before which the values are requested
+#endif
+struct Sf2dDummyCfg
+{
+   template <int> struct field
+   {
+      static constexpr int ND1D = 1;
+   };
+};
 
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
 {
@@ -380,19 +445,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
    constexpr int WG_C0 = WS_WRITER_WG; // first compute warpgroup
    static_assert(WS_WRITER_WG == 2, "writer warpgroup w serves compute warpgroup w");
    extern __shared__ __align__(16) unsigned char smraw[];
-   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blob[2];
-   __shared__ PatchDesc Dd[2];
+   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blobF[2], bar_blobG[2];
+   __shared__ __align__(16) PatchDesc Dd[2][2]; // [warpgroup][patch parity]
    // warpgroup index, made warp-uniform for the compiler (uniform registers instead of spilled vector registers)
    const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), tid = threadIdx.x & (PE - 1);
    const bool wy = a.write_y != 0;
-   const int wg_bytes = SR_BYTES + SA_BYTES + P.max_yblob + P.max_vblob;
+   const int wg_bytes = SR_BYTES + SA_BYTES + P.max_yg + P.max_yf + P.max_vg + P.max_vf;
    if (threadIdx.x == 0)
    {
       for (int k = 0; k < 2; k++)
       {
          mbar_init(&bar_full[k], PE);
-         mbar_init(&bar_empty[k], PE);
-         mbar_init(&bar_blob[k], 1);
+         mbar_init(&bar_empty[k], MADB_WS_JOINT ? 2 * PE : PE);
+         mbar_init(&bar_blobF[k], 1);
+         mbar_init(&bar_blobG[k], 1);
       }
    }
    __syncthreads();
@@ -403,6 +469,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
       asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WS_REG_COMPUTE));
       const int w = wg - WG_C0;
       unsigned char *base = smraw + (size_t)w * wg_bytes;
+      Sf2dIn<typename std::conditional<use_sf2d<Func, Cfg, MODE>(), Cfg, Sf2dDummyCfg>::type, false> sf_in;
       for (int it = 0;; it++)
       {
          const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
@@ -413,6 +480,56 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          const unsigned par = (it & 1) ^ 1; // parity of "the writer has drained the previous patch of this buffer"
          if constexpr (use_sf2d<Func, Cfg, MODE>())
          {
+#if MADB_WS_PREFETCH
+            // The inputs of this element were loaded during the matrix phase of the previous patch (registers): the two
+            // dependent loads (element maps -> dof values / vertex coordinates) are off the critical path.  The maps of the
+            // next element are read at the end of the quadrature loop, the values between two blocks of the matrix phase.
+            constexpr int ND1 = Cfg::template field<0>::ND1D;
+            static_assert(NVD == ND1 * ND1, "scalar field");
+            const int tc = valid ? t : a.end - 1;
+            if (it == 0) { sf2d_gather<Func, Cfg, false>(a, tc, sf_in); }
+            const Sf2dIn<Cfg, false> in = sf_in;
+            const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+            const int tn0 = pn * PE + tid, tn = (pn < P.npatch && tn0 < a.end) ? tn0 : tc; // past the end: reload this one
+            int nidx[4 + NVD];
+            auto load_maps = [&]()
+            {
+#pragma unroll
+               for (int k = 0; k < 4; k++) { nidx[k] = ldg_nc_s32(a.e2n + (size_t)k * a.stride + tn); }
+#pragma unroll
+               for (int i = 0; i < NVD; i++) { nidx[4 + i] = ldg_nc_s32(a.vmap + (size_t)i * a.stride + tn) & 0x7fffffff; }
+               bb_break(a.stride);
+            };
+            auto load_values = [&](int blk)
+            {
+               if (blk != MADB_WS_PREFETCH_AT) { return; }
+               bb_break(a.stride);
+#pragma unroll
+               for (int k = 0; k < 4; k++) { ldg_nc_f64x2(a.coords + (size_t)nidx[k] * 2, sf_in.X[k][0], sf_in.X[k][1]); }
+#pragma unroll
+               for (int i = 0; i < NVD; i++) { sf_in.u[i / ND1][i % ND1] = ldg_nc_f64(a.x + nidx[4 + i]); }
+               bb_break(a.stride);
+            };
+            if (valid && !(P.diag & 2))
+            {
+               element_compute_sf2d_core<Func, Cfg, MODE>(
+                  a, in, r, [&](int k, double v) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = v; },
+                  [&]()
+                  {
+                     mbar_wait(&bar_empty[w], par);
+#pragma unroll
+                     for (int i = 0; i < NVD; i++) { *(double *)(base + 8 * (i * LD + tid)) = r[i]; }
+                     load_maps();
+                  },
+                  load_values);
+            }
+            else
+            {
+               mbar_wait(&bar_empty[w], par);
+               load_maps();
+               load_values(MADB_WS_PREFETCH_AT);
+            }
+#else
             if (valid)
             {
                element_compute_sf2d<Func, Cfg, MODE>(
@@ -429,6 +546,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
             // threads past the end of the last patch take part in the hand-off like the others: without this wait their
             // arrival on `full` would be counted in the previous, still open phase and the writers could start early
             else { mbar_wait(&bar_empty[w], par); }
+#endif
          }
          else
          {
@@ -451,38 +569,95 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
       // ================= writer warpgroup(s) =================
       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WS_REG_WRITER));
       // writer warpgroup ww drains the patches of compute warpgroup ww (own named barrier): the two write-outs run
-      // concurrently and the compute warpgroups are not coupled through a common drain order
-      const int ww = wg, wtid = tid; // 0..PE-1
-      auto prefetch = [&](int w, int p)
+      // concurrently and the compute warpgroups are not coupled through a common drain order.
+      // Maps of a patch = descriptor (80 bytes) + fold lists F + gather part G (madb_host.hpp).  Measured (MADB_DIAG=3:
+      // hand-offs and map traffic only): fetching them after the drain, descriptor then maps (two dependent DRAM round
+      // trips), costs 3.2 us per patch on the writers' serial path, a third of their cycle.  Hence: the descriptor of the
+      // next patch is requested at the top of a drain (cp.async, lands in the other slot of Dd), its fold lists as soon
+      // as the fold of the current patch is done (their region is dead then), its gather part at the end of the drain;
+      // the writers need the gather part only after their fold phase, which covers most of its latency.
+      // MADB_WS_JOINT: both writer warpgroups (8 warps) drain one buffer at a time, alternating between the two compute
+      // warpgroups (a drain is bound by the latency of its dependent shared-memory accesses per warp, so twice the warps
+      // halve it and the chain "matrix phase -> drain -> matrix phase" of a buffer gets shorter); the maps of a buffer's
+      // next patch land while the other buffer is drained.
+      constexpr bool JOINT = MADB_WS_JOINT != 0;
+      constexpr int WNT = JOINT ? 2 * PE : PE;
+      const int wtid = JOINT ? (int)threadIdx.x : tid; // the writer warpgroups are warpgroups 0 and 1
+      const int bar_id = JOINT ? 1 : 1 + wg;
+      const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_yf = o_yb + P.max_yg, o_vb = o_yf + P.max_yf, o_vf = o_vb + P.max_vg;
+      auto fetch_F = [&](const int w, const PatchDesc &Dn)
       {
-         // one thread: descriptor to shared memory, then the bulk copies of the patch's maps
-         const PatchDesc *src = P.desc + p;
-         for (int k = 0; k < (int)(sizeof(PatchDesc) / sizeof(int)); k++) { ((int *)&Dd[w])[k] = __ldg((const int *)src + k); }
-         unsigned char *mb = smraw + (size_t)w * wg_bytes + SR_BYTES + SA_BYTES;
-         const int yb = wy ? Dd[w].yblob_bytes : 0, vb = Dd[w].vblob_bytes;
+         unsigned char *base = smraw + (size_t)w * wg_bytes;
+         const int yf = wy ? patch_al16(4 * Dn.nyfold) : 0, vf = patch_al16(4 * Dn.nvfold);
          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-         mbar_expect_tx(&bar_blob[w], (unsigned)(yb + vb));
-         if (yb) { bulk_g2s(mb, P.yblob + (size_t)Dd[w].yblob_off * 16, yb, &bar_blob[w]); }
-         if (vb) { bulk_g2s(mb + P.max_yblob, P.vblob + (size_t)Dd[w].vblob_off * 16, vb, &bar_blob[w]); }
+         mbar_expect_tx(&bar_blobF[w], (unsigned)(yf + vf));
+         if (yf) { bulk_g2s(base + o_yf, P.yblob + (size_t)Dn.yblob_off * 16 + patch_yg_bytes(Dn), yf, &bar_blobF[w]); }
+         if (vf) { bulk_g2s(base + o_vf, P.vblob + (size_t)Dn.vblob_off * 16 + patch_vg_bytes(Dn), vf, &bar_blobF[w]); }
       };
+      auto fetch_G = [&](const int w, const PatchDesc &Dn)
       {
-         const int p0 = (int)blockIdx.x * 2 + ww;
-         if (wtid == 0 && p0 < P.npatch) { prefetch(ww, p0); }
+         unsigned char *base = smraw + (size_t)w * wg_bytes;
+         const int yg = wy ? patch_yg_bytes(Dn) : 0, vg = patch_vg_bytes(Dn);
+         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+         mbar_expect_tx(&bar_blobG[w], (unsigned)(yg + vg));
+         if (yg) { bulk_g2s(base + o_yb, P.yblob + (size_t)Dn.yblob_off * 16, yg, &bar_blobG[w]); }
+         if (vg) { bulk_g2s(base + o_vb, P.vblob + (size_t)Dn.vblob_off * 16, vg, &bar_blobG[w]); }
+      };
+      if (wtid == 0)
+      {
+         for (int w = JOINT ? 0 : wg; w < (JOINT ? 2 : wg + 1); w++)
+         {
+            const int p0 = (int)blockIdx.x * 2 + w;
+            if (p0 >= P.npatch) { break; }
+            for (int k = 0; k < (int)(sizeof(PatchDesc) / sizeof(int)); k++) { ((int *)&Dd[w][0])[k] = __ldg((const int *)(P.desc + p0) + k); }
+            fetch_F(w, Dd[w][0]);
+            fetch_G(w, Dd[w][0]);
+         }
       }
-      const int o_sa = SR_BYTES, o_yb = SR_BYTES + SA_BYTES, o_vb = o_yb + P.max_yblob;
-      unsigned char *base = smraw + (size_t)ww * wg_bytes;
-      for (int it = 0;; it++)
+      patch_bar<1, WNT>(bar_id); // the first descriptors are visible to the writers
+      for (int s = 0;; s++)
       {
-         const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + ww;
-         if (p >= P.npatch) { break; }
-         mbar_wait(&bar_blob[ww], it & 1); // maps and descriptor (Dd[ww], stable until the next prefetch) have landed
-         mbar_wait(&bar_full[ww], it & 1); // the compute warpgroup has staged the patch
-         patch_drain<1, PE, 4>(base, o_sa, o_yb, o_vb, Dd[ww], wy, true, wtid, a.y, a.vals, P.ystage, P.vstage, 1 + ww);
-         mbar_arrive(&bar_empty[ww]);
-         // all threads of this warpgroup are done with the maps of the buffer: fetch those of its next patch
-         patch_bar<1, PE>(1 + ww);
-         const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + ww;
-         if (wtid == 0 && pn < P.npatch) { prefetch(ww, pn); }
+         const int w = JOINT ? (s & 1) : wg, it = JOINT ? (s >> 1) : s;
+         const int p = (it * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+         if (p >= P.npatch) { break; } // p grows with s
+         const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+         const bool more = pn < P.npatch;
+         unsigned char *base = smraw + (size_t)w * wg_bytes;
+         const PatchDesc &D = Dd[w][it & 1];
+         PatchDesc &Dn = Dd[w][(it & 1) ^ 1];
+         if (wtid == 0 && more)
+         {
+            static_assert(sizeof(PatchDesc) % 16 == 0, "descriptor copied in 16-byte pieces");
+#pragma unroll
+            for (int k = 0; k < (int)sizeof(PatchDesc) / 16; k++)
+            {
+               asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32((unsigned char *)&Dn + 16 * k)),
+                            "l"((const unsigned char *)(P.desc + pn) + 16 * k)
+                            : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+         }
+         mbar_wait(&bar_blobF[w], it & 1); // fold lists of this patch
+         mbar_wait(&bar_full[w], it & 1);  // the compute warpgroup has staged the patch
+         auto after_fold = [&]()
+         {
+            if (wtid == 0 && more)
+            {
+               asm volatile("cp.async.wait_group 0;" ::: "memory");
+               fetch_F(w, Dn);
+            }
+            mbar_wait(&bar_blobG[w], it & 1); // gather part of this patch
+         };
+         if (!(P.diag & 1))
+         {
+            patch_drain<1, WNT, 4>(base, o_sa, o_yb, o_yf, o_vb, o_vf, D, wy, true, wtid, a.y, a.vals, P.ystage, P.vstage, bar_id, after_fold);
+         }
+         else { after_fold(); }
+         mbar_arrive(&bar_empty[w]);
+         // all writers are done with the gather part (and thread 0's copy of the next descriptor is visible to them
+         // after this barrier): fetch the gather part of the buffer's next patch
+         patch_bar<1, WNT>(bar_id);
+         if (wtid == 0 && more) { fetch_G(w, Dn); }
       }
    }
 }
@@ -573,7 +748,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       if (!done && wv && use_ws && P.vblob)
       {
          auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
-         const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yblob + P.max_vblob) + 16;
+         const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yg + P.max_yf + P.max_vg + P.max_vf) + 16;
          if (nsm == 0) { cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
          if (ws_bytes <= 226 * 1024)
          {
@@ -584,7 +759,10 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
                ws_smem_set = ws_bytes;
             }
             const int grid = std::min(nsm, (P.npatch + 1) / 2);
-            kws<<<grid, WS_THREADS, ws_bytes, L.stream>>>(a, P);
+            static const int diag = getenv("MADB_DIAG") ? atoi(getenv("MADB_DIAG")) : 0;
+            PatchDev Pd = P;
+            Pd.diag = diag;
+            kws<<<grid, WS_THREADS, ws_bytes, L.stream>>>(a, Pd);
             done = true;
          }
       }

@@ -61,6 +61,9 @@ template <class Func, class Cfg, bool UNROLLQ> int launch_impl(const LaunchCtx &
 {
    using Args = AsmArgs<Func, Cfg>;
    Args &a = fill_args<Func, Cfg>(L);
+   // the even / odd contraction of the sum-factorised 2-D path needs mirror-symmetric 1-D nodes and points (every
+   // tensor basis and Gauss rule of MFEM is): refuse anything else loudly instead of assembling wrong values
+   if (!sf2d_mirror_ok(a.sf)) { return MADB_RC_MIRROR; }
    if constexpr (patch_eligible(Cfg::NVD))
    {
       if (L.patch && mode != MODE_ENERGY && mode != MODE_COEF)

@@ -321,7 +321,9 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
       PatchDev &P = I.pdev;
       P.npatch = (int)I.pdesc.size();
       P.max_yblob = I.max_yblob;
-      P.max_vblob = 0;
+      P.max_yg = I.max_yg;
+      P.max_yf = I.max_yf;
+      P.max_vblob = P.max_vg = P.max_vf = 0;
       P.desc = I.d_pdesc;
       P.yblob = I.d_yblob;
       P.ystage = I.d_ystage;
@@ -466,6 +468,8 @@ static int ensure_pattern_device(Integrator &I)
       CUDA_OK(cudaMemcpy(I.d_pdesc, I.pdesc.data(), I.pdesc.size() * sizeof(PatchDesc), cudaMemcpyHostToDevice));
       PatchDev &P = I.pdev;
       P.max_vblob = I.max_vblob;
+      P.max_vg = I.max_vg;
+      P.max_vf = I.max_vf;
       P.vblob = I.d_vblob;
       P.vstage = I.d_vstage;
       P.nv_ifc = (int)(H.dst.size() + H.dst4.size());
@@ -580,6 +584,11 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
       L.coef_variant = coef_variant;
    }
    const int rc = I.ops.launch(L, mode);
+   if (rc == MADB_RC_MIRROR)
+   {
+      set_error("sum-factorised 2-D path: the 1-D basis / quadrature tables are not mirror-symmetric about 1/2");
+      return 2;
+   }
    if (rc != 0) { set_error(std::string("kernel launch failed: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
 
    if (mode == MODE_ENERGY)
