@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- AD residual+Jacobian assembly throughput (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n NX]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--n NX] [--config 2|5] [--check]
 
 A step = one pass of the hot path over the whole mesh: ONE residual + ONE
 Jacobian assembly at the same state (one Newton iteration's worth).
@@ -11,6 +11,14 @@ MinimalSurfaceEnergy (ex2.cpp:12-24, eps=0.5), state u = sin(pi x)sin(pi y) +
 0.1 U(-1,1) seed 1234.  Under torchrun (N>1) every rank assembles its own
 1000x1000 block of a (Px*1000)x(Py*1000) mesh (weak scaling) and the shared
 interface dofs of the residual are summed across ranks over NCCL.
+
+--config 5 makes BASELINE.json's config 5 the workload of the line: the ex4 LVPP block system (H1 order 3 x L2
+order 1, FermiDirac entropy, 5x5 points; ex4.cpp:93-104) on 1024x1024 elements PER GPU, overlapping element
+partition (one ghost layer), step = P x over NCCL (madb_exchange_*) + fused residual + Jacobian assembly, which
+gives the owned rows of P^T A P complete (ex4.cpp:136,169,190).  The default line (config 2) carries the device
+timings of configs 3, 4 and 5 in "other_configs" (N = 1) and the weak-scaled config 5 in "config5" (every N), so
+that those numbers are driver-run too.  --check asserts parity against the CPU oracle (small meshes, same code
+path; the multi-GPU cases of tests/mgpu_check.py when N > 1) before anything is timed.
 
 The JSON line follows the driver contract; see DESIGN.md "Measurement".
 """
@@ -185,14 +193,29 @@ def run_gpu(args):
             print("[rank %d] %s %.1fs" % (rank, msg, time.perf_counter() - t_start), file=sys.stderr, flush=True)
     t_start = time.perf_counter()
 
-    nx = args.n
     from mfem_ad_b200 import parallel as PAR
+    ctx = M.Context(local)
+    comm = PAR.Comm(ctx) if world > 1 else None
+    if args.check:
+        check_parity(ctx, comm, rank, world, local)
+        note("parity check passed")
+    if args.config == 5:
+        out = run_config5(args, ctx, comm, dist, rank, world, local, dev)
+        if rank == 0:
+            if args.check:
+                out["check"] = "parity vs CPU oracle asserted before timing"
+            print(json.dumps(out))
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    nx = args.n
     blk = PAR.cartesian_block(rank, world, nx, P)  # this rank's block of the (px*nx) x (py*nx) mesh
     px, py = blk["px"], blk["py"]
     mesh = blk["mesh"]
     space = dict(blk["space"], mode=M.GRAD)
     ndof = space["ndofs"]
-    ctx = M.Context(local)
     gm = M.Mesh(ctx, mesh)
     gs = M.Space(ctx, gm, space)
     fn = M.Functional(ctx, "minsurf", params=[EPS])
@@ -210,14 +233,18 @@ def run_gpu(args):
     yp = torch.empty(ndof, dtype=torch.float64).pin_memory()
     vp = torch.empty(nnz, dtype=torch.float64).pin_memory()
 
-    # shared-dof exchange P^T y: interface dofs summed on their owner rank, fixed order (deterministic)
+    # shared-dof exchange P^T y behind the C ABI (madb_exchange_*: pack kernel, ncclSend/ncclRecv group on the
+    # communication stream, unpack-add in ascending peer rank: deterministic), asynchronous on the context stream
     note("integrator + pattern ready")
-    ex = PAR.SharedDofExchange(blk["l2g"], blk["candidates"], dev, ctx=ctx) if world > 1 else None
+    ex = None
+    if world > 1:
+        owner = PAR.lowest_rank_owner(blk["l2g"], blk["candidates"], ndof, rank, world)
+        ex = PAR.HaloExchange(*PAR.halo_lists(blk["l2g"], owner, rank, world), ctx=ctx, comm=comm)
     note("exchange lists ready")
 
     def exchange():
         if ex is not None:
-            ex.reduce_to_owner(y)
+            ex.reverse(y)
 
     def step_device():
         gi.assemble(x, y, vals)
@@ -235,7 +262,7 @@ def run_gpu(args):
     stats = gi.patch_stats()
     patch = stats["patches"] > 0
     # patch path: k_patch_ws + one interface reduction launch (residual rows and CSR entries); colour path: one launch per colour
-    launches_per_step = 2 if patch else gi.ncolors
+    launches_per_step = (2 if patch else gi.ncolors) + (2 if world > 1 else 0)  # + pack / unpack of the exchange
     kernel_launches = 1 if patch else gi.ncolors
     gi.set_timing(True)
     with torch.cuda.stream(stream):
@@ -324,14 +351,348 @@ def run_gpu(args):
             forms = cpu_forms(nx, nx, cores)
             cpu_step(forms)
             t = min(cpu_step(forms) for _ in range(3))
+            # one thread (the reference is single-threaded per rank): bounded sample, a 250x250 corner
+            m1 = min(250, nx)
+            f1 = cpu_forms(m1, m1, 1)
+            t1 = min(cpu_step(f1) for _ in range(2))
+            out["cpu_baseline_1thread"] = {"value": (m1 * P + 1) ** 2 / t1, "unit": "DOF/s", "cores": 1, "kind": "port",
+                                           "ms_per_step": t1 * 1e3,
+                                           "sample": "%dx%d Q%d mesh, one oracle thread, residual+Jacobian, best of 2" % (m1, m1, P)}
             out["cpu_baseline"] = {"value": ndof / t, "unit": "DOF/s", "cores": len(forms), "kind": "port",
                                    "ms_per_step": t * 1e3,
                                    "sample": "full %dx%d Q%d mesh split in %d strips, one oracle thread per strip "
                                              "(mimics mpirun -np N), residual+Jacobian, best of 3" % (nx, nx, P, len(forms))}
+        if args.check:
+            out["check"] = "parity vs CPU oracle asserted before timing"
+    # the other configurations, driver-run: configs 3 - 5 device timings at N = 1, weak-scaled config 5 at every N
+    extra5 = None
+    if not args.no_extra:
+        del gi, vals, vp, y, yp
+        torch.cuda.empty_cache()
+        try:
+            extra5 = c5_summary(args, ctx, comm, dist, rank, world, local, dev)
+        except Exception as ex5:  # never lose the main line
+            extra5 = {"error": repr(ex5)[:300]}
+    if rank == 0:
+        if extra5 is not None:
+            out["config5"] = extra5
+        if world == 1 and not args.no_extra:
+            try:
+                out["other_configs"] = [r for r in other_configs() if r.get("config") in ("3", "4") or "error" in r]
+            except Exception as exo:
+                out["other_configs"] = [{"error": repr(exo)[:300]}]
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------
+# config 5: ex4 LVPP block system, weak-scaled, overlapping element partition + P x over NCCL
+# ----------------------------------------------------------------------------------
+C5_ORDER = 2  # ex4.cpp -o 2: H1 order 3 x L2 order 1, rule order 3*2+3 = 9 -> 5x5 points
+C5_ALPHA = 0.1
+
+
+def c5_spec():
+    import spec as S
+    return S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), C5_ALPHA)
+
+
+def c5_cpu_forms(m, nthreads):
+    """The oracle on an m x m sample of the config-5 mesh, one strip per thread."""
+    from mfem_ad_b200 import meshgen as G
+    from oracle import oracle as O
+    forms = []
+    rows = [m // nthreads + (1 if r < m % nthreads else 0) for r in range(nthreads)]
+    for r in range(nthreads):
+        if rows[r] == 0:
+            continue
+        mesh = G.cartesian_mesh((m, rows[r]), lengths=(1.0, rows[r] / m))
+        h1 = G.h1_space(mesh, C5_ORDER + 1, mode=O.VALUE | O.GRAD)
+        l2 = G.l2_space(mesh, C5_ORDER - 1, mode=O.VALUE)
+        pk = np.zeros(l2["ndofs"])
+        f = O.OracleForm(mesh, [h1, l2], c5_spec().oracle(), quad_order=3 * C5_ORDER + 3,
+                         params=[dict(type=O.PRM_GF, size=1, data=pk, space=l2)])
+        f.pattern()
+        nd = h1["ndofs"] + l2["ndofs"]
+        x = 0.1 * np.random.default_rng(r).uniform(-1, 1, nd)
+        forms.append((f, x, nd))
+    return forms
+
+
+def c5_cpu_sample(m, cores):
+    forms = c5_cpu_forms(m, cores)
+    cpu_step(forms)
+    t = min(cpu_step(forms) for _ in range(2))
+    nd = (m * (C5_ORDER + 1) + 1) ** 2 + m * m * C5_ORDER ** 2
+    return nd / t, t, len(forms)
+
+
+def c5_setup(ctx, comm, rank, world, local, n):
+    """This rank's block (+ ghost layer), spaces, integrator, exchanges and device vectors."""
+    import torch
+    import mfem_ad_b200 as M
+    from mfem_ad_b200 import parallel as PAR
+    dev = torch.device("cuda", local)
+    blk = PAR.cartesian_block_ghost(rank, world, n, C5_ORDER + 1, C5_ORDER - 1)
+    h1 = dict(blk["h1"], mode=M.VALUE | M.GRAD)
+    l2 = dict(blk["l2"], mode=M.VALUE)
+    nh, nl = h1["ndofs"], l2["ndofs"]
+    gm = M.Mesh(ctx, blk["mesh"])
+    gh, gl = M.Space(ctx, gm, h1), M.Space(ctx, gm, l2)
+    fn = c5_spec().madb(ctx)
+    gi = M.Integrator(ctx, [(gh, M.VALUE | M.GRAD), (gl, M.VALUE), (gl, M.VALUE, M.ROLE_PARAM)], fn,
+                      quad_order=3 * C5_ORDER + 3)
+    nh_glob = (blk["px"] * n * (C5_ORDER + 1) + 1) * (blk["py"] * n * (C5_ORDER + 1) + 1)
+    l2g = np.concatenate([blk["l2g_h1"], nh_glob + blk["l2g_l2"]])
+    owner = np.concatenate([blk["owner_h1"], blk["owner_l2"]])
+    ex = exl = None
+    if world > 1:
+        ex = PAR.HaloExchange(*PAR.halo_lists(l2g, owner, rank, world), ctx=ctx, comm=comm)
+        exl = PAR.HaloExchange(*PAR.halo_lists(blk["l2g_l2"], blk["owner_l2"], rank, world), ctx=ctx, comm=comm)
+    mine = owner == rank
+    # state: a smooth function of the GLOBAL dof id (every rank agrees), copies start with garbage and are filled by P
+    xg = 0.1 * np.sin(0.37 * (l2g % 9973)) + 0.05 * np.cos(0.011 * (l2g % 7919))
+    x = torch.from_numpy(np.where(mine, xg, -77.0)).to(dev)
+    pk = torch.from_numpy(np.where(blk["owner_l2"] == rank, 0.01 * np.sin(0.5 * (blk["l2g_l2"] % 1013)), -55.0)).to(dev)
+    if exl is not None:
+        exl.forward(pk)
+    gi.set_param_field(2, pk)
+    nnz = gi.nnz
+    y = torch.empty(nh + nl, dtype=torch.float64, device=dev)
+    vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    ne_loc = int(np.asarray(blk["mesh"]["e2n"]).shape[0])
+    return dict(blk=blk, gi=gi, ex=ex, exl=exl, x=x, y=y, vals=vals, pk=pk, xg=xg, mine=mine, nh=nh, nl=nl, nnz=int(nnz),
+                n_owned=int(mine.sum()), ne_local=int(ne_loc), ne_owned=int(blk["owned_elements"].sum()),
+                keep=(gm, gh, gl, fn))
+
+
+def c5_time(ctx, W, dist, dev, steps, warmup, sampler=None):
+    """Device-timed weak-scaling step: P x (halo of the state) + fused residual + Jacobian assembly."""
+    import torch
+    gi, ex, x, y, vals = W["gi"], W["ex"], W["x"], W["y"], W["vals"]
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if ex is not None:
+            ex.begin(x)
+            ex.end(x)
+        gi.assemble(x, y, vals)
+
+    gi.set_timing(True)
+    with torch.cuda.stream(stream):
+        for _ in range(max(warmup, 3)):
+            step()
+        barrier()
+        if sampler is not None:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        ms_step = e0.elapsed_time(e1) / steps
+        kms = []
+        for _ in range(min(steps, 5)):
+            step()
+            kms.append(gi.last_kernel_ms())
+        ms_kernel = float(np.mean(kms))
+        # the exchange alone
+        ms_ex = 0.0
+        if ex is not None:
+            barrier()
+            e0.record(stream)
+            for _ in range(steps):
+                ex.begin(x)
+                ex.end(x)
+            e1.record(stream)
+            barrier()
+            ms_ex = e0.elapsed_time(e1) / steps
+        if sampler is not None:
+            t_end = time.perf_counter() + 1.0
+            while time.perf_counter() < t_end:
+                gi.assemble(x, y, vals)
+            torch.cuda.synchronize()
+    gi.set_timing(False)
+    return ms_step, ms_kernel, ms_ex
+
+
+def c5_alg_bytes(W, n):
+    """state + residual (8 B per dof each), vertex coordinates, element->dof maps (16 + 4 ints), psi_k, CSR values."""
+    nd = W["nh"] + W["nl"]
+    return 8 * nd * 2 + 16 * (n + 1) ** 2 + 80 * W["ne_local"] + 8 * W["nnz"] + 8 * W["nl"]
+
+
+def c5_workload(n, px, py):
+    return {"workload": "config5: ex4 LVPP block system (H1 order 3 x L2 order 1, FermiDirac entropy, alpha=%g, 5x5 points; "
+                        "ex4.cpp:93-104), %dx%d quads per GPU + one ghost layer, P x over NCCL + fused residual+Jacobian "
+                        "assembly (owned rows of P^T A P complete), CSR sorted columns" % (C5_ALPHA, n, n),
+            "elements_per_gpu": n * n, "order": "H1 p3 x L2 p1", "quadrature": "5x5 Gauss-Legendre", "rank_grid": "%dx%d" % (px, py),
+            "l2": "working set per step (3 GB of CSR values) is > 20x the 126 MB L2; no explicit flush"}
+
+
+def run_config5(args, ctx, comm, dist, rank, world, local, dev):
+    import torch
+    n = args.n5
+    W = c5_setup(ctx, comm, rank, world, local, n)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_step, ms_kernel, ms_ex = c5_time(ctx, W, dist, dev, args.steps, args.warmup, sampler)
+    clocks = sampler.stop() if sampler is not None else None
+    # end to end: host (pinned) state in, residual + CSR values out, P x inside
+    gi = W["gi"]
+    nd = W["nh"] + W["nl"]
+    xp = W["x"].cpu().pin_memory()
+    yp = torch.empty(nd, dtype=torch.float64).pin_memory()
+    vp = torch.empty(W["nnz"], dtype=torch.float64).pin_memory()
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    def step_e2e():
+        if W["ex"] is not None:
+            W["x"].copy_(xp, non_blocking=True)
+            W["ex"].begin(W["x"])
+            W["ex"].end(W["x"])
+            gi.assemble(W["x"], W["y"], W["vals"])
+            yp.copy_(W["y"], non_blocking=True)
+            vp.copy_(W["vals"], non_blocking=True)
+        else:
+            gi.assemble(xp.numpy(), yp.numpy(), vp.numpy())
+    with torch.cuda.stream(stream):
+        step_e2e()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step_e2e()
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / 3
+    owned = torch.tensor([float(W["n_owned"])], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, ms_kernel, ms_ex, e2e_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    ms_step, ms_kernel, ms_ex, e2e_ms = [float(v) for v in t.tolist()]
+    ndof_total = float(owned.item())
+    if rank != 0:
+        return None
+    peak, peak_src = peaks()
+    alg = c5_alg_bytes(W, n)
+    achieved = alg / (ms_kernel * 1e-3) / 1e9
+    blk = W["blk"]
+    out = {
+        "metric": "AD residual+Jacobian assembly DOF/s", "value": ndof_total / (ms_step * 1e-3), "unit": "DOF/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": c5_workload(n, blk["px"], blk["py"]),
+        "qpts_per_s": world * 25 * n * n / (ms_step * 1e-3),
+        "dofs_total": ndof_total, "nnz_per_gpu": W["nnz"], "exchange_ms": ms_ex,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel": "k_patch<PGFunctional<ObstacleEnergy<2>,FermiDiracEntropy>,H1p3xL2p1,RES|JAC>",
+                     "launches_per_step": 1, "avg_launch_ms": ms_kernel, "algorithmic_bytes_per_step": alg,
+                     "note": "64-element patches, 4 threads per element; FP64 / latency bound, see DESIGN.md"},
+        "e2e": {"value": ndof_total / (e2e_ms * 1e-3), "unit": "DOF/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 8 * nd, "d2h_bytes_per_step": 8 * nd + 8 * W["nnz"]},
+        "gpu_launches": (2 + (4 if world > 1 else 0)) * args.steps,
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        m = 160
+        v, tt, nf = c5_cpu_sample(m, cores)
+        out["cpu_baseline"] = {"value": v, "unit": "DOF/s", "cores": nf, "kind": "port", "ms_per_step": tt * 1e3,
+                               "sample": "%dx%d elements of the config-5 block form, %d strips, one oracle thread per strip, "
+                                         "residual+Jacobian, best of 2" % (m, m, nf)}
+    return out
+
+
+def c5_summary(args, ctx, comm, dist, rank, world, local, dev):
+    """Weak-scaled config 5 as a sub-object of the default (config 2) line."""
+    W = c5_setup(ctx, comm, rank, world, local, args.n5)
+    import torch
+    ms_step, ms_kernel, ms_ex = c5_time(ctx, W, dist, dev, max(3, min(args.steps, 5)), 3)
+    owned = torch.tensor([float(W["n_owned"])], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_step, ms_kernel, ms_ex], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(owned, op=dist.ReduceOp.SUM)
+    ms_step, ms_kernel, ms_ex = [float(v) for v in t.tolist()]
+    peak, _ = peaks()
+    alg = c5_alg_bytes(W, args.n5)
+    res = {"workload": c5_workload(args.n5, W["blk"]["px"], W["blk"]["py"])["workload"], "n_gpus": world,
+           "ms_per_step": ms_step, "element_kernel_ms": ms_kernel, "exchange_ms": ms_ex,
+           "value": float(owned.item()) / (ms_step * 1e-3), "unit": "DOF/s", "scaling": "weak",
+           "hbm_frac_kernel": alg / (ms_kernel * 1e-3) / 1e9 / peak, "nnz_per_gpu": W["nnz"]}
+    del W
+    torch.cuda.empty_cache()
+    return res
+
+
+def other_configs(scale=1):
+    """Device timings of configs 3 - 5 (tools/bench_configs.py) collected for the default line (N = 1)."""
+    import io
+    import contextlib
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "tools", "bench_configs.py"))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    import mfem_ad_b200 as M
+    ctx = M.Context(0)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        for fn in (bc.config3, bc.config4, bc.config5):
+            try:
+                fn(ctx, scale)
+            except Exception as ex:  # one config must not hide the others
+                print(json.dumps({"config": fn.__name__, "error": repr(ex)[:200]}))
+    return [json.loads(l) for l in buf.getvalue().splitlines() if l.startswith("{")]
+
+
+def check_parity(ctx, comm, rank, world, local):
+    """--check: the CUDA path against the CPU oracle on small meshes, before anything is timed."""
+    import torch
+    if world > 1:
+        import mgpu_check as MC
+        for name, fn in (("residual", MC.case_residual), ("block", MC.case_block)):
+            err, flag = fn(rank, world, local, ctx, comm)
+            t = torch.tensor([err, 0.0 if flag else 1.0], device=torch.device("cuda", local), dtype=torch.float64)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            assert t[0].item() <= 1e-12 and t[1].item() == 0.0, ("multi-GPU parity check failed", name, t.tolist())
+        return
+    import contextlib
+    import __graft_entry__ as GE
+    with contextlib.redirect_stdout(sys.stderr):  # stdout carries the JSON line only
+        GE.smoke()
+
+
+def run_reference_c5(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    m = 160
+    forms = c5_cpu_forms(m, cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        cpu_step(forms)
+    ts = [cpu_step(forms) for _ in range(max(1, min(args.steps, 5)))]
+    t = float(np.mean(ts))
+    nd = (m * (C5_ORDER + 1) + 1) ** 2 + m * m * C5_ORDER ** 2
+    val = nd / t
+    sample = "%dx%d elements of the config-5 block form split in %d strips, one thread per strip, residual+Jacobian" % (m, m, len(forms))
+    print(json.dumps({
+        "impl": "reference", "metric": "AD residual+Jacobian assembly DOF/s", "value": val, "unit": "DOF/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": c5_workload(args.n5, 1, 1), "qpts_per_s": 25 * m * m / t,
+        "cpu_baseline": {"value": val, "unit": "DOF/s", "cores": len(forms), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
 
 
 def main():
@@ -340,8 +701,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--n", type=int, default=1000, help="elements per direction per GPU")
+    ap.add_argument("--n", type=int, default=1000, help="elements per direction per GPU (config 2)")
+    ap.add_argument("--n5", type=int, default=1024, help="elements per direction per GPU (config 5)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5], help="BASELINE.json configuration of the line")
+    ap.add_argument("--check", action="store_true", help="assert parity against the CPU oracle before timing")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other_configs / config5 legs of the default line")
     args = ap.parse_args()
     # stdout carries the JSON line and nothing else: libraries that write to file descriptor 1 themselves (NCCL prints
     # its version banner there) are sent to stderr; the line is written to the original descriptor at the end.
@@ -350,7 +715,7 @@ def main():
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_c5 if args.config == 5 else run_reference)(args)
     else:
         run_gpu(args)
     sys.stdout.flush()

@@ -432,7 +432,11 @@ constexpr int WS_WRITER_WG = 2;                              // writer warpgroup
 constexpr int WS_THREADS = (WS_WRITER_WG + 2) * PATCH_PE;
 // Register split after setmaxnreg.  setmaxnreg only redistributes the CTA's own launch allocation (512 x 128 = 64 K
 // registers here) and the total must stay BELOW it: an exact fit deadlocks the increase.
-constexpr int WS_REG_COMPUTE = 208, WS_REG_WRITER = 40;
+#ifndef MADB_WS_REGC
+#define MADB_WS_REGC 208
+#define MADB_WS_REGW 40
+#endif
+constexpr int WS_REG_COMPUTE = MADB_WS_REGC, WS_REG_WRITER = MADB_WS_REGW;
 static_assert(2 * PATCH_PE * WS_REG_COMPUTE + WS_WRITER_WG * PATCH_PE * WS_REG_WRITER <= 65536 - 1024, "setmaxnreg budget");
 
 template <class Func, class Cfg, bool UNROLLQ>

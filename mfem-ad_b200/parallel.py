@@ -218,6 +218,20 @@ def halo_lists(l2g, owner, rank, world, group=None):
     return own, need
 
 
+def lowest_rank_owner(l2g, candidates, ndofs, rank, world, group=None):
+    """Owner rank of every local dof of a NON-overlapping partition: the lowest rank that holds it (candidates = local
+    indices of the dofs that may be shared, e.g. those on the block boundary)."""
+    l2g = np.asarray(l2g, dtype=np.int64)
+    cand = np.asarray(candidates, dtype=np.int64)
+    allg = [None] * world
+    dist.all_gather_object(allg, l2g[cand], group=group)
+    owner = np.full(ndofs, rank, dtype=np.int64)
+    for r in range(rank):
+        hit = cand[np.isin(l2g[cand], allg[r])]
+        owner[hit] = np.minimum(owner[hit], r)
+    return owner
+
+
 class HaloExchange:
     """P (forward: owner -> copies) and P^T (reverse: copies -> owner, added in ascending peer rank) for one local
     vector.  CUDA tensors go through the C ABI (madb_exchange_*: pack kernel, ncclSend/ncclRecv group on a
