@@ -42,6 +42,7 @@ typedef struct madb_mesh madb_mesh;
 typedef struct madb_space madb_space;
 typedef struct madb_functional madb_functional;
 typedef struct madb_integrator madb_integrator;
+typedef struct madb_solver madb_solver;
 typedef struct madb_comm madb_comm;
 typedef struct madb_exchange madb_exchange;
 
@@ -63,6 +64,10 @@ enum { MADB_ROLE_INPUT = 0, MADB_ROLE_PARAM = 1 };
 
 int madb_version(void);
 const char *madb_last_error(void);
+/* 1 if fused kernels are registered under `key` = "<functional key>|<element configuration key>" (the key an integrator
+ * looks up; madb_integrator_create names it when it is missing).  Plugins (user functionals compiled out of tree,
+ * the AD_IMPL bodies of src/ad_native.hpp:332-365) add keys when their library is loaded. */
+int madb_registry_has(const char *key);
 
 /* One context per GPU / rank (replaces nothing in the reference: it has no device). */
 int madb_ctx_create(int device, madb_ctx **out);
@@ -255,6 +260,26 @@ int madb_integrator_param_gradient(madb_integrator *I, const double *design, dou
 int madb_integrator_qpoint_coords(madb_integrator *I, double *xyz);
 /* matrix-free Jacobian action y = J(x) v (no reference equivalent; config 3) */
 int madb_integrator_grad_mult(madb_integrator *I, const double *x, const double *v, double *y);
+
+/* ---- linear solve of a Newton step on the device -----------------------------------------------
+ * The reference solves J dx = -r on the host: UMFPackSolver (ex2.cpp:80), MUMPSMonoSolver (src/tools.hpp:128-154), or a
+ * Krylov method with PGPreconditioner (src/pg.hpp:378-504).  A solver object works on the CSR pattern of an integrator
+ * (madb_integrator_pattern); vals / b / x are host or device pointers (detected), vals normally the device array
+ * madb_integrator_assemble has just filled, so that the Jacobian never crosses PCIe.  x holds the initial guess on entry.
+ * Stopping: ||r|| <= max(rtol ||b||, atol), at most maxit iterations; *iters / *relres report what was reached. */
+int madb_solver_create(madb_integrator *I, madb_solver **out);
+int madb_solver_destroy(madb_solver *s);
+/* Jacobi-preconditioned conjugate gradients (SPD Jacobians: ex1 - ex3 with essential dofs eliminated DIAG_ONE) */
+int madb_solver_pcg(madb_solver *s, const double *vals, const double *b, double *x, double rtol, double atol, int maxit,
+                    int *iters, double *relres);
+/* Proximal-Galerkin block systems [[A, C], [C^T, -D]] (ex4.cpp:136-142, ex5, par_template): unknowns [0, nh) primal,
+ * [nh, n) latent on an L2 space with nb dofs per element (D block diagonal, definite: the entropy-Hessian-weighted mass
+ * matrix of PGPreconditioner).  The latent block is eliminated exactly, S = A + C D^-1 C^T is solved by Jacobi-PCG, the
+ * latent part follows by back-substitution. */
+int madb_solver_condensed_pcg(madb_solver *s, int nh, int nb, const double *vals, const double *b, double *x, double rtol,
+                              double atol, int maxit, int *iters, double *relres);
+/* y = A x with the solver's pattern (hand-written CSR kernel, deterministic) */
+int madb_csr_spmv(madb_solver *s, const double *vals, const double *x, double *y);
 
 #ifdef __cplusplus
 }

@@ -96,6 +96,13 @@ def lib():
         L.madb_integrator_assemble.argtypes = [vp, dp, dp, dp]
         L.madb_integrator_grad_mult.argtypes = [vp, dp, dp, dp]
         L.madb_integrator_coefficient.argtypes = [vp, dp, dp, dp]
+        L.madb_solver_create.argtypes = [vp, pp]
+        L.madb_solver_destroy.argtypes = [vp]
+        L.madb_solver_pcg.argtypes = [vp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.madb_solver_condensed_pcg.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
+                                                C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.madb_csr_spmv.argtypes = [vp, dp, dp, dp]
+        L.madb_registry_has.argtypes = [C.c_char_p]
         _lib = L
     return _lib
 
@@ -423,6 +430,62 @@ def patch_selftest_img(mesh, space, tpe):
                                          e2l.ctypes.data, tpe, C.byref(err), st))
     keys = ("patches", "ifc_dofs", "ifc_entries", "staged_vals", "smem_per_group", "nnz", "bulk_entries", "map_bytes")
     return err.value, dict(zip(keys, [int(v) for v in st]))
+
+
+class Solver:
+    """Linear solve of a Newton step on the device (madb_solver_*): Jacobi-PCG on SPD Jacobians, and the statically
+    condensed PCG for proximal-Galerkin block systems (latent L2 block eliminated exactly).  Replaces the host direct
+    solvers of the drivers (ex2.cpp:80, src/tools.hpp:128-154) so that the CSR values stay on the GPU."""
+
+    def __init__(self, integrator):
+        h = C.c_void_p()
+        _check(lib().madb_solver_create(integrator.h, C.byref(h)))
+        self.h, self.integrator = h, integrator
+        self.n = integrator.vsize if hasattr(integrator, "vsize") else None
+
+    def _out(self, b, x):
+        if x is None:
+            x = np.zeros_like(b) if isinstance(b, np.ndarray) else b.new_zeros(b.shape)
+        return x
+
+    def pcg(self, vals, b, x=None, rtol=1e-10, atol=0.0, maxit=10000):
+        x = self._out(b, x)
+        it, rr = C.c_int(0), C.c_double(0.0)
+        _check(lib().madb_solver_pcg(self.h, _ptr(vals), _ptr(b), _ptr(x), rtol, atol, maxit, C.byref(it), C.byref(rr)))
+        return x, it.value, rr.value
+
+    def condensed_pcg(self, nh, nb, vals, b, x=None, rtol=1e-10, atol=0.0, maxit=10000):
+        x = self._out(b, x)
+        it, rr = C.c_int(0), C.c_double(0.0)
+        _check(lib().madb_solver_condensed_pcg(self.h, nh, nb, _ptr(vals), _ptr(b), _ptr(x), rtol, atol, maxit,
+                                               C.byref(it), C.byref(rr)))
+        return x, it.value, rr.value
+
+    def spmv(self, vals, x, y=None):
+        y = self._out(x, y)
+        _check(lib().madb_csr_spmv(self.h, _ptr(vals), _ptr(x), _ptr(y)))
+        return y
+
+    def __del__(self):
+        try:
+            lib().madb_solver_destroy(self.h)
+        except Exception:
+            pass
+
+
+def load_vector(ctx, space, f, quad_order=None):
+    """Load vector b_i = (f, phi_i) of a scalar space on the device (MFEM: LinearForm + DomainLFIntegrator(f),
+    ex4.cpp:145-148).  f: host callback xyz[npts, dim] -> [npts] sampled at the rule's points
+    (Coefficient-type source), or an array [ne, nq] already sampled there.  quad_order None: MFEM's linear-form rule
+    (order 2p).  Implemented as the residual of the energy f(x) u (functional "load"): same kernels as every other form."""
+    order = int(space.desc["order"])
+    fn = Functional(ctx, "load")
+    gi = Integrator(ctx, [(space, VALUE)], fn, quad_order=2 * order if quad_order is None else quad_order)
+    if callable(f):
+        gi.set_param_coefficient(f)
+    else:
+        gi.set_param_qf(np.ascontiguousarray(f, dtype=np.float64))
+    return gi.mult(np.zeros(space.desc["ndofs"]))
 
 
 def lvpp_update(ctx, alpha, psi, psik, lambda_prev, w=None):

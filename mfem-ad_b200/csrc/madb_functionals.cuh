@@ -65,6 +65,15 @@ template <int N> struct MassEnergy
    }
 };
 
+// Linear form (f, v): energy f(x) u with f a per-point parameter (a Coefficient sampled at the points).  Its gradient
+// is the load vector MFEM's DomainLFIntegrator assembles (ex4.cpp:145-148); its Hessian is zero.
+struct LoadFunctional
+{
+   static constexpr int N_INPUT = 1, N_PARAM = 0, N_QPRM = 1;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *qp) const { return x[0] * qp[0]; }
+};
+
 // src/ad_native.hpp:421-481.  KDIM selects the K kind at compile time
 // (0 none, 1 scalar, DIM diagonal, DIM*DIM full, column-major) instead of the
 // per-point size dispatch of the reference.  K is a constant here;

@@ -210,6 +210,7 @@ static int upload_ifc(const PatchHost &H, int *(&d)[5], IfcListDev &L)
 }
 
 static int ensure_pattern_device(Integrator &I);
+int solver_new(Ctx *ctx, int n, long nnz, const int *d_rowptr, const int *d_colidx, madb_solver **out); // madb_solve.cu
 static void release_device_maps(Integrator &I)
 {
    cudaFree(I.d_e2n); cudaFree(I.d_vmap); cudaFree(I.d_pmap); cudaFree(I.d_perm); cudaFree(I.d_e2csr);
@@ -634,7 +635,8 @@ struct madb_integrator : Integrator {};
 extern "C"
 {
 
-   int madb_version(void) { return 100; }
+   int madb_version(void) { return 101; }
+   int madb_registry_has(const char *key) { return (key && registry().count(key)) ? 1 : 0; }
    const char *madb_last_error(void) { return last_error(); }
 
    int madb_ctx_create(int device, madb_ctx **out)
@@ -1170,6 +1172,13 @@ extern "C"
          else { std::memcpy(colidx, I->colidx.data(), I->colidx.size() * sizeof(int)); }
       }
       return 0;
+   }
+   int madb_solver_create(madb_integrator *I, madb_solver **out)
+   {
+      CUDA_OK(cudaSetDevice(I->ctx->device));
+      if (I->ops.matrix_free_only) { set_error("madb_solver_create: the integrator has no assembled Jacobian (matrix-free only)"); return 1; }
+      if (ensure_pattern_device(*I)) { return 1; }
+      return solver_new(I->ctx, (int)I->ntotal, (long)I->colidx.size(), I->d_rowptr, I->d_colidx, out);
    }
    int madb_integrator_grad_assemble(madb_integrator *I, const double *x, double *vals)
    {

@@ -316,4 +316,37 @@ public:
 };
 typedef BlockNonlinearForm NonlinearForm;
 
+/// LinearForm + DomainLFIntegrator(f) of the drivers (ex4.cpp:145-148): b_i = (f, phi_i) on a scalar space, assembled on
+/// the device as the residual of the energy f(x) u (functional "load"); f is sampled at the rule's points on the host
+/// (Coefficient-type source).  ir_order < 0: MFEM's linear-form rule (order 2p).
+class LinearForm : public Vector
+{
+   FiniteElementSpace &fes;
+public:
+   explicit LinearForm(FiniteElementSpace *s) : fes(*s) {}
+   template <class F> void AddDomainIntegrator(F f, int ir_order = -1)
+   {
+      madb_functional *fn = nullptr;
+      madb_integrator *intg = nullptr;
+      madb_ctx *ctx = Device::Get().ctx;
+      MADB_CALL(madb_functional_create(ctx, "load", 0, nullptr, 0, nullptr, 0, nullptr, &fn));
+      madb_space *sp = fes.h;
+      int md = MADB_VALUE, rl = MADB_ROLE_INPUT;
+      const int ord = ir_order < 0 ? 2 * fes.order : ir_order, nq1 = (ord | 1) / 2 + 1; // IntRules.Get(geom, order)
+      MADB_CALL(madb_integrator_create(ctx, 1, &sp, &md, &rl, fn, ord, &intg));
+      const int64_t npts = (int64_t)fes.mesh.GetNE() * nq1 * nq1;
+      std::vector<double> xyz((size_t)npts * fes.mesh.dim), qf((size_t)npts);
+      MADB_CALL(madb_integrator_qpoint_coords(intg, xyz.data()));
+      for (int64_t k = 0; k < npts; k++) { qf[k] = f(&xyz[(size_t)k * fes.mesh.dim]); }
+      MADB_CALL(madb_integrator_set_param_qf(intg, 1, qf.data()));
+      Vector zero((size_t)fes.GetVSize(), 0.0), b((size_t)fes.GetVSize(), 0.0);
+      MADB_CALL(madb_integrator_mult(intg, zero.data(), b.data()));
+      if (size() != b.size()) { assign(b.size(), 0.0); }
+      for (size_t i = 0; i < b.size(); i++) { (*this)[i] += b[i]; }
+      madb_integrator_destroy(intg);
+      madb_functional_destroy(fn);
+   }
+   void Assemble() {} // the integrators assemble when they are added
+};
+
 } // namespace madb_host

@@ -4,18 +4,50 @@ proximal-Galerkin iteration of the reference's drivers.
     newton()      <-> mfem::NewtonSolver::Mult [MFEM-upstream] as configured at ex4.cpp:166-176
     lvpp_solve()  <-> the outer loop of ex4.cpp:183-219 / ex5.cpp:174-212
 
-The linear solve inside Newton is out of scope of the hot path (SURVEY 8f rank 1);
-both the CUDA path and the CPU oracle are driven through the same SuperLU
-factorisation (scipy) so that iteration counts are comparable.  `op` is any object
-with  mult(x) -> residual,  grad(x) -> CSR values,  pattern() -> (rowptr, colidx).
+Linear solve inside Newton: by default both the CUDA path and the CPU oracle are driven through
+the same SuperLU factorisation (scipy) so that iteration counts are comparable; with `linear=` the CUDA path solves on the
+device (madb_solver_*: Jacobi-PCG, or the statically condensed PCG for proximal-Galerkin block systems) and the CSR
+values never leave the GPU.  `op` is any object with  mult(x) -> residual,  grad(x) -> CSR values,
+pattern() -> (rowptr, colidx).
 """
 import numpy as np
 import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 
-def newton(op, b, x, abs_tol=1e-9, rel_tol=0.0, max_iter=20):
-    """x is updated in place (iterative_mode = true).  Returns (converged, iterations, final_norm)."""
+class DeviceLinear:
+    """Device linear solve for newton(): kind "pcg" (SPD Jacobians) or "condensed" (PG block systems, primal dofs [0, nh),
+    latent L2 dofs after them, nb per element).  The CSR values live in one device array that the assembly fills."""
+
+    def __init__(self, integrator, kind="pcg", nh=None, nb=None, rtol=1e-12, maxit=20000):
+        import torch
+        import mfem_ad_b200 as M
+        self.gi, self.kind, self.nh, self.nb, self.rtol, self.maxit = integrator, kind, nh, nb, rtol, maxit
+        self.solver = M.Solver(integrator)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.vals = torch.empty(integrator.nnz, dtype=torch.float64, device=dev)
+        self.linear_iterations = []
+
+    def step(self, x, b):
+        """Newton correction c with J(x) c = F(x) - b; returns (c, residual used)."""
+        r = np.empty_like(x)
+        self.gi.assemble(x, r, self.vals)  # residual to the host, Jacobian values stay on the device
+        r -= b
+        c = np.zeros_like(x)
+        if self.kind == "pcg":
+            c, it, rr = self.solver.pcg(self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
+        else:
+            c, it, rr = self.solver.condensed_pcg(self.nh, self.nb, self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
+        self.linear_iterations.append(it)
+        self.relres = getattr(self, "relres", []) + [rr]
+        if not rr <= max(1e3 * self.rtol, 1e-8):
+            raise RuntimeError("device linear solve stalled: relative residual %.2e after %d iterations" % (rr, it))
+        return c
+
+
+def newton(op, b, x, abs_tol=1e-9, rel_tol=0.0, max_iter=20, linear=None):
+    """x is updated in place (iterative_mode = true).  Returns (converged, iterations, final_norm).
+    linear: a DeviceLinear (solve on the GPU) or None (SuperLU on the host)."""
     rowptr, colidx = op.pattern()
     n = x.size
     r = op.mult(x) - b
@@ -27,9 +59,12 @@ def newton(op, b, x, abs_tol=1e-9, rel_tol=0.0, max_iter=20):
             return True, it, norm
         if it >= max_iter:
             return False, it, norm
-        vals = op.grad(x)
-        J = sp.csr_matrix((vals, colidx, rowptr), shape=(n, n)).tocsc()
-        c = spla.splu(J).solve(r)
+        if linear is not None:
+            c = linear.step(x, b)
+        else:
+            vals = op.grad(x)
+            J = sp.csr_matrix((vals, colidx, rowptr), shape=(n, n)).tocsc()
+            c = spla.splu(J).solve(r)
         x -= c
         r = op.mult(x) - b
         norm = np.linalg.norm(r)

@@ -160,7 +160,7 @@ enum Kind
    K_MINSURF = 6, K_OBSTACLE = 7, K_GRADOBSTACLE = 8, K_LAGRANGIAN = 9,
    K_AL = 10, K_PG = 11, K_LAMBDAPG = 12, K_SHANNON = 13, K_FERMIDIRAC = 14,
    K_HELLINGER = 15, K_SIMPLEX = 16, K_SIMP = 17, K_PARAMCOMPLIANCE = 18,
-   K_EMPTY = 19, K_EX0VEC = 20
+   K_EMPTY = 19, K_EX0VEC = 20, K_LOAD = 21
 };
 
 extern "C" struct orc_fn_t
@@ -273,6 +273,11 @@ template <class T> T fn_eval(const Ctx &c, int id, const Vec<T> &x)
          return x * x * 0.5;
       case K_EMPTY: // src/_dof_pg.hpp:14
          return zero<T>();
+      case K_LOAD: // linear form (f, v): the gradient of f(x) u is MFEM's DomainLFIntegrator(f) (ex4.cpp:145-148)
+      {
+         T result = x[0] * (qp ? qp[0] : f.param[0]);
+         return result;
+      }
       case K_LAGRANGIAN: // src/ad_native.hpp:607-618
       {
          const int nobj = c.nodes[f.child[0]].n_input;

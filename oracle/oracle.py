@@ -17,7 +17,7 @@ _LIB = None
 K_EX0, K_MASS, K_DIFFUSION, K_DIFF, K_ELASTICITY, K_MINSURF, K_OBSTACLE, \
     K_GRADOBSTACLE, K_LAGRANGIAN, K_AL, K_PG, K_LAMBDAPG, K_SHANNON, \
     K_FERMIDIRAC, K_HELLINGER, K_SIMPLEX, K_SIMP, K_PARAMCOMPLIANCE, K_EMPTY, \
-    K_EX0VEC = range(1, 21)
+    K_EX0VEC, K_LOAD = range(1, 22)
 
 # ADEval flags (src/_ad_intg.hpp:24-36)
 QVALUE, VALUE, GRAD, DIV, CURL, HESSIAN, VECTOR, VECFE = (1 << i for i in range(8))

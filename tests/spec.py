@@ -13,7 +13,7 @@ class FSpec:
     _OK = dict(ex0=O.K_EX0, mass=O.K_MASS, diffusion=O.K_DIFFUSION, diff=O.K_DIFF, elasticity=O.K_ELASTICITY,
                minsurf=O.K_MINSURF, obstacle=O.K_OBSTACLE, gradobstacle=O.K_GRADOBSTACLE, pg=O.K_PG,
                lambdapg=O.K_LAMBDAPG, lagrangian=O.K_LAGRANGIAN, al=O.K_AL, shannon=O.K_SHANNON, fermidirac=O.K_FERMIDIRAC, hellinger=O.K_HELLINGER,
-               simplex=O.K_SIMPLEX, simp=O.K_SIMP, paramcompliance=O.K_PARAMCOMPLIANCE, empty=O.K_EMPTY)
+               simplex=O.K_SIMPLEX, simp=O.K_SIMP, paramcompliance=O.K_PARAMCOMPLIANCE, empty=O.K_EMPTY, load=O.K_LOAD)
 
     def _add(self, F):
         ch = [c._add(F) for c in self.children]
@@ -66,6 +66,11 @@ def diff(energy, qoff=0):
 
 def mass(n):
     return FSpec("mass", n)
+
+
+def load():
+    """f(x) u with f the first per-point parameter: its gradient is the load vector (DomainLFIntegrator, ex4.cpp:145-148)."""
+    return FSpec("load", 1, qoff=0)
 
 
 def elasticity(dim, lam, mu):

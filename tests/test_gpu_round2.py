@@ -175,3 +175,32 @@ def test_partial_last_patch_many_iterations(ctx):
     Ks = sp.csr_matrix((vs, cis, rps), shape=(big.size,) * 2)
     rows = np.nonzero(inner)[0]
     assert np.max(np.abs(K[big[rows]][:, big].toarray() - Ks[rows].toarray())) <= TOL * np.max(np.abs(vs))
+
+
+def test_load_vector_matches_oracle_and_closed_form(ctx):
+    """b_i = (f, phi_i) (LinearForm + DomainLFIntegrator, ex4.cpp:145-148) on the device: against the
+    oracle's gradient of the same energy, against the exact integral of f (sum of b = int f: partition of unity) and,
+    for f = 1 on a uniform Q1 mesh, against the hand values h^2/4 x (number of elements at the node)."""
+    import mfem_ad_b200 as M
+    mesh = G.cartesian_mesh((7, 5), perturb=0.2)
+    f = lambda p: 2.0 * np.pi ** 2 * np.sin(np.pi * p[:, 0]) * np.sin(np.pi * p[:, 1])  # ex4.cpp:93-98
+    for order, qo in ((1, 2), (2, 4), (3, 6), (3, 9)):
+        s = G.h1_space(mesh, order, mode=O.VALUE)
+        gm = M.Mesh(ctx, mesh)
+        gs = M.Space(ctx, gm, s)
+        b = M.load_vector(ctx, gs, f, quad_order=qo)
+        gi = M.Integrator(ctx, [(gs, O.VALUE)], S.load().madb(ctx), quad_order=qo)
+        qf = gi.set_param_coefficient(f)
+        ref = O.OracleForm(mesh, [s], S.load().oracle(), quad_order=qo, params=[dict(type=O.PRM_QF, size=1, data=qf)]).mult(np.zeros(s["ndofs"]))
+        assert S.csr_rel_err(b, ref) <= 1e-13
+    # exact integral of f over [0,1]^2 is 8; order-3 space with the 5x5 rule on the unperturbed mesh
+    mesh = G.cartesian_mesh((8, 8))
+    s = G.h1_space(mesh, 3, mode=O.VALUE)
+    gm = M.Mesh(ctx, mesh)
+    b = M.load_vector(ctx, M.Space(ctx, gm, s), f, quad_order=9)
+    assert abs(b.sum() - 8.0) <= 1e-7
+    s1 = G.h1_space(mesh, 1, mode=O.VALUE)
+    b1 = M.load_vector(ctx, M.Space(ctx, gm, s1), lambda p: np.ones(p.shape[0]))
+    cnt = np.zeros(s1["ndofs"])
+    np.add.at(cnt, np.asarray(s1["e2l"]).reshape(-1), 1.0)
+    assert np.max(np.abs(b1 - cnt / 64.0 / 4.0)) <= 1e-15
