@@ -278,6 +278,12 @@ int madb_solver_pcg(madb_solver *s, const double *vals, const double *b, double 
  * latent part follows by back-substitution. */
 int madb_solver_condensed_pcg(madb_solver *s, int nh, int nb, const double *vals, const double *b, double *x, double rtol,
                               double atol, int maxit, int *iters, double *relres);
+/* The same block systems without condensation: preconditioned MINRES on the symmetric indefinite matrix with the block
+ * diagonal preconditioner diag(|diag A|, S_e), S_e = D_e + C_e^T diag(A)^-1 C_e per element (the PGPreconditioner idea,
+ * src/pg.hpp:378-504, with Jacobi instead of AMG on the primal block).  Robust when the entropy Hessian degenerates
+ * (active sets: D -> 0), where the condensed operator becomes a penalty matrix.  Stopping on the preconditioned residual. */
+int madb_solver_pg_minres(madb_solver *s, int nh, int nb, const double *vals, const double *b, double *x, double rtol,
+                          double atol, int maxit, int *iters, double *relres);
 /* y = A x with the solver's pattern (hand-written CSR kernel, deterministic) */
 int madb_csr_spmv(madb_solver *s, const double *vals, const double *x, double *y);
 

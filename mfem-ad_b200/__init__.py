@@ -101,6 +101,8 @@ def lib():
         L.madb_solver_pcg.argtypes = [vp, dp, dp, dp, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.madb_solver_condensed_pcg.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
                                                 C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.madb_solver_pg_minres.argtypes = [vp, C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int,
+                                            C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.madb_csr_spmv.argtypes = [vp, dp, dp, dp]
         L.madb_registry_has.argtypes = [C.c_char_p]
         _lib = L
@@ -459,6 +461,13 @@ class Solver:
         it, rr = C.c_int(0), C.c_double(0.0)
         _check(lib().madb_solver_condensed_pcg(self.h, nh, nb, _ptr(vals), _ptr(b), _ptr(x), rtol, atol, maxit,
                                                C.byref(it), C.byref(rr)))
+        return x, it.value, rr.value
+
+    def pg_minres(self, nh, nb, vals, b, x=None, rtol=1e-10, atol=0.0, maxit=20000):
+        x = self._out(b, x)
+        it, rr = C.c_int(0), C.c_double(0.0)
+        _check(lib().madb_solver_pg_minres(self.h, nh, nb, _ptr(vals), _ptr(b), _ptr(x), rtol, atol, maxit,
+                                           C.byref(it), C.byref(rr)))
         return x, it.value, rr.value
 
     def spmv(self, vals, x, y=None):

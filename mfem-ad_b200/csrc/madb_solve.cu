@@ -289,6 +289,122 @@ __global__ void k_diag_schur(const int nh, const int *rowptr, const int *colidx,
    dinv[i] = (d != 0.0) ? 1.0 / d : 1.0;
 }
 
+/// partial of a.b (fixed grid)
+__global__ void __launch_bounds__(RED_THREADS) k_dot(const int n, const double *a, const double *b, double *partial)
+{
+   __shared__ double sm[RED_THREADS];
+   double acc = 0.0;
+   for (int i = blockIdx.x * RED_THREADS + threadIdx.x; i < n; i += gridDim.x * RED_THREADS) { acc = fma(a[i], b[i], acc); }
+   const double s = block_sum(acc, sm);
+   if (threadIdx.x == 0) { partial[blockIdx.x] = s; }
+}
+/// y = a x + b y + c z
+__global__ void k_lincomb3(const int n, const double a, const double *x, const double b, double *y, const double c, const double *z)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { y[i] = a * x[i] + b * y[i] + c * z[i]; }
+}
+/// out = a x + b y + c z (out may alias none of them)
+__global__ void k_lincomb3o(const int n, const double a, const double *x, const double b, const double *y, const double c, const double *z, double *out)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { out[i] = a * x[i] + b * y[i] + c * z[i]; }
+}
+__global__ void k_scale(const int n, const double a, double *x)
+{
+   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { x[i] *= a; }
+}
+
+/// Block-diagonal preconditioner of the saddle-point system [[A, C], [C^T, -D]] (the PGPreconditioner idea,
+/// src/pg.hpp:378-504, with Jacobi on the primal block): element blocks of the approximate latent Schur complement
+///    S_e = D_e + C_e^T diag(A)^-1 C_e     (NB x NB, symmetric positive definite)
+/// The latent rows of one element have the same primal columns in the same (sorted) order: full element connectivity.
+template <int NB>
+__global__ void k_schur_blocks(const int nel, const int nh, const int *rowptr, const int *colidx, const double *vals,
+                               const double *dinvA, double *blocks)
+{
+   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+   if (e >= nel) { return; }
+   double Sb[NB][NB];
+   int start[NB], nprim = 0;
+#pragma unroll
+   for (int r = 0; r < NB; r++)
+   {
+      const int row = nh + e * NB + r;
+      start[r] = rowptr[row];
+      int lo = rowptr[row], hi = rowptr[row + 1];
+      while (lo < hi) // first latent column of the row
+      {
+         const int m = (lo + hi) >> 1;
+         if (colidx[m] < nh) { lo = m + 1; } else { hi = m; }
+      }
+      if (r == 0) { nprim = lo - rowptr[row]; }
+      // latent block -D_e: the NB columns nh + e * NB ..
+      int l2 = lo;
+      while (colidx[l2] < nh + e * NB) { l2++; }
+#pragma unroll
+      for (int c = 0; c < NB; c++) { Sb[r][c] = -vals[l2 + c]; }
+   }
+   for (int k = 0; k < nprim; k++)
+   {
+      const double di = dinvA[colidx[start[0] + k]];
+      double c[NB];
+#pragma unroll
+      for (int r = 0; r < NB; r++) { c[r] = vals[start[r] + k]; }
+#pragma unroll
+      for (int r = 0; r < NB; r++)
+      {
+#pragma unroll
+         for (int q = 0; q < NB; q++) { Sb[r][q] = fma(c[r] * di, c[q], Sb[r][q]); }
+      }
+   }
+#pragma unroll
+   for (int r = 0; r < NB; r++)
+   {
+#pragma unroll
+      for (int c = 0; c < NB; c++) { blocks[((size_t)e * NB + r) * NB + c] = Sb[r][c]; }
+   }
+}
+/// z = P^-1 v: z_u = |dinvA| v_u (positive definite preconditioner), z_psi,e = S_e^-1 v_psi,e
+template <int NB>
+__global__ void k_apply_precond(const int nel, const int nh, const double *dinvA, const double *blocks, const double *v, double *z)
+{
+   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+   for (int i = t; i < nh; i += gridDim.x * blockDim.x) { z[i] = fabs(dinvA[i]) * v[i]; }
+   for (int e = t; e < nel; e += gridDim.x * blockDim.x)
+   {
+      double A[NB][NB], b[NB];
+#pragma unroll
+      for (int r = 0; r < NB; r++)
+      {
+#pragma unroll
+         for (int c = 0; c < NB; c++) { A[r][c] = blocks[((size_t)e * NB + r) * NB + c]; }
+         b[r] = v[nh + e * NB + r];
+      }
+#pragma unroll
+      for (int p = 0; p < NB; p++)
+      {
+         const double piv = 1.0 / A[p][p];
+#pragma unroll
+         for (int r = p + 1; r < NB; r++)
+         {
+            const double f = A[r][p] * piv;
+#pragma unroll
+            for (int c = p + 1; c < NB; c++) { A[r][c] = fma(-f, A[p][c], A[r][c]); }
+            b[r] = fma(-f, b[p], b[r]);
+         }
+      }
+#pragma unroll
+      for (int r = NB - 1; r >= 0; r--)
+      {
+         double s = b[r];
+#pragma unroll
+         for (int c = r + 1; c < NB; c++) { s = fma(-A[r][c], b[c], s); }
+         b[r] = s / A[r][r];
+      }
+#pragma unroll
+      for (int r = 0; r < NB; r++) { z[nh + e * NB + r] = b[r]; }
+   }
+}
+
 bool is_dev(const void *p)
 {
    if (!p) { return false; }
@@ -306,11 +422,13 @@ struct Solver
    const int *rowptr = nullptr, *colidx = nullptr; // device (the integrator's pattern, or own copies)
    int *own_rowptr = nullptr, *own_colidx = nullptr;
    double *work = nullptr; // r, z, p, q, dinv, w, t1, t2, bS (9 n) + partials + scalars
+   double *work2 = nullptr; // MINRES: 8 vectors + preconditioner blocks
+   size_t work2_words = 0;
    double *vals_buf = nullptr, *b_buf = nullptr, *x_buf = nullptr;
    int tpr = 8;
    ~Solver()
    {
-      cudaFree(own_rowptr); cudaFree(own_colidx); cudaFree(work); cudaFree(vals_buf); cudaFree(b_buf); cudaFree(x_buf);
+      cudaFree(own_rowptr); cudaFree(own_colidx); cudaFree(work); cudaFree(work2); cudaFree(vals_buf); cudaFree(b_buf); cudaFree(x_buf);
    }
 };
 
@@ -533,6 +651,112 @@ extern "C"
       spmv(S, st, nh, n, dv, w, t1 - nh, nullptr, nullptr);
       k_axpby<<<RED_BLOCKS, RED_THREADS, 0, st>>>(nl, 1.0, db + nh, -1.0, t1);
       if (block_solve(S, st, nel, nh, nb, dv, t1, dx + nh, 1.0)) { return 1; }
+      if (!is_dev(x)) { SOLVE_OK(cudaMemcpyAsync(x, dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st)); }
+      SOLVE_OK(cudaStreamSynchronize(st));
+      return 0;
+   }
+
+   int madb_solver_pg_minres(madb_solver *s, int nh, int nb, const double *vals, const double *b, double *x, double rtol,
+                             double atol, int maxit, int *iters, double *relres)
+   {
+      Solver &S = *reinterpret_cast<Solver *>(s);
+      SOLVE_OK(cudaSetDevice(S.ctx->device));
+      cudaStream_t st = S.ctx->stream;
+      const int n = S.n, nl = n - nh;
+      if (nh <= 0 || nl <= 0 || nb <= 0 || nl % nb != 0) { set_error("madb_solver_pg_minres: bad block sizes"); return 1; }
+      const int nel = nl / nb;
+      const double *dv, *db, *dx0;
+      if (stage_in(S, vals, (size_t)S.nnz, &S.vals_buf, &dv) || stage_in(S, b, (size_t)n, &S.b_buf, &db) || stage_in(S, x, (size_t)n, &S.x_buf, &dx0))
+      {
+         return 2;
+      }
+      double *dx = const_cast<double *>(dx0);
+      const size_t need = 8 * (size_t)n + (size_t)nl * nb + 16;
+      if (S.work2_words < need)
+      {
+         cudaFree(S.work2);
+         S.work2 = nullptr;
+         SOLVE_OK(cudaMalloc((void **)&S.work2, need * sizeof(double)));
+         S.work2_words = need;
+      }
+      double *v0 = S.work2, *v1 = v0 + n, *v2 = v1 + n, *z1 = v2 + n, *z2 = z1 + n, *w0 = z2 + n, *w1 = w0 + n, *w2 = w1 + n, *blocks = w2 + n;
+      double *dinvA = S.work + 4 * (size_t)n, *partial = S.work + 9 * (size_t)n, *scal = partial + 2 * RED_BLOCKS;
+      k_diag_inv<<<(nh + 255) / 256, 256, 0, st>>>(nh, S.rowptr, S.colidx, dv, dinvA);
+      auto precond = [&](const double *v, double *z) -> int
+      {
+         const int grid = RED_BLOCKS;
+         switch (nb)
+         {
+            case 1: k_apply_precond<1><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
+            case 3: k_apply_precond<3><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
+            case 4: k_apply_precond<4><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
+            case 8: k_apply_precond<8><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
+            case 9: k_apply_precond<9><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
+            default: return 1;
+         }
+         return 0;
+      };
+      {
+         const int grid = (nel + 127) / 128;
+         switch (nb)
+         {
+            case 1: k_schur_blocks<1><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
+            case 3: k_schur_blocks<3><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
+            case 4: k_schur_blocks<4><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
+            case 8: k_schur_blocks<8><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
+            case 9: k_schur_blocks<9><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
+            default: set_error("madb_solver_pg_minres: latent blocks of 1, 3, 4, 8 or 9 dofs per element"); return 1;
+         }
+      }
+      auto dot = [&](const double *a, const double *c, double *out) -> int
+      {
+         k_dot<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, a, c, partial);
+         k_final<<<1, RED_THREADS, 0, st>>>(partial, RED_BLOCKS, 1, scal);
+         SOLVE_OK(cudaMemcpyAsync(out, scal, sizeof(double), cudaMemcpyDeviceToHost, st));
+         SOLVE_OK(cudaStreamSynchronize(st));
+         return 0;
+      };
+      // preconditioned MINRES (Paige & Saunders; notation of Elman, Silvester, Wathen, Algorithm 4.1)
+      SOLVE_OK(cudaMemsetAsync(v0, 0, (size_t)n * sizeof(double), st));
+      SOLVE_OK(cudaMemsetAsync(w0, 0, (size_t)n * sizeof(double), st));
+      SOLVE_OK(cudaMemsetAsync(w1, 0, (size_t)n * sizeof(double), st));
+      spmv(S, st, 0, n, dv, dx, v1, nullptr, nullptr);
+      k_axpby<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, 1.0, db, -1.0, v1); // v1 = b - A x0
+      if (precond(v1, z1)) { return 1; }
+      double g2 = 0.0, bb = 0.0;
+      if (dot(z1, v1, &g2)) { return 2; }
+      if (precond(db, z2) || dot(z2, db, &bb)) { return 2; }
+      double gamma0 = 1.0, gamma1 = std::sqrt(std::max(g2, 0.0)), eta = gamma1, s0 = 0.0, s1 = 0.0, c0 = 1.0, c1 = 1.0;
+      const double bnorm = std::sqrt(std::max(bb, 0.0)), tol = std::max(rtol * bnorm, atol);
+      int it = 0;
+      while (std::fabs(eta) > tol && it < maxit && gamma1 > 0.0)
+      {
+         k_scale<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, 1.0 / gamma1, z1);
+         spmv(S, st, 0, n, dv, z1, v2, nullptr, nullptr); // v2 = A z1
+         double delta = 0.0;
+         if (dot(v2, z1, &delta)) { return 2; }
+         k_lincomb3<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, -delta / gamma1, v1, 1.0, v2, -gamma1 / gamma0, v0);
+         if (precond(v2, z2)) { return 1; }
+         double g2n = 0.0;
+         if (dot(z2, v2, &g2n)) { return 2; }
+         const double gamma2 = std::sqrt(std::max(g2n, 0.0));
+         const double a0 = c1 * delta - c0 * s1 * gamma1, a1 = std::sqrt(a0 * a0 + gamma2 * gamma2), a2 = s1 * delta + c0 * c1 * gamma1,
+                      a3 = s0 * gamma1;
+         const double c2 = a0 / a1, s2 = gamma2 / a1;
+         k_lincomb3o<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, 1.0 / a1, z1, -a3 / a1, w0, -a2 / a1, w1, w2);
+         k_axpby<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, c2 * eta, w2, 1.0, dx);
+         eta = -s2 * eta;
+         // rotate
+         double *t = v0; v0 = v1; v1 = v2; v2 = t;
+         t = z1; z1 = z2; z2 = t;
+         t = w0; w0 = w1; w1 = w2; w2 = t;
+         gamma0 = gamma1; gamma1 = gamma2;
+         c0 = c1; c1 = c2; s0 = s1; s1 = s2;
+         it++;
+         if (!(eta == eta)) { set_error("madb_solver_pg_minres: breakdown (NaN)"); return 3; }
+      }
+      if (iters) { *iters = it; }
+      if (relres) { *relres = (bnorm > 0.0) ? std::fabs(eta) / bnorm : std::fabs(eta); }
       if (!is_dev(x)) { SOLVE_OK(cudaMemcpyAsync(x, dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st)); }
       SOLVE_OK(cudaStreamSynchronize(st));
       return 0;

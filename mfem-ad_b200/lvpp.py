@@ -16,8 +16,8 @@ import scipy.sparse.linalg as spla
 
 
 class DeviceLinear:
-    """Device linear solve for newton(): kind "pcg" (SPD Jacobians) or "condensed" (PG block systems, primal dofs [0, nh),
-    latent L2 dofs after them, nb per element).  The CSR values live in one device array that the assembly fills."""
+    """Device linear solve for newton(): kind "pcg" (SPD Jacobians), "condensed" or "minres" (PG block systems, primal dofs
+    [0, nh), latent L2 dofs after them, nb per element; "minres" stays robust when the entropy Hessian degenerates).  The CSR values live in one device array that the assembly fills."""
 
     def __init__(self, integrator, kind="pcg", nh=None, nb=None, rtol=1e-12, maxit=20000):
         import torch
@@ -36,8 +36,10 @@ class DeviceLinear:
         c = np.zeros_like(x)
         if self.kind == "pcg":
             c, it, rr = self.solver.pcg(self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
-        else:
+        elif self.kind == "condensed":
             c, it, rr = self.solver.condensed_pcg(self.nh, self.nb, self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
+        else:  # "minres": the block system as it is, block-diagonal preconditioner
+            c, it, rr = self.solver.pg_minres(self.nh, self.nb, self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
         self.linear_iterations.append(it)
         self.relres = getattr(self, "relres", []) + [rr]
         if not rr <= max(1e3 * self.rtol, 1e-8):

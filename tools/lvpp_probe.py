@@ -8,12 +8,13 @@ ctx = M.Context(0)
 mesh, h1, l2, ess, b, gi = T._ex4_problem(ctx, 6)
 wl = G.lumped_weights(mesh, l2)
 l1 = lambda v: float(np.sum(wl * np.abs(v)))
-rule = M.PGStepSizeRule(M.PGStepSizeRule.CONSTANT, 1.0)
+rule = M.PGStepSizeRule(2, 0.1, 1e4, 2.0, 1.0)
+kind = sys.argv[1] if len(sys.argv) > 1 else "minres"
 sl = slice(h1["ndofs"], h1["ndofs"] + l2["ndofs"])
-lin = lvpp.DeviceLinear(gi, "condensed", nh=h1["ndofs"], nb=4, rtol=1e-13, maxit=5000)
+lin = lvpp.DeviceLinear(gi, kind, nh=h1["ndofs"], nb=4, rtol=1e-13, maxit=5000)
 x = np.zeros(b.size)
 try:
-    h = lvpp.lvpp_solve(gi, lambda a: gi.fn.set_params([a]), lambda p: gi.set_param_field(2, p), rule, b, x, sl, l1, max_pg=8,
+    h = lvpp.lvpp_solve(gi, lambda a: gi.fn.set_params([a]), lambda p: gi.set_param_field(2, p), rule, b, x, sl, l1, max_pg=30,
                         newton_kw=dict(abs_tol=1e-9, rel_tol=0.0, max_iter=20, linear=lin), log=print)
     print(h)
 except Exception as e:
