@@ -43,3 +43,14 @@ using DiffK4e = DiffusionEnergy<2, 4>;
 MADB_EVAL_INSTANCE("diffusion:4", DiffK4e)
 using DiffMass1e = DiffEnergy<MassEnergy<1>>;
 MADB_EVAL_INSTANCE("diff[mass]", DiffMass1e)
+
+// several equality constraints (std::vector<ADFunction*> eq_con, src/ad_native.hpp:583,648) and two entropies
+// (src/pg.hpp:105-127): statically composed lists
+using Lag2 = LagrangianN<DiffusionEnergy<2, 0>, -1, MinS2, DiffusionEnergy<2, 0>>;
+using AL2 = ALFunctionalN<DiffusionEnergy<2, 0>, -1, MinS2, DiffusionEnergy<2, 0>>;
+using Lag2c1 = LagrangianN<DiffusionEnergy<2, 0>, 1, MinS2, DiffusionEnergy<2, 0>>;
+MADB_EVAL_INSTANCE("lagrangian:-1[diffusion:0,minsurf,diffusion:0]", Lag2)
+MADB_EVAL_INSTANCE("lagrangian:1[diffusion:0,minsurf,diffusion:0]", Lag2c1)
+MADB_EVAL_INSTANCE("al:-1[diffusion:0,minsurf,diffusion:0]", AL2)
+using PG2ObsFDHell = PGFunctional2<ObstacleEnergy<2>, FermiDiracEntropy, 0, Hell2, 1>;
+MADB_EVAL_INSTANCE("pg:0,1[obstacle,fermidirac,hellinger]", PG2ObsFDHell)

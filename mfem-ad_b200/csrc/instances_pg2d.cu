@@ -25,3 +25,15 @@ MADB_INSTANCE("pg:0[gradobstacle,hellinger]", PGGrad, Ex5o2, false)
 // ex5.cpp:114-117: the Hellinger bound as a spatial coefficient -> a quadrature-function parameter of the entropy
 using PGGradQ = PGFunctional<GradientObstacleEnergy<2>, HellingerEntropy<2, true>, 0>;
 MADB_INSTANCE("pg:0[gradobstacle,hellingerq]", PGGradQ, Ex5o2, false)
+
+// ADEval::QVALUE latent variable (src/ad_intg.hpp:127, quadrature-space unknowns of src/tools.hpp:156-177): H1 p1 primal,
+// one latent value per point of the default 3x3 rule = VALUE on the nodal L2 space of order 2 on the rule's points
+using Ex4q = Config<2, 3, Field<2, 1, EV_VALUE | EV_GRAD>, Field<3, 1, EV_VALUE>, Field<3, 1, EV_VALUE, ROLE_PARAM>>;
+MADB_INSTANCE("pg:0[obstacle,fermidirac]", PGObs, Ex4q, false)
+
+// ADPGFunctional with two entropies (src/pg.hpp:105-127): bound constraint on u (FermiDirac, primal index 0) and gradient
+// bound (Hellinger, primal index 1) on the obstacle energy; H1 p2 x L2 p0 x (L2 p0)^2, previous latents as parameters
+using PG2 = PGFunctional2<ObstacleEnergy<2>, FermiDiracEntropy, 0, HellingerEntropy<2>, 1>;
+using PG2cfg = Config<2, 4, Field<3, 1, EV_VALUE | EV_GRAD>, Field<1, 1, EV_VALUE>, Field<1, 2, EV_VALUE>,
+                      Field<1, 1, EV_VALUE, ROLE_PARAM>, Field<1, 2, EV_VALUE, ROLE_PARAM>>;
+MADB_INSTANCE("pg:0,1[obstacle,fermidirac,hellinger]", PG2, PG2cfg, false)

@@ -20,3 +20,11 @@ using ALDM = ALFunctionalOf<Diff2, MinS2, -1>;
 using Q1L0 = Config<2, 3, Field<2, 1, EV_GRAD>, Field<1, 1, EV_VALUE>>;
 MADB_INSTANCE("lagrangian:-1[diffusion:0,minsurf]", LagDM, Q1L0, true)
 MADB_INSTANCE("al:-1[diffusion:0,minsurf]", ALDM, Q2, true)
+
+// two equality constraints: Lagrangian on H1 order 1 x (L2 order 0)^2 (multipliers as a vector space), augmented
+// Lagrangian on the order-2 space
+using Lag2 = LagrangianN<Diff2, -1, MinS2, Diff2>;
+using AL2 = ALFunctionalN<Diff2, -1, MinS2, Diff2>;
+using Q1L0x2 = Config<2, 3, Field<2, 1, EV_GRAD>, Field<1, 2, EV_VALUE>>;
+MADB_INSTANCE("lagrangian:-1[diffusion:0,minsurf,diffusion:0]", Lag2, Q1L0x2, true)
+MADB_INSTANCE("al:-1[diffusion:0,minsurf,diffusion:0]", AL2, Q2, true)

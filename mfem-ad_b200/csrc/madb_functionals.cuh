@@ -212,59 +212,109 @@ template <class E> struct DiffEnergy
    }
 };
 
-// src/ad_native.hpp:570-621: Lagrangian f(x) + lambda c(x) with ONE equality constraint; inputs [x, lambda].
-// MODE is the reference's eval_mode (-1 full, -2 objective only, 0 the constraint), a structural integer here.
-template <class F, class C, int MODE> struct LagrangianOf
+// Equality constraints c_0 .. c_{k-1} of Lagrangian / ALFunctional (std::vector<ADFunction*> eq_con in the reference), composed
+// statically; parameters of the constraints follow each other.
+template <class... Cs> struct ConList
 {
-   static_assert(F::N_INPUT == C::N_INPUT && F::N_QPRM == 0 && C::N_QPRM == 0, "objective and constraint act on the same x");
-   static constexpr int NF = F::N_INPUT;
-   static constexpr int N_INPUT = NF + 1, N_PARAM = F::N_PARAM + C::N_PARAM, N_QPRM = 0;
+   static constexpr int NC = 0, N_PARAM = 0;
+   MADB_HD void load(const double *) {}
+};
+template <class C0, class... Cs> struct ConList<C0, Cs...>
+{
+   static constexpr int NC = 1 + (int)sizeof...(Cs), N_PARAM = C0::N_PARAM + ConList<Cs...>::N_PARAM;
+   C0 c;
+   ConList<Cs...> rest;
+   MADB_HD void load(const double *p)
+   {
+      c.load(p);
+      rest.load(p + C0::N_PARAM);
+   }
+   /// c_K(x)
+   template <int K, class T> MADB_HD T con(const T *x, const double *qp) const
+   {
+      if constexpr (K == 0) { return c(x, qp); }
+      else { return rest.template con<K - 1>(x, qp); }
+   }
+   /// sum_i c_i(x) lambda_i  (src/ad_native.hpp:617)
+   template <class T> MADB_HD T lagr(const T *x, const T *lambda, const double *qp) const
+   {
+      T r = c(x, qp) * lambda[0];
+      if constexpr (sizeof...(Cs) > 0) { r += rest.lagr(x, lambda + 1, qp); }
+      return r;
+   }
+   /// sum_i c~_i (lambda_i + mu/2 c~_i), c~_i = c_i(x) - rhs_i  (src/ad_native.hpp:684-690)
+   template <class T> MADB_HD T al(const T *x, const double *rhs, const double *lambda, const double mu, const double *qp) const
+   {
+      T cx = c(x, qp) - rhs[0];
+      T r = cx * (lambda[0] + (mu * 0.5) * cx);
+      if constexpr (sizeof...(Cs) > 0) { r += rest.al(x, rhs + 1, lambda + 1, mu, qp); }
+      return r;
+   }
+   template <int K, class T> MADB_HD T al_con(const T *x, const double *rhs, const double *qp) const
+   {
+      if constexpr (K == 0) { return c(x, qp) - rhs[0]; }
+      else { return rest.template al_con<K - 1>(x, rhs + 1, qp); }
+   }
+};
+
+// src/ad_native.hpp:570-621: Lagrangian f(x) + sum_i lambda_i c_i(x); inputs [x, lambda_0 .. lambda_{k-1}].
+// MODE is the reference's eval_mode (-1 full, -2 objective only, i >= 0 constraint i), a structural integer here.
+template <class F, int MODE, class... Cs> struct LagrangianN
+{
+   static_assert(((F::N_INPUT == Cs::N_INPUT) && ...) && F::N_QPRM == 0 && ((Cs::N_QPRM == 0) && ...), "objective and constraints act on the same x");
+   static constexpr int NF = F::N_INPUT, NC = (int)sizeof...(Cs);
+   static_assert(MODE < NC, "eval_mode: constraint index out of range");
+   static constexpr int N_INPUT = NF + NC, N_PARAM = F::N_PARAM + ConList<Cs...>::N_PARAM, N_QPRM = 0;
    F f;
-   C c;
+   ConList<Cs...> cons;
    MADB_HD void load(const double *p)
    {
       f.load(p);
-      c.load(p + F::N_PARAM);
+      cons.load(p + F::N_PARAM);
    }
    template <class T> MADB_HD T operator()(const T *x_and_lambda, const double *qp) const
    {
-      if constexpr (MODE >= 0) { return c(x_and_lambda, qp); }
+      if constexpr (MODE >= 0) { return cons.template con<MODE>(x_and_lambda, qp); }
       else
       {
          T result = f(x_and_lambda, qp);
          if constexpr (MODE == -2) { return result; }
-         else { return result + c(x_and_lambda, qp) * x_and_lambda[NF]; }
+         else { return result + cons.lagr(x_and_lambda, x_and_lambda + NF, qp); }
       }
    }
 };
+template <class F, class C, int MODE> using LagrangianOf = LagrangianN<F, MODE, C>;
 
-// src/ad_native.hpp:624-691: augmented Lagrangian f(x) + c~ (lambda + mu/2 c~), c~ = c(x) - rhs, one constraint;
-// parameters [mu, rhs, lambda] (SetPenalty / SetEqRHS / SetLambda), then those of f and c.
-template <class F, class C, int MODE> struct ALFunctionalOf
+// src/ad_native.hpp:624-691: augmented Lagrangian f(x) + sum_i c~_i (lambda_i + mu/2 c~_i), c~_i = c_i(x) - rhs_i;
+// parameters [mu, rhs_0 .., lambda_0 ..] (SetPenalty / SetEqRHS / SetLambda), then those of f and of the constraints.
+template <class F, int MODE, class... Cs> struct ALFunctionalN
 {
-   static_assert(F::N_INPUT == C::N_INPUT && F::N_QPRM == 0 && C::N_QPRM == 0, "objective and constraint act on the same x");
-   static constexpr int N_INPUT = F::N_INPUT, N_PARAM = 3 + F::N_PARAM + C::N_PARAM, N_QPRM = 0;
-   double mu, rhs, lambda;
+   static_assert(((F::N_INPUT == Cs::N_INPUT) && ...) && F::N_QPRM == 0 && ((Cs::N_QPRM == 0) && ...), "objective and constraints act on the same x");
+   static constexpr int NC = (int)sizeof...(Cs);
+   static_assert(MODE < NC, "eval_mode: constraint index out of range");
+   static constexpr int N_INPUT = F::N_INPUT, N_PARAM = 1 + 2 * NC + F::N_PARAM + ConList<Cs...>::N_PARAM, N_QPRM = 0;
+   double mu, rhs[NC], lambda[NC];
    F f;
-   C c;
+   ConList<Cs...> cons;
    MADB_HD void load(const double *p)
    {
-      mu = p[0]; rhs = p[1]; lambda = p[2];
-      f.load(p + 3);
-      c.load(p + 3 + F::N_PARAM);
+      mu = p[0];
+      for (int i = 0; i < NC; i++) { rhs[i] = p[1 + i]; lambda[i] = p[1 + NC + i]; }
+      f.load(p + 1 + 2 * NC);
+      cons.load(p + 1 + 2 * NC + F::N_PARAM);
    }
    template <class T> MADB_HD T operator()(const T *x, const double *qp) const
    {
-      T cx = c(x, qp) - rhs;
-      if constexpr (MODE >= 0) { return cx; }
+      if constexpr (MODE >= 0) { return cons.template al_con<MODE>(x, rhs, qp); }
       else
       {
          T result = f(x, qp);
          if constexpr (MODE == -2) { return result; }
-         else { return result + cx * (lambda + (mu * 0.5) * cx); }
+         else { return result + cons.al(x, rhs, lambda, mu, qp); }
       }
    }
 };
+template <class F, class C, int MODE> using ALFunctionalOf = ALFunctionalN<F, MODE, C>;
 
 // ---------------------------------------------------------------------------
 // Dual entropies (src/pg.hpp:253-376): gradients are the latent->primal maps
@@ -365,6 +415,44 @@ template <class F, class E, int PRIMAL_IDX> struct PGFunctional
       for (int j = 1; j < NE; j++) { cross_entropy += x_psi[PRIMAL_IDX + j] * (psi[j] - psi_k[j]); }
       T dual_entropy_sum = entropy(psi, qp + NE + F::N_QPRM);
       return f(x_psi, qp + NE) + (cross_entropy - dual_entropy_sum) / alpha;
+   }
+};
+
+// ADPGFunctional with TWO entropies (the multi-entropy constructors, src/pg.hpp:105-127, and the loop of :193-213):
+//   L = f(x) + sum_i [ sum_j x[idx_i + j] (psi_i,j - psi_k,i,j) - E*_i(psi_i) ] / alpha,   inputs [x, psi_1, psi_2],
+// per-point parameters [psi_k,1, psi_k,2, those of f, E_1, E_2].  The latent blocks follow each other after the inputs
+// of f (dual_idx[i] = f.n_input + sizes of the earlier entropies).  NOTE: the reference's multi-entropy constructor
+// never fills dual_idx (src/pg.hpp:110: value-initialised to 0), so as written every psi_i aliases the first inputs
+// of f; no driver uses that constructor.  The device (and the oracle) implement the evident intent.
+template <class F, class E1, int IDX1, class E2, int IDX2> struct PGFunctional2
+{
+   static constexpr int NF = F::N_INPUT, NE1 = E1::N_INPUT, NE2 = E2::N_INPUT;
+   static constexpr int N_INPUT = NF + NE1 + NE2, N_PARAM = 1 + F::N_PARAM + E1::N_PARAM + E2::N_PARAM;
+   static constexpr int N_QPRM = NE1 + NE2 + F::N_QPRM + E1::N_QPRM + E2::N_QPRM;
+   static_assert(NF >= IDX1 + NE1 && NF >= IDX2 + NE2, "ADPGFunctional: f.n_input must be larger than primal_begin[i] + dual_entropy.n_input[i]");
+   double alpha;
+   F f;
+   E1 e1;
+   E2 e2;
+   MADB_HD void load(const double *p)
+   {
+      alpha = p[0];
+      f.load(p + 1);
+      e1.load(p + 1 + F::N_PARAM);
+      e2.load(p + 1 + F::N_PARAM + E1::N_PARAM);
+   }
+   template <class T> MADB_HD T operator()(const T *x_psi, const double *qp) const
+   {
+      const T *psi1 = x_psi + NF, *psi2 = x_psi + NF + NE1;
+      const double *pk1 = qp, *pk2 = qp + NE1;
+      T cross_entropy = x_psi[IDX1] * (psi1[0] - pk1[0]);
+#pragma unroll
+      for (int j = 1; j < NE1; j++) { cross_entropy += x_psi[IDX1 + j] * (psi1[j] - pk1[j]); }
+      T dual_entropy_sum = e1(psi1, qp + NE1 + NE2 + F::N_QPRM);
+#pragma unroll
+      for (int j = 0; j < NE2; j++) { cross_entropy += x_psi[IDX2 + j] * (psi2[j] - pk2[j]); }
+      dual_entropy_sum += e2(psi2, qp + NE1 + NE2 + F::N_QPRM + E1::N_QPRM);
+      return f(x_psi, qp + NE1 + NE2) + (cross_entropy - dual_entropy_sum) / alpha;
    }
 };
 

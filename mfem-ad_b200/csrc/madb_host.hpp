@@ -138,6 +138,7 @@ struct LaunchCtx
    const int *color_off; // host, [ncolors+1] sorted-element offsets
    const int *e2n, *vmap, *pmap, *e2csr;
    const double *coords;
+   const double *xe; // 2-D: vertex coordinates per element [4][stride][2] (null otherwise)
    const double *pdata[8];
    const double *qf;
    const double *x, *v;
@@ -236,6 +237,7 @@ struct FieldDesc
    Space *space;
    unsigned mode;
    int role; // ROLE_INPUT / ROLE_PARAM
+   bool qvalue = false; // declared as ADEval::QVALUE (treated as VALUE on the rule's nodal L2 space)
 };
 
 struct Integrator
@@ -264,6 +266,7 @@ struct Integrator
 
    // device data
    int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
+   double *d_xe = nullptr; // 2-D: vertex coordinates per element, [4][stride][2]
    int *d_rowptr = nullptr, *d_colidx = nullptr, *d_perm = nullptr;
    double *d_cvalue = nullptr, *d_cgrad = nullptr, *d_chess = nullptr;
    double *d_energy = nullptr, *d_esum = nullptr;

@@ -37,6 +37,7 @@ template <class Func, class Cfg> struct AsmArgs
    int write_y, write_vals;
    const int *e2n;       // [NGN][stride] vertex ids, lexicographic
    const double *coords; // [nnodes][DIM]
+   const double *xe;     // 2-D: vertex coordinates per element [4][stride][2] (sum-factorised path)
    const int *vmap;      // [NVD][stride] index into x / y (bit 31: first touch)
    const int *pmap;      // [NDOF_ALL-NVD][stride] indices into pdata
    const double *pdata[Cfg::NF]; // parameter-field vectors (null for input fields)
@@ -533,10 +534,24 @@ template <class Cfg, bool ACT> struct Sf2dIn
    double X[4][2];
    double u[ND][ND], vd[ACT ? ND : 1][ACT ? ND : 1];
 };
+#ifndef MADB_SF2D_XE
+#define MADB_SF2D_XE 0 // 1: vertex coordinates from a per-element array (one dependent load less, +32 MB of traffic per assembly of
+                       // config 2): no measurable gain (0.266 vs 0.264 ms), off
+#endif
+/// vertex coordinates of sorted element t (MADB_SF2D_XE: one coalesced 16-byte load per vertex from the per-element array)
 template <class Func, class Cfg, bool ACT>
-__device__ __forceinline__ void sf2d_gather(const AsmArgs<Func, Cfg> &a, const int t, Sf2dIn<Cfg, ACT> &in)
+__device__ __forceinline__ void sf2d_gather_x(const AsmArgs<Func, Cfg> &a, const int t, Sf2dIn<Cfg, ACT> &in)
 {
-   constexpr int ND = Cfg::template field<0>::ND1D, NVD = Cfg::NVD;
+#if MADB_SF2D_XE
+   const double2 *xe = reinterpret_cast<const double2 *>(a.xe);
+#pragma unroll
+   for (int k = 0; k < 4; k++)
+   {
+      const double2 v = __ldg(xe + (size_t)k * a.stride + t);
+      in.X[k][0] = v.x;
+      in.X[k][1] = v.y;
+   }
+#else
 #pragma unroll
    for (int k = 0; k < 4; k++)
    {
@@ -544,6 +559,13 @@ __device__ __forceinline__ void sf2d_gather(const AsmArgs<Func, Cfg> &a, const i
       in.X[k][0] = a.coords[(size_t)n * 2];
       in.X[k][1] = a.coords[(size_t)n * 2 + 1];
    }
+#endif
+}
+template <class Func, class Cfg, bool ACT>
+__device__ __forceinline__ void sf2d_gather(const AsmArgs<Func, Cfg> &a, const int t, Sf2dIn<Cfg, ACT> &in)
+{
+   constexpr int ND = Cfg::template field<0>::ND1D, NVD = Cfg::NVD;
+   sf2d_gather_x<Func, Cfg, ACT>(a, t, in);
 #pragma unroll
    for (int i = 0; i < NVD; i++)
    {

@@ -400,6 +400,12 @@ __device__ __forceinline__ void bb_break(const int never_negative)
                            // gain 10 % (0.223 -> 0.200 ms), the full kernel loses (0.269 -> 0.321 ms): ptxas spills the
                            // prefetched values right after the loads, which stalls the warp until they land
 #endif
+#ifndef MADB_WS_STAGE_U
+#define MADB_WS_STAGE_U 0 // 1: the writer warpgroup gathers the dof values of its compute warpgroup's next patch into shared
+                          // memory while it waits for `full`.  Measured (config 2): 0.298 ms against 0.266 ms without: the
+                          // stalls of the gather prologue are not lost time (the other compute warpgroup has the FP64 pipe
+                          // to itself meanwhile), the gather on the writers' serial path is
+#endif
 #ifndef MADB_WS_PREFETCH_AT
 #define MADB_WS_PREFETCH_AT 2 // block of the matrix phase (0..5 for order 2) before which the values are requested
 #endif
@@ -449,12 +455,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
    constexpr int WG_C0 = WS_WRITER_WG; // first compute warpgroup
    static_assert(WS_WRITER_WG == 2, "writer warpgroup w serves compute warpgroup w");
    extern __shared__ __align__(16) unsigned char smraw[];
-   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blobF[2], bar_blobG[2];
+   __shared__ __align__(8) unsigned long long bar_full[2], bar_empty[2], bar_blobF[2], bar_blobG[2], bar_in_full[2], bar_in_empty[2];
    __shared__ __align__(16) PatchDesc Dd[2][2]; // [warpgroup][patch parity]
    // warpgroup index, made warp-uniform for the compiler (uniform registers instead of spilled vector registers)
    const int wg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 7), 0), tid = threadIdx.x & (PE - 1);
    const bool wy = a.write_y != 0;
-   const int wg_bytes = SR_BYTES + SA_BYTES + P.max_yg + P.max_yf + P.max_vg + P.max_vf;
+   constexpr bool STAGE_U = (MADB_WS_STAGE_U != 0) && use_sf2d<Func, Cfg, MODE>() && !(MADB_WS_PREFETCH) && !(MADB_WS_JOINT);
+   constexpr int U_BYTES = STAGE_U ? patch_al16(NVD * PE * 8) : 0; // staged dof values [NVD][PE]
+   const int o_u = SR_BYTES + SA_BYTES + P.max_yg + P.max_yf + P.max_vg + P.max_vf;
+   const int wg_bytes = o_u + U_BYTES;
    if (threadIdx.x == 0)
    {
       for (int k = 0; k < 2; k++)
@@ -463,6 +472,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          mbar_init(&bar_empty[k], MADB_WS_JOINT ? 2 * PE : PE);
          mbar_init(&bar_blobF[k], 1);
          mbar_init(&bar_blobG[k], 1);
+         mbar_init(&bar_in_full[k], PE);
+         mbar_init(&bar_in_empty[k], PE);
       }
    }
    __syncthreads();
@@ -534,10 +545,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
                load_values(MADB_WS_PREFETCH_AT);
             }
 #else
-            if (valid)
+            if constexpr (STAGE_U)
             {
-               element_compute_sf2d<Func, Cfg, MODE>(
-                  a, t, r, [&](int k, double v) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = v; },
+               // dof values of this patch: gathered by the writer warpgroup into shared memory ([i][element])
+               constexpr int ND1 = Cfg::template field<0>::ND1D;
+               mbar_wait(&bar_in_full[w], it & 1);
+#pragma unroll
+               for (int i = 0; i < NVD; i++) { sf_in.u[i / ND1][i % ND1] = *(const double *)(base + o_u + 8 * (i * PE + tid)); }
+               mbar_arrive(&bar_in_empty[w]);
+               if (valid) { sf2d_gather_x<Func, Cfg, false>(a, t, sf_in); }
+            }
+            else
+            {
+               if (valid) { sf2d_gather<Func, Cfg, false>(a, t, sf_in); }
+            }
+            if (valid && !(P.diag & 2))
+            {
+               element_compute_sf2d_core<Func, Cfg, MODE>(
+                  a, sf_in, r, [&](int k, double v) { *(double *)(base + SR_BYTES + 8 * (k * LD + tid)) = v; },
                   [&]()
                   {
                      // the element vector is final: wait for the buffer and store it before the matrix phase
@@ -607,6 +632,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          if (yg) { bulk_g2s(base + o_yb, P.yblob + (size_t)Dn.yblob_off * 16, yg, &bar_blobG[w]); }
          if (vg) { bulk_g2s(base + o_vb, P.vblob + (size_t)Dn.vblob_off * 16, vg, &bar_blobG[w]); }
       };
+      // dof values of patch pp of compute warpgroup w -> shared memory (thread = element), then `in_full`
+      auto stage_u = [&](const int w, const int pp)
+      {
+         if constexpr (STAGE_U)
+         {
+            unsigned char *ub = smraw + (size_t)w * wg_bytes + o_u;
+            const int t = pp * PE + wtid;
+            const bool live = t < a.end;
+            int idx[NVD];
+#pragma unroll
+            for (int i = 0; i < NVD; i++) { idx[i] = live ? (__ldg(a.vmap + (size_t)i * a.stride + t) & 0x7fffffff) : 0; }
+#pragma unroll
+            for (int i = 0; i < NVD; i++) { *(double *)(ub + 8 * (i * PE + wtid)) = __ldg(a.x + idx[i]); }
+            mbar_arrive(&bar_in_full[w]);
+         }
+      };
+      if constexpr (STAGE_U)
+      {
+         const int p0 = (int)blockIdx.x * 2 + wg;
+         if (p0 < P.npatch) { stage_u(wg, p0); }
+      }
       if (wtid == 0)
       {
          for (int w = JOINT ? 0 : wg; w < (JOINT ? 2 : wg + 1); w++)
@@ -640,6 +686,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
                             : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
+         }
+         if constexpr (STAGE_U)
+         {
+            if (more)
+            {
+               mbar_wait(&bar_in_empty[w], it & 1); // the compute warpgroup has read the values of patch `it`
+               stage_u(w, pn);
+            }
          }
          mbar_wait(&bar_blobF[w], it & 1); // fold lists of this patch
          mbar_wait(&bar_full[w], it & 1);  // the compute warpgroup has staged the patch
@@ -752,7 +806,9 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       if (!done && wv && use_ws && P.vblob)
       {
          auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
-         const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yg + P.max_yf + P.max_vg + P.max_vf) + 16;
+         constexpr bool STAGE_U = (MADB_WS_STAGE_U != 0) && use_sf2d<Func, Cfg, MODE>() && !(MADB_WS_PREFETCH) && !(MADB_WS_JOINT);
+         const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yg + P.max_yf + P.max_vg + P.max_vf +
+                                   (STAGE_U ? patch_al16(Cfg::NVD * PATCH_PE * 8) : 0)) + 16;
          if (nsm == 0) { cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
          if (ws_bytes <= 226 * 1024)
          {

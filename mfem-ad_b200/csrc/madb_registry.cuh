@@ -33,6 +33,7 @@ template <class Func, class Cfg> AsmArgs<Func, Cfg> &fill_args(const LaunchCtx &
    a.write_vals = L.write_vals;
    a.e2n = L.e2n;
    a.coords = L.coords;
+   a.xe = L.xe;
    a.vmap = L.vmap;
    a.pmap = L.pmap;
    for (int f = 0; f < Cfg::NF; f++) { a.pdata[f] = L.pdata[f]; }

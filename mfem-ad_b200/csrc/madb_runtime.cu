@@ -57,7 +57,7 @@ void Functional::flat_params(std::vector<double> &out) const
 
 Integrator::~Integrator()
 {
-   cudaFree(d_e2n); cudaFree(d_vmap); cudaFree(d_pmap); cudaFree(d_e2csr);
+   cudaFree(d_e2n); cudaFree(d_vmap); cudaFree(d_pmap); cudaFree(d_e2csr); cudaFree(d_xe);
    cudaFree(d_rowptr); cudaFree(d_colidx); cudaFree(d_perm); cudaFree(d_cvalue); cudaFree(d_cgrad); cudaFree(d_chess); cudaFree(d_energy); cudaFree(d_esum);
    cudaFree(d_x); cudaFree(d_v); cudaFree(d_v2); cudaFree(d_y); cudaFree(d_vals); cudaFree(d_qf); cudaFree(d_ess);
    for (double *p : d_pstage) { cudaFree(p); }
@@ -213,7 +213,8 @@ static int ensure_pattern_device(Integrator &I);
 int solver_new(Ctx *ctx, int n, long nnz, const int *d_rowptr, const int *d_colidx, madb_solver **out); // madb_solve.cu
 static void release_device_maps(Integrator &I)
 {
-   cudaFree(I.d_e2n); cudaFree(I.d_vmap); cudaFree(I.d_pmap); cudaFree(I.d_perm); cudaFree(I.d_e2csr);
+   cudaFree(I.d_e2n); cudaFree(I.d_vmap); cudaFree(I.d_pmap); cudaFree(I.d_perm); cudaFree(I.d_e2csr); cudaFree(I.d_xe);
+   I.d_xe = nullptr;
    cudaFree(I.d_pdesc); cudaFree(I.d_yblob); cudaFree(I.d_vblob); cudaFree(I.d_ystage); cudaFree(I.d_vstage);
    cudaFree(I.d_rowptr); cudaFree(I.d_colidx);
    I.d_e2n = I.d_vmap = I.d_pmap = I.d_perm = I.d_e2csr = nullptr;
@@ -313,6 +314,23 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
       }
    }
    if (upload(e2n, &I.d_e2n) || upload(vmap, &I.d_vmap) || upload(pmap, &I.d_pmap) || upload(I.perm, &I.d_perm)) { return 2; }
+   static const bool want_xe = getenv("MADB_XE") && atoi(getenv("MADB_XE")) != 0; // only for builds with -DMADB_SF2D_XE=1
+   if (want_xe && I.mesh->dim == 2 && !aos)
+   {
+      // vertex coordinates per element, SoA [4][stride] of (x, y): the sum-factorised 2-D path reads them directly
+      // (one coalesced 16-byte load per vertex) instead of through the element->vertex map (two dependent loads)
+      std::vector<double> xe((size_t)8 * I.stride, 0.0);
+      for (int t = 0; t < I.ne; t++)
+      {
+         for (int k = 0; k < 4; k++)
+         {
+            const int n = I.mesh->e2n[(size_t)I.perm[t] * 4 + k];
+            xe[((size_t)k * I.stride + t) * 2] = I.mesh->coords[(size_t)n * 2];
+            xe[((size_t)k * I.stride + t) * 2 + 1] = I.mesh->coords[(size_t)n * 2 + 1];
+         }
+      }
+      if (upload(xe, &I.d_xe)) { return 2; }
+   }
    if (I.use_patches)
    {
       PatchHost H;
@@ -511,6 +529,7 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
    L.ncolors = (int)I.color_off.size() - 1;
    L.color_off = I.color_off.data();
    L.e2n = I.d_e2n; L.vmap = I.d_vmap; L.pmap = I.d_pmap;
+   L.xe = I.d_xe;
    L.coords = I.mesh->d_coords;
    for (size_t f = 0; f < I.fields.size(); f++)
    {
@@ -931,13 +950,28 @@ extern "C"
       int max_order = 0;
       for (int i = 0; i < nfields; i++)
       {
-         const unsigned m = (unsigned)modes[i];
          // isValidADEval (src/_ad_intg.hpp:55-66) + the modes the reference marks "not yet implemented" (:29-34)
-         if (m & (EV_HESSIAN | EV_DIV | EV_CURL | EV_VECFE | EV_QVALUE))
+         unsigned m = (unsigned)modes[i];
+         if (m & (EV_HESSIAN | EV_DIV | EV_CURL | EV_VECFE))
          {
             delete I;
-            set_error("madb_integrator_create: ADEval modes QVALUE/DIV/CURL/Hessian/VECFE are not supported by the B200 path");
+            set_error("madb_integrator_create: ADEval modes DIV/CURL/Hessian/VECFE are not supported by the B200 path (the reference marks them 'not yet implemented', src/_ad_intg.hpp:29-34)");
             return 1;
+         }
+         // ADEval::QVALUE (src/ad_intg.hpp:127: the shape is the unit vector at ip.index; quadrature-space unknowns,
+         // src/tools.hpp:156-177): exactly VALUE on an L2 space whose nodes are the rule's Gauss points (order nq1d - 1:
+         // a Lagrange basis evaluated at its own nodes is the identity), checked once the rule is known
+         bool qvalue = false;
+         if (m & EV_QVALUE)
+         {
+            if (m & ~(unsigned)(EV_QVALUE | EV_VECTOR))
+            {
+               delete I;
+               set_error("madb_integrator_create: Invalid ADEval mode: QVALUE can only be combined with VECTOR (src/_ad_intg.hpp:55-66)");
+               return 1;
+            }
+            qvalue = true;
+            m = (m & ~(unsigned)EV_QVALUE) | EV_VALUE;
          }
          if (!(m & (EV_VALUE | EV_GRAD))) { delete I; set_error("madb_integrator_create: a field needs VALUE and/or GRAD"); return 1; }
          if (spaces[i]->vdim > 1 && !(m & EV_VECTOR) && (!roles || roles[i] == ROLE_INPUT))
@@ -952,11 +986,22 @@ extern "C"
          fd.space = spaces[i];
          fd.mode = m;
          fd.role = roles ? roles[i] : ROLE_INPUT;
+         fd.qvalue = qvalue;
          I->fields.push_back(fd);
-         if (fd.role == ROLE_INPUT) { max_order = std::max(max_order, spaces[i]->order); }
+         if (fd.role == ROLE_INPUT && !qvalue) { max_order = std::max(max_order, spaces[i]->order); } // a quadrature space has no order
       }
       I->quad_order = quad_order >= 0 ? quad_order : 2 * max_order + 2; // src/_ad_intg.hpp:103-104, :303-312
       I->nq1d = rule_npts_1d(I->quad_order);
+      for (const FieldDesc &fd : I->fields)
+      {
+         if (fd.qvalue && (fd.space->basis != MADB_BASIS_L2 || fd.space->order + 1 != I->nq1d))
+         {
+            delete I;
+            set_error("madb_integrator_create: QVALUE needs a quadrature space: MADB_BASIS_L2 of order " + std::to_string(I->nq1d - 1) +
+                      " (nodes = the " + std::to_string(I->nq1d) + " Gauss points per direction of the rule)");
+            return 1;
+         }
+      }
       std::string key = f->key() + "|d" + std::to_string(I->mesh->dim) + "q" + std::to_string(I->nq1d);
       for (const FieldDesc &fd : I->fields)
       {

@@ -111,13 +111,24 @@ def pg(f, entropy, alpha, primal_idx=0):
 
 
 def lagrangian(f, c, mode=-1):
-    """Lagrangian f(x) + lambda c(x), one equality constraint (src/ad_native.hpp:570-621); inputs [x, lambda]."""
-    return FSpec("lagrangian", f.n_input + 1, [], [mode], [f, c])
+    """Lagrangian f(x) + sum_i lambda_i c_i(x) (src/ad_native.hpp:570-621); c: one constraint or a list; inputs [x, lambda]."""
+    cs = list(c) if isinstance(c, (list, tuple)) else [c]
+    return FSpec("lagrangian", f.n_input + len(cs), [], [mode], [f] + cs)
 
 
 def al(f, c, mu, rhs, lam, mode=-1):
-    """ALFunctional f + c~ (lambda + mu/2 c~), c~ = c - rhs (src/ad_native.hpp:624-691)."""
-    return FSpec("al", f.n_input, [mu, rhs, lam], [mode], [f, c])
+    """ALFunctional f + sum_i c~_i (lambda_i + mu/2 c~_i), c~_i = c_i - rhs_i (src/ad_native.hpp:624-691); c, rhs, lam: one
+    constraint with scalars, or lists of equal length."""
+    cs = list(c) if isinstance(c, (list, tuple)) else [c]
+    rhs = list(rhs) if isinstance(rhs, (list, tuple)) else [rhs]
+    lam = list(lam) if isinstance(lam, (list, tuple)) else [lam]
+    return FSpec("al", f.n_input, [mu] + rhs + lam, [mode], [f] + cs)
+
+
+def pg2(f, e1, idx1, e2, idx2, alpha):
+    """ADPGFunctional with two entropies (src/pg.hpp:105-127, :193-213): inputs [x, psi_1, psi_2], psi_k blocks first in the
+    per-point parameters."""
+    return FSpec("pg", f.n_input + e1.n_input + e2.n_input, [alpha], [idx1, idx2], [f, e1, e2], qoff=0)
 
 
 def lambdapg(f, entropy, alpha, primal_idx=0):

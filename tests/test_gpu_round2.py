@@ -204,3 +204,75 @@ def test_load_vector_matches_oracle_and_closed_form(ctx):
     cnt = np.zeros(s1["ndofs"])
     np.add.at(cnt, np.asarray(s1["e2l"]).reshape(-1), 1.0)
     assert np.max(np.abs(b1 - cnt / 64.0 / 4.0)) <= 1e-15
+
+
+def test_qvalue_latent_on_the_quadrature_space(ctx):
+    """ADEval::QVALUE (src/ad_intg.hpp:127: the shape of a quadrature-space unknown is the unit vector at ip.index;
+    src/tools.hpp:156-177): the device treats it as VALUE on the L2 space whose nodes are the rule's Gauss points; the
+    oracle implements the unit vector literally.  ex4-type PG block, H1 order 1 primal, latent at the 3x3 points."""
+    import mfem_ad_b200 as M
+    mesh = G.cartesian_mesh((9, 8), perturb=0.15)
+    h1 = G.h1_space(mesh, 1, mode=O.VALUE | O.GRAD)
+    lq = G.l2_space(mesh, 2, mode=O.QVALUE)  # 9 dofs per element = the 9 points, x fastest like ip.index
+    fs = S.pg(S.obstacle(2), S.fermidirac(0.0, 0.5), 0.6)
+    psik = np.random.default_rng(4).normal(0, 1, lq["ndofs"])
+    of = O.OracleForm(mesh, [h1, lq], fs.oracle(), quad_order=4, params=[dict(type=O.PRM_GF, size=1, data=psik, space=dict(lq, mode=O.VALUE))])
+    gm = M.Mesh(ctx, mesh)
+    gh, gl = M.Space(ctx, gm, h1), M.Space(ctx, gm, lq)
+    gi = M.Integrator(ctx, [(gh, O.VALUE | O.GRAD), (gl, O.QVALUE), (gl, O.VALUE, M.ROLE_PARAM)], fs.madb(ctx), quad_order=4)
+    gi.set_param_field(2, psik)
+    _compare(of, gi, _block_state(mesh, [h1, lq]))
+    # a space that is not the rule's quadrature space is refused
+    l1 = G.l2_space(mesh, 1, mode=O.QVALUE)
+    with pytest.raises(M.MadbError, match="quadrature space"):
+        M.Integrator(ctx, [(gh, O.VALUE | O.GRAD), (M.Space(ctx, gm, l1), O.QVALUE), (gl, O.VALUE, M.ROLE_PARAM)], fs.madb(ctx), quad_order=4)
+    with pytest.raises(M.MadbError, match="QVALUE can only be combined"):
+        M.Integrator(ctx, [(gh, O.VALUE | O.GRAD), (gl, O.QVALUE | O.VALUE), (gl, O.VALUE, M.ROLE_PARAM)], fs.madb(ctx), quad_order=4)
+
+
+@pytest.mark.parametrize("fs,n,qn", [
+    (S.lagrangian(S.diffusion(2), [S.minsurf(2, 0.5), S.diffusion(2)]), 4, 0),
+    (S.lagrangian(S.diffusion(2), [S.minsurf(2, 0.5), S.diffusion(2)], mode=1), 4, 0),
+    (S.al(S.diffusion(2), [S.minsurf(2, 0.5), S.diffusion(2)], 2.5, [1.2, -0.4], [-0.7, 0.3]), 2, 0),
+    (S.pg2(S.obstacle(2), S.fermidirac(0.0, 0.5), 0, S.hellinger(2, 0.7), 1, 0.6), 6, 3),
+])
+def test_pointwise_multi_constraint_and_multi_entropy(ctx, fs, n, qn):
+    """Several equality constraints (src/ad_native.hpp:583,607-618,648,684-690) and two entropies (src/pg.hpp:105-127)."""
+    rng = np.random.default_rng(7)
+    x = rng.normal(0, 1.2, (48, n))
+    q = rng.normal(0, 1, (48, qn)) if qn else None
+    v, g, h = fs.madb(ctx).eval(x, q)
+    fo = fs.oracle()
+    for p in range(x.shape[0]):
+        qp = None if q is None else q[p]
+        vr, gr, hr = fo.value(x[p], qp), fo.gradient(x[p], qp), fo.hessian(x[p], qp)
+        sc = max(1.0, abs(vr), np.max(np.abs(gr)), np.max(np.abs(hr)))
+        assert abs(v[p] - vr) <= 1e-13 * sc and np.max(np.abs(g[p] - gr)) <= 1e-13 * sc and np.max(np.abs(h[p] - hr)) <= 1e-13 * sc
+
+
+def test_multi_constraint_and_multi_entropy_forms(ctx):
+    mesh = G.cartesian_mesh((13, 9), perturb=0.15)
+    h1 = G.h1_space(mesh, 1, mode=O.GRAD)
+    l0v = G.l2_space(mesh, 0, vdim=2, mode=O.VALUE | O.VECTOR)
+    of, gi = S.make_pair(ctx, mesh, [h1, l0v], S.lagrangian(S.diffusion(2), [S.minsurf(2, 0.5), S.diffusion(2)]))
+    _compare(of, gi, _block_state(mesh, [h1, l0v]))
+    h2 = G.h1_space(mesh, 2, mode=O.GRAD)
+    of, gi = S.make_pair(ctx, mesh, [h2], S.al(S.diffusion(2), [S.minsurf(2, 0.5), S.diffusion(2)], 2.5, [1.2, -0.4], [-0.7, 0.3]))
+    _compare(of, gi, _state(mesh, h2))
+    # two entropies: u in [0, 0.5] (FermiDirac on u) and |grad u| bounded (Hellinger on grad u)
+    import mfem_ad_b200 as M
+    hv = G.h1_space(mesh, 2, mode=O.VALUE | O.GRAD)
+    p1 = G.l2_space(mesh, 0, mode=O.VALUE)
+    p2 = G.l2_space(mesh, 0, vdim=2, mode=O.VALUE | O.VECTOR)
+    fs = S.pg2(S.obstacle(2), S.fermidirac(0.0, 0.5), 0, S.hellinger(2, 0.7), 1, 0.6)
+    rng = np.random.default_rng(3)
+    k1, k2 = rng.normal(0, 1, p1["ndofs"]), rng.normal(0, 1, 2 * p2["ndofs"])
+    of = O.OracleForm(mesh, [hv, p1, p2], fs.oracle(), quad_order=6,
+                      params=[dict(type=O.PRM_GF, size=1, data=k1, space=p1), dict(type=O.PRM_GF, size=2, data=k2, space=p2)])
+    gm = M.Mesh(ctx, mesh)
+    gh, g1, g2 = M.Space(ctx, gm, hv), M.Space(ctx, gm, p1), M.Space(ctx, gm, p2)
+    gi = M.Integrator(ctx, [(gh, O.VALUE | O.GRAD), (g1, O.VALUE), (g2, O.VALUE | O.VECTOR), (g1, O.VALUE, M.ROLE_PARAM),
+                            (g2, O.VALUE | O.VECTOR, M.ROLE_PARAM)], fs.madb(ctx), quad_order=6)
+    gi.set_param_field(3, k1)
+    gi.set_param_field(4, k2)
+    _compare(of, gi, _block_state(mesh, [hv, p1, p2]))
