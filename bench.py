@@ -247,8 +247,14 @@ def run_gpu(args):
             ex.reverse(y)
 
     def step_device():
-        gi.assemble(x, y, vals)
-        exchange()
+        if ex is None:
+            gi.assemble(x, y, vals)
+        else:
+            # residual first, P^T y over NCCL under the interface reduction of the CSR values
+            gi.assemble_begin(x, y, vals)
+            ex.begin(y, True)
+            gi.assemble_end()
+            ex.end(y, True)
 
     def step_e2e():
         gi.assemble(xp.numpy(), yp.numpy(), vp.numpy())
@@ -278,8 +284,7 @@ def run_gpu(args):
         barrier()
         ev0.record(stream)
         for k in range(args.steps):
-            gi.assemble(x, y, vals)
-            exchange()
+            step_device()
         ev1.record(stream)
         barrier()
         ms_total = ev0.elapsed_time(ev1)

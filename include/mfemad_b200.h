@@ -239,6 +239,12 @@ int madb_integrator_pattern(madb_integrator *I, int64_t *nrows, int64_t *nnz, in
 int madb_integrator_grad_assemble(madb_integrator *I, const double *x, double *vals);
 /* residual + Jacobian at the same state in one pass (one Newton iteration's assembly) */
 int madb_integrator_assemble(madb_integrator *I, const double *x, double *y, double *vals);
+/* The same in two steps for parallel runs (device pointers only): _begin launches the element kernel and completes the
+ * residual; the caller then starts the shared-dof exchange of the residual (madb_exchange_begin, P^T of ParNonlinearForm::
+ * Mult, ex4.cpp:136); _end launches the interface reduction (and essential-dof elimination) of the CSR values, which runs
+ * while NCCL moves the residual; madb_exchange_end afterwards.  _end without a pending _begin is a no-op. */
+int madb_integrator_assemble_begin(madb_integrator *I, const double *x, double *y, double *vals);
+int madb_integrator_assemble_end(madb_integrator *I);
 /* DifferentiableCoefficient::Eval and ::Gradient().Eval projected to the rule's points
  * (src/ad_native.hpp:267-323; ex4.cpp:124-128,200: the latent->primal map grad E*(psi) as a
  * QuadratureFunction).  value [ne*nq] and/or grad [ne*nq*n_input] (may be NULL), layout [e][q][.] */

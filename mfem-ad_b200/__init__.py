@@ -95,6 +95,8 @@ def lib():
         L.madb_integrator_grad_assemble.argtypes = [vp, dp, dp]
         L.madb_integrator_assemble.argtypes = [vp, dp, dp, dp]
         L.madb_integrator_grad_mult.argtypes = [vp, dp, dp, dp]
+        L.madb_integrator_assemble_begin.argtypes = [vp, dp, dp, dp]
+        L.madb_integrator_assemble_end.argtypes = [vp]
         L.madb_integrator_coefficient.argtypes = [vp, dp, dp, dp]
         L.madb_solver_create.argtypes = [vp, pp]
         L.madb_solver_destroy.argtypes = [vp]
@@ -327,6 +329,14 @@ class Integrator:
             vals = np.empty(self.nnz) if vals is None else vals
         _check(lib().madb_integrator_assemble(self.h, _ptr(x), _ptr(y), _ptr(vals)))
         return y, vals
+
+    def assemble_begin(self, x, y, vals):
+        """Element kernel + residual complete; the interface reduction of the CSR values is launched by assemble_end()
+        (start the exchange of y in between: it then overlaps that kernel).  Device tensors only."""
+        _check(lib().madb_integrator_assemble_begin(self.h, _ptr(x), _ptr(y), _ptr(vals)))
+
+    def assemble_end(self):
+        _check(lib().madb_integrator_assemble_end(self.h))
 
     def coefficient(self, x, want_value=True, want_grad=True):
         """f and grad f at every quadrature point, [ne, nq] and [ne, nq, n] (DifferentiableCoefficient)."""

@@ -131,6 +131,8 @@ struct PatchDev
                  // element computation
 };
 
+int launch_ifc_v(const PatchDev &P, double *vals, cudaStream_t stream); // madb_ifc.cu
+
 struct LaunchCtx
 {
    cudaStream_t stream;
@@ -155,6 +157,7 @@ struct LaunchCtx
    const double *b1d[8], *g1d[8];
    const double *xq1d, *w1d;
    const PatchDev *patch; // non-null: patch assembly (elements in patch order)
+   int defer_v_ifc;       // 1: the interface reduction of the CSR values is left to launch_ifc_v (madb_integrator_assemble_end)
    cudaEvent_t ev0, ev1;  // non-null: recorded around the element kernel(s) (madb_integrator_set_timing)
 };
 
@@ -267,6 +270,7 @@ struct Integrator
    // device data
    int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
    double *d_xe = nullptr; // 2-D: vertex coordinates per element, [4][stride][2]
+   double *pending_vals = nullptr; // madb_integrator_assemble_begin: CSR values whose interface reduction is still to be launched
    int *d_rowptr = nullptr, *d_colidx = nullptr, *d_perm = nullptr;
    double *d_cvalue = nullptr, *d_cgrad = nullptr, *d_chess = nullptr;
    double *d_energy = nullptr, *d_esum = nullptr;

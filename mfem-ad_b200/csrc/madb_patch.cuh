@@ -840,7 +840,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       ly.stage = P.ystage; ly.out = L.y;
       lv.stage = P.vstage; lv.out = L.vals;
       if (!wy) { ly.n4 = ly.ng = 0; }
-      if (!wv) { lv.n4 = lv.ng = 0; }
+      if (!wv || L.defer_v_ifc) { lv.n4 = lv.ng = 0; }
       const int nb0 = (ly.n4 + 255) / 256, nb1 = nb0 + (ly.ng + 255) / 256, nb2 = nb1 + (lv.n4 + 255) / 256,
                 nb3 = nb2 + (lv.ng + 255) / 256;
       if (nb3 > 0) { k_ifc_reduce<<<nb3, 256, 0, L.stream>>>(ly, lv, nb0, nb1, nb2); }

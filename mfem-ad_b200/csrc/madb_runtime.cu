@@ -518,7 +518,7 @@ static int stage_out_begin(Integrator &I, double *p, size_t n, double **buf, dou
 }
 
 static int run(Integrator &I, int mode, const double *x, const double *v, double *y, double *vals, double *energy,
-               double *cvalue = nullptr, double *cgrad = nullptr, double *chess = nullptr, int coef_variant = 0)
+               double *cvalue = nullptr, double *cgrad = nullptr, double *chess = nullptr, int coef_variant = 0, int defer_v = 0)
 {
    CUDA_OK(cudaSetDevice(I.ctx->device));
    const size_t N = (size_t)I.ntotal;
@@ -603,6 +603,7 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
       L.cvalue = dcv; L.cgrad = dcg; L.chess = dch;
       L.coef_variant = coef_variant;
    }
+   L.defer_v_ifc = (defer_v && L.patch) ? 1 : 0;
    const int rc = I.ops.launch(L, mode);
    if (rc == MADB_RC_MIRROR)
    {
@@ -631,8 +632,9 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
       const int g = (I.ness + 127) / 128;
       if (dy && mode == MODE_ACT) { k_ess_copy<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, v_orig, dy); }
       else if (dy) { k_ess_zero<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, dy); }
-      if (dvals) { k_ess_rowcol<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, I.d_rowptr, I.d_colidx, dvals); }
+      if (dvals && !L.defer_v_ifc) { k_ess_rowcol<<<g, 128, 0, L.stream>>>(I.d_ess, I.ness, I.d_rowptr, I.d_colidx, dvals); }
    }
+   if (L.defer_v_ifc) { I.pending_vals = dvals; }
    bool sync = false;
    if (y && dy != y) { CUDA_OK(cudaMemcpyAsync(y, dy, N * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); sync = true; }
    if (vals && dvals != vals) { CUDA_OK(cudaMemcpyAsync(vals, dvals, I.colidx.size() * sizeof(double), cudaMemcpyDeviceToHost, L.stream)); sync = true; }
@@ -1216,6 +1218,24 @@ extern "C"
          if (is_device_ptr(colidx)) { CUDA_OK(cudaMemcpy(colidx, I->colidx.data(), I->colidx.size() * sizeof(int), cudaMemcpyHostToDevice)); }
          else { std::memcpy(colidx, I->colidx.data(), I->colidx.size() * sizeof(int)); }
       }
+      return 0;
+   }
+   int madb_integrator_assemble_begin(madb_integrator *I, const double *x, double *y, double *vals)
+   {
+      if (!is_device_ptr(vals) || (y && !is_device_ptr(y))) { set_error("madb_integrator_assemble_begin: y and vals must be device pointers"); return 1; }
+      if (I->pending_vals) { set_error("madb_integrator_assemble_begin: the previous assembly was not finished (madb_integrator_assemble_end)"); return 1; }
+      return run(*I, MODE_RES | MODE_JAC, x, nullptr, y, vals, nullptr, nullptr, nullptr, nullptr, 0, 1);
+   }
+   int madb_integrator_assemble_end(madb_integrator *I)
+   {
+      if (!I->pending_vals) { return 0; } // nothing deferred (colour path, or no begin)
+      CUDA_OK(cudaSetDevice(I->ctx->device));
+      double *dvals = I->pending_vals;
+      I->pending_vals = nullptr;
+      const int rc = launch_ifc_v(I->pdev, dvals, I->ctx->stream);
+      if (rc) { set_error(std::string("interface reduction: ") + cudaGetErrorString((cudaError_t)rc)); return 2; }
+      if (I->ness > 0) { k_ess_rowcol<<<(I->ness + 127) / 128, 128, 0, I->ctx->stream>>>(I->d_ess, I->ness, I->d_rowptr, I->d_colidx, dvals); }
+      CUDA_OK(cudaGetLastError());
       return 0;
    }
    int madb_solver_create(madb_integrator *I, madb_solver **out)

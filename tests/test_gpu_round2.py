@@ -276,3 +276,23 @@ def test_multi_constraint_and_multi_entropy_forms(ctx):
     gi.set_param_field(3, k1)
     gi.set_param_field(4, k2)
     _compare(of, gi, _block_state(mesh, [hv, p1, p2]))
+
+
+def test_assemble_begin_end_matches_assemble(ctx):
+    """madb_integrator_assemble_begin / _end (the split used to overlap the shared-dof exchange with the interface
+    reduction of the CSR values): same bits as the one-call assembly, with essential dofs, several patches."""
+    import torch
+    mesh = G.cartesian_mesh((40, 37), perturb=0.15)
+    s = G.h1_space(mesh, 2, mode=O.GRAD)
+    ess = G.boundary_dofs(mesh, s)
+    _, gi = S.make_pair(ctx, mesh, [s], S.minsurf(2, 0.5), ess=ess)
+    x = torch.from_numpy(_state(mesh, s)).cuda()
+    y0, y1 = torch.empty_like(x), torch.empty_like(x)
+    v0 = torch.empty(gi.nnz, dtype=torch.float64, device=x.device)
+    v1 = torch.full_like(v0, -3.0)
+    gi.assemble(x, y0, v0)
+    gi.assemble_begin(x, y1, v1)
+    gi.assemble_end()
+    gi.assemble_end()  # no-op
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1) and torch.equal(v0, v1)
