@@ -270,6 +270,7 @@ struct Integrator
    // device data
    int *d_e2n = nullptr, *d_vmap = nullptr, *d_pmap = nullptr, *d_e2csr = nullptr;
    double *d_xe = nullptr; // 2-D: vertex coordinates per element, [4][stride][2]
+   long untouched_rows = 0; // dofs of the concatenated vector that belong to no element (residual zeroed before assembly then)
    double *pending_vals = nullptr; // madb_integrator_assemble_begin: CSR values whose interface reduction is still to be launched
    int *d_rowptr = nullptr, *d_colidx = nullptr, *d_perm = nullptr;
    double *d_cvalue = nullptr, *d_cgrad = nullptr, *d_chess = nullptr;

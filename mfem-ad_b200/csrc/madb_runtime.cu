@@ -290,6 +290,17 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
       const int e = I.perm[t];
       for (int k = 0; k < ngn; k++) { e2n[aos ? (size_t)t * ngn + k : (size_t)k * I.stride + t] = I.mesh->e2n[(size_t)e * ngn + k]; }
       build_vdofs(I, e, vd);
+      // a dof that appears twice in one element (periodic meshes one or two elements wide, duplicated dof maps) would lose
+      // one contribution on the scatter paths (all loads of an element precede its stores): refuse it loudly
+      {
+         std::vector<int> sv(vd.begin(), vd.begin() + I.nvd);
+         std::sort(sv.begin(), sv.end());
+         if (std::adjacent_find(sv.begin(), sv.end()) != sv.end())
+         {
+            set_error("element " + std::to_string(e) + " lists the same dof twice in its element->dof map: not supported");
+            return 1;
+         }
+      }
       for (int i = 0; i < I.nvd; i++)
       {
          int m = vd[i];
@@ -313,6 +324,10 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
          }
       }
    }
+   // rows no element touches (dofs outside every element of this rank) are never written by the first-touch scatter:
+   // the residual is zeroed before every assembly when such rows exist
+   I.untouched_rows = 0;
+   for (long m = 0; m < I.ntotal; m++) { I.untouched_rows += touched[m] ? 0 : 1; }
    if (upload(e2n, &I.d_e2n) || upload(vmap, &I.d_vmap) || upload(pmap, &I.d_pmap) || upload(I.perm, &I.d_perm)) { return 2; }
    static const bool want_xe = getenv("MADB_XE") && atoi(getenv("MADB_XE")) != 0; // only for builds with -DMADB_SF2D_XE=1
    if (want_xe && I.mesh->dim == 2 && !aos)
@@ -604,6 +619,7 @@ static int run(Integrator &I, int mode, const double *x, const double *v, double
       L.coef_variant = coef_variant;
    }
    L.defer_v_ifc = (defer_v && L.patch) ? 1 : 0;
+   if (I.untouched_rows > 0 && dy && mode != MODE_ENERGY && mode != MODE_COEF) { CUDA_OK(cudaMemsetAsync(dy, 0, N * sizeof(double), L.stream)); }
    const int rc = I.ops.launch(L, mode);
    if (rc == MADB_RC_MIRROR)
    {
@@ -855,6 +871,7 @@ extern "C"
                         double *d_pp, double *d_up)
    {
       CUDA_OK(cudaSetDevice(ctx->device));
+      if (!u || !psi || !psik || !w) { set_error("madb_dofpg_nodal: u, psi, psik and the nodal weights w must be given (zero weights reproduce the reference, SURVEY H7)"); return 1; }
       const std::string key = entropy->key() + "|n1";
       auto it = eval_registry().find(key);
       if (it == eval_registry().end() || !it->second.dofpg)
