@@ -84,6 +84,11 @@ void *madb_ctx_stream(madb_ctx *ctx);
  *   coords [nnodes*dim]  xyzxyz... */
 int madb_mesh_create(madb_ctx *ctx, int dim, int ne, const int32_t *e2n, int nnodes, const double *coords,
                      madb_mesh **out);
+/* Triangles (Mesh::MakeCartesian2D(..., Element::TRIANGLE), ex5.cpp:72-73): e2n [ne*3], affine map of the 3 vertices.
+ * Spaces on such a mesh: H1 orders 1 and 2 (element dofs: the 3 vertices, then the edge midpoints in edge order (0,1),
+ * (1,2), (2,0)), L2 order 0; rules: MFEM's triangle rules of order 0 - 6 (default 2p+2: 6 points for P1, 12 for P2). */
+int madb_mesh_create_simplex(madb_ctx *ctx, int dim, int ne, const int32_t *e2n, int nnodes, const double *coords,
+                             madb_mesh **out);
 int madb_mesh_destroy(madb_mesh *m);
 
 /* FiniteElementSpace view: element -> scalar dof map, basis and vdim.

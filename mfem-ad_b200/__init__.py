@@ -51,6 +51,7 @@ def lib():
         L.madb_ctx_stream.restype = C.c_void_p
         L.madb_ctx_stream.argtypes = [vp]
         L.madb_mesh_create.argtypes = [vp, C.c_int, C.c_int, ip, C.c_int, dp, pp]
+        L.madb_mesh_create_simplex.argtypes = [vp, C.c_int, C.c_int, ip, C.c_int, dp, pp]
         L.madb_mesh_destroy.argtypes = [vp]
         L.madb_space_create.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, pp]
         L.madb_space_destroy.argtypes = [vp]
@@ -159,8 +160,8 @@ class Mesh:
     def __init__(self, ctx, mesh):
         e2n, coords = _i32(mesh["e2n"]), _f64(mesh["coords"])
         h = C.c_void_p()
-        _check(lib().madb_mesh_create(ctx.h, mesh["dim"], e2n.shape[0], e2n.ctypes.data, coords.shape[0],
-                                      coords.ctypes.data, C.byref(h)))
+        create = lib().madb_mesh_create_simplex if mesh.get("simplex") else lib().madb_mesh_create
+        _check(create(ctx.h, mesh["dim"], e2n.shape[0], e2n.ctypes.data, coords.shape[0], coords.ctypes.data, C.byref(h)))
         self.h, self.ctx, self.dim, self.ne = h, ctx, mesh["dim"], e2n.shape[0]
 
     def __del__(self):

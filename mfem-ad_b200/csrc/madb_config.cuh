@@ -43,6 +43,7 @@ template <int I, class T, class... Ts> struct type_at<I, T, Ts...> { using type 
 
 template <int DIM_, int NQ1D_, class... Fs> struct Config
 {
+   static constexpr bool TENSOR = true;
    static constexpr int DIM = DIM_, NQ1D = NQ1D_, NF = sizeof...(Fs);
    static constexpr int NQ = ipow(NQ1D_, DIM_);
    static constexpr int NGN = ipow(2, DIM_); // geometry nodes (order-1 isoparametric map)
@@ -87,6 +88,61 @@ template <int DIM_, int NQ1D_, class... Fs> struct Config
    static constexpr int NVD = voff<NF>();    // element vector size
    static constexpr int NDOF_ALL = doff<NF>(); // gathered dofs incl. parameter fields
    static constexpr int NTAB = toff<NF>();   // sum of nd over fields
+   static constexpr int NSYM = NVD * (NVD + 1) / 2;
+};
+
+// ---- simplex elements (triangles: ex5.cpp:72-73) ------------------------------------------------
+// Non-tensor bases: a field is described by its number of scalar dofs per element (3 for P1, 6 for P2, 1 for the
+// constant), the rule by its number of points (MFEM's triangle rules: 6 points for order 4, 12 for order 6).  Only the
+// table-driven generic element computation applies (no sum factorisation); the geometry is the affine map of the
+// 3 vertices.  Same static interface as Config.
+template <int ND_, int VDIM_, unsigned MODE_, int ROLE_ = ROLE_INPUT> struct SField
+{
+   static constexpr int ND = ND_, ND1D = 0, VDIM = VDIM_, ROLE = ROLE_;
+   static constexpr unsigned MODE = MODE_;
+   static constexpr bool HAS_VALUE = (MODE_ & EV_VALUE) != 0, HAS_GRAD = (MODE_ & EV_GRAD) != 0;
+};
+template <int NQ_, class... Fs> struct SConfig
+{
+   static constexpr bool TENSOR = false;
+   static constexpr int DIM = 2, NQ1D = 0, NF = sizeof...(Fs);
+   static constexpr int NQ = NQ_;
+   static constexpr int NGN = 3;
+   template <int F> using field = typename type_at<F, Fs...>::type;
+   template <int F> static constexpr int nd() { return field<F>::ND; }
+   template <int F> static constexpr int sd() { return (field<F>::HAS_VALUE ? 1 : 0) + (field<F>::HAS_GRAD ? DIM : 0); }
+   template <int F> static constexpr int nslots() { return sd<F>() * field<F>::VDIM; }
+   template <int F> static constexpr bool is_input() { return field<F>::ROLE == ROLE_INPUT; }
+   template <int F> static constexpr int xoff()
+   {
+      if constexpr (F == 0) { return 0; }
+      else { return xoff<F - 1>() + (is_input<F - 1>() ? nslots<F - 1>() : 0); }
+   }
+   template <int F> static constexpr int poff()
+   {
+      if constexpr (F == 0) { return 0; }
+      else { return poff<F - 1>() + (is_input<F - 1>() ? 0 : nslots<F - 1>()); }
+   }
+   template <int F> static constexpr int voff()
+   {
+      if constexpr (F == 0) { return 0; }
+      else { return voff<F - 1>() + (is_input<F - 1>() ? nd<F - 1>() * field<F - 1>::VDIM : 0); }
+   }
+   template <int F> static constexpr int doff()
+   {
+      if constexpr (F == 0) { return 0; }
+      else { return doff<F - 1>() + nd<F - 1>() * field<F - 1>::VDIM; }
+   }
+   template <int F> static constexpr int toff()
+   {
+      if constexpr (F == 0) { return 0; }
+      else { return toff<F - 1>() + nd<F - 1>(); }
+   }
+   static constexpr int N_INPUT = xoff<NF>();
+   static constexpr int N_FIELD_QPRM = poff<NF>();
+   static constexpr int NVD = voff<NF>();
+   static constexpr int NDOF_ALL = doff<NF>();
+   static constexpr int NTAB = toff<NF>();
    static constexpr int NSYM = NVD * (NVD + 1) / 2;
 };
 

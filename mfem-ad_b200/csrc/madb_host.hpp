@@ -201,10 +201,22 @@ struct Mesh
 {
    Ctx *ctx;
    int dim, ne, geom_order, nnodes;
-   std::vector<int> e2n;       // [ne][2^dim] lexicographic
+   bool simplex = false;       // triangles (madb_mesh_create_simplex): 3 vertices per element, affine map
+   std::vector<int> e2n;       // [ne][ngn()]: 2^dim vertices lexicographic, or the dim+1 vertices of a simplex
    std::vector<double> coords; // [nnodes][dim]
    double *d_coords = nullptr;
+   int ngn() const { return simplex ? dim + 1 : (1 << dim); }
 };
+
+// ---- triangles: rules and nodal bases as MFEM defines them (restated; MFEM is not available here) ------------------------
+/// IntRules.Get(Geometry::TRIANGLE, order), orders 0 - 6: points (x, y) on the reference triangle (0,0),(1,0),(0,1),
+/// weights summing to 1/2.  Returns false for orders without a table here.
+bool triangle_rule(int order, std::vector<double> &pts, std::vector<double> &w);
+/// number of scalar dofs of the order-p nodal space on a triangle: H1 p = 1, 2 (vertices, then edge midpoints in edge
+/// order (0,1), (1,2), (2,0)); L2 p = 0 (constant).  0: not available.
+int triangle_ndof(int basis, int order);
+/// shape functions and reference derivatives at (x, y): phi[nd], dphi[nd][2]
+void triangle_shapes(int basis, int order, double x, double y, double *phi, double *dphi);
 
 enum { BASIS_H1 = 0, BASIS_L2 = 1 };
 enum { ORD_BYNODES = 0, ORD_BYVDIM = 1 };
@@ -218,6 +230,7 @@ struct Space
    std::vector<int> e2l; // [ne][(order+1)^dim] lexicographic scalar dof ids
    int nd_el() const
    {
+      if (mesh->simplex) { return triangle_ndof(basis, order); }
       int n = 1;
       for (int d = 0; d < mesh->dim; d++) { n *= (order + 1); }
       return n;
@@ -283,6 +296,7 @@ struct Integrator
    std::vector<double> phi, dphi, gdphi, w;
    std::vector<std::vector<double>> b1d, g1d;
    std::vector<double> xq1d, w1d;
+   std::vector<double> tri_pts; // simplex meshes: reference points of the rule [nq][2]
 
    // patch assembly
    bool use_patches = false;

@@ -90,7 +90,7 @@ static void rcb(std::vector<int> &idx, int lo, int hi, const std::vector<double>
 // Patch order: fills I.perm (sorted position -> element) and I.pdesc[p].ne.
 void patch_order(Integrator &I)
 {
-   const int ne = I.ne, dim = I.mesh->dim, ngn = 1 << dim, pe = I.pe;
+   const int ne = I.ne, dim = I.mesh->dim, ngn = I.mesh->ngn(), pe = I.pe;
    std::vector<double> cen((size_t)ne * 3, 0.0);
    for (int e = 0; e < ne; e++)
    {

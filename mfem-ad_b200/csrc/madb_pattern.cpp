@@ -298,3 +298,99 @@ void build_e2csr(const Integrator &I, const std::vector<int> &color, std::vector
 }
 
 } // namespace madb
+
+// ---------------------------------------------------------------------------------------------
+// Triangles: MFEM's integration rules and nodal bases (restated from the published tables: Strang-Fix / Dunavant points
+// as MFEM's IntegrationRules::TriangleIntegrationRule lists them, point order of AddTriMidPoint / AddTriPoints3 /
+// AddTriPoints6).  tests/test_simplex.py checks the polynomial exactness of every rule, which pins the digits.
+// ---------------------------------------------------------------------------------------------
+namespace madb
+{
+namespace
+{
+void tri_mid(std::vector<double> &p, std::vector<double> &w, double weight)
+{
+   p.push_back(1.0 / 3.0); p.push_back(1.0 / 3.0);
+   w.push_back(weight);
+}
+void tri3(std::vector<double> &p, std::vector<double> &w, double a, double weight)
+{
+   const double b = 1.0 - 2.0 * a;
+   const double xy[3][2] = {{a, a}, {a, b}, {b, a}};
+   for (auto &q : xy) { p.push_back(q[0]); p.push_back(q[1]); w.push_back(weight); }
+}
+void tri6(std::vector<double> &p, std::vector<double> &w, double a, double b, double weight)
+{
+   const double c = 1.0 - a - b;
+   const double xy[6][2] = {{a, b}, {b, a}, {a, c}, {c, a}, {b, c}, {c, b}};
+   for (auto &q : xy) { p.push_back(q[0]); p.push_back(q[1]); w.push_back(weight); }
+}
+} // namespace
+
+bool triangle_rule(int order, std::vector<double> &p, std::vector<double> &w)
+{
+   p.clear();
+   w.clear();
+   switch (order)
+   {
+      case 0:
+      case 1: tri_mid(p, w, 0.5); break;
+      case 2: tri3(p, w, 1.0 / 6.0, 1.0 / 6.0); break;
+      case 3:
+         tri_mid(p, w, -0.28125);
+         tri3(p, w, 0.2, 25.0 / 96.0);
+         break;
+      case 4:
+         tri3(p, w, 0.091576213509770743460, 0.054975871827660933819);
+         tri3(p, w, 0.44594849091596488632, 0.11169079483900573285);
+         break;
+      case 5:
+         tri_mid(p, w, 0.1125);
+         tri3(p, w, 0.10128650732345633880, 0.062969590272413576298);
+         tri3(p, w, 0.47014206410511508977, 0.066197076394253090369);
+         break;
+      case 6:
+         tri3(p, w, 0.063089014491502228340, 0.025422453185103408460);
+         tri3(p, w, 0.24928674517091042129, 0.058393137863189683013);
+         tri6(p, w, 0.053145049844816947353, 0.31035245103378440542, 0.041425537809186787597);
+         break;
+      default: return false;
+   }
+   return true;
+}
+
+int triangle_ndof(int basis, int order)
+{
+   if (basis == BASIS_H1) { return order == 1 ? 3 : (order == 2 ? 6 : 0); }
+   return order == 0 ? 1 : 0;
+}
+
+void triangle_shapes(int basis, int order, double x, double y, double *phi, double *dphi)
+{
+   if (basis != BASIS_H1)
+   {
+      phi[0] = 1.0;
+      dphi[0] = dphi[1] = 0.0;
+      return;
+   }
+   const double l[3] = {1.0 - x - y, x, y};
+   const double dl[3][2] = {{-1.0, -1.0}, {1.0, 0.0}, {0.0, 1.0}};
+   if (order == 1)
+   {
+      for (int i = 0; i < 3; i++) { phi[i] = l[i]; dphi[2 * i] = dl[i][0]; dphi[2 * i + 1] = dl[i][1]; }
+      return;
+   }
+   for (int i = 0; i < 3; i++)
+   {
+      phi[i] = l[i] * (2.0 * l[i] - 1.0);
+      for (int k = 0; k < 2; k++) { dphi[2 * i + k] = (4.0 * l[i] - 1.0) * dl[i][k]; }
+   }
+   const int ed[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+   for (int e = 0; e < 3; e++)
+   {
+      const int a = ed[e][0], b = ed[e][1];
+      phi[3 + e] = 4.0 * l[a] * l[b];
+      for (int k = 0; k < 2; k++) { dphi[2 * (3 + e) + k] = 4.0 * (dl[a][k] * l[b] + l[a] * dl[b][k]); }
+   }
+}
+} // namespace madb

@@ -13,12 +13,14 @@ namespace madb
 
 template <class Cfg> std::string config_key()
 {
-   std::string k = "d" + std::to_string(Cfg::DIM) + "q" + std::to_string(Cfg::NQ1D);
+   // tensor elements: "d<dim>q<points per direction>|<dofs per direction>...."; simplices: "s<dim>q<points>|<dofs per element>...."
+   std::string k = Cfg::TENSOR ? "d" + std::to_string(Cfg::DIM) + "q" + std::to_string(Cfg::NQ1D)
+                               : "s" + std::to_string(Cfg::DIM) + "q" + std::to_string(Cfg::NQ);
    static_for<Cfg::NF>([&](auto F)
    {
       constexpr int fi = decltype(F)::value;
       using Fd = typename Cfg::template field<fi>;
-      k += "|" + std::to_string(Fd::ND1D) + "." + std::to_string(Fd::VDIM) + "." +
+      k += "|" + std::to_string(Cfg::TENSOR ? Fd::ND1D : Cfg::template nd<fi>()) + "." + std::to_string(Fd::VDIM) + "." +
            std::to_string((int)(Fd::MODE & (EV_VALUE | EV_GRAD))) + "." + std::to_string(Fd::ROLE);
    });
    return k;

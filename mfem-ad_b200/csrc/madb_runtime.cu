@@ -279,7 +279,7 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
    }
 
    // device maps in sorted order
-   const int ngn = 1 << dim;
+   const int ngn = I.mesh->ngn();
    std::vector<int> e2n((size_t)ngn * I.stride, 0), vmap((size_t)I.nvd * I.stride, 0),
        pmap((size_t)std::max(I.npd, 1) * I.stride, 0);
    std::vector<unsigned char> touched(I.ntotal, 0);
@@ -364,66 +364,110 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
       P.ny_ifc = (int)(H.dst.size() + H.dst4.size());
    }
 
-   // basis tables at the quadrature points: [q][toff_f + i], x fastest in q and i
-   std::vector<double> xq, wq;
-   gauss_legendre_01(I.nq1d, xq, wq);
-   I.nq = 1;
-   for (int d = 0; d < dim; d++) { I.nq *= I.nq1d; }
-   int ntab = 0;
-   for (const FieldDesc &f : I.fields) { ntab += f.space->nd_el(); }
-   I.phi.assign((size_t)I.nq * ntab, 0.0);
-   I.dphi.assign((size_t)I.nq * ntab * dim, 0.0);
-   I.gdphi.assign((size_t)I.nq * ngn * dim, 0.0);
-   I.w.assign(I.nq, 0.0);
-   auto fill_tables = [&](const std::vector<double> &nodes, int toff, int ncols, double *phi, double *dphi)
+   if (I.mesh->simplex)
    {
-      const int nn = (int)nodes.size();
-      std::vector<double> B, G;
-      lagrange_tables(nodes, xq, B, G);
-      int nd = 1;
-      for (int d = 0; d < dim; d++) { nd *= nn; }
-      for (int q = 0; q < I.nq; q++)
+      // triangles: MFEM's rule of the requested order, nodal P1 / P2 / P0 tables, affine geometry (constant dN/dxi)
+      std::vector<double> pts, wt;
+      if (!triangle_rule(I.quad_order, pts, wt)) { set_error("triangle rules of order 0 - 6 are available, not " + std::to_string(I.quad_order)); return 1; }
+      I.nq = (int)wt.size();
+      int ntab = 0;
+      for (const FieldDesc &f : I.fields) { ntab += f.space->nd_el(); }
+      I.phi.assign((size_t)I.nq * ntab, 0.0);
+      I.dphi.assign((size_t)I.nq * ntab * 2, 0.0);
+      I.gdphi.assign((size_t)I.nq * 3 * 2, 0.0);
+      I.w = wt;
+      I.tri_pts = pts;
+      int toff = 0;
+      I.b1d.assign(I.fields.size(), std::vector<double>(1, 0.0));
+      I.g1d.assign(I.fields.size(), std::vector<double>(1, 0.0));
+      I.xq1d.assign(1, 0.0);
+      I.w1d.assign(1, 0.0);
+      for (const FieldDesc &f : I.fields)
       {
-         int qd[3], r = q;
-         for (int d = 0; d < dim; d++) { qd[d] = r % I.nq1d; r /= I.nq1d; }
-         for (int i = 0; i < nd; i++)
+         const int nd = f.space->nd_el();
+         std::vector<double> ph(nd), dp(2 * nd);
+         for (int q = 0; q < I.nq; q++)
          {
-            int id[3], s = i;
-            for (int d = 0; d < dim; d++) { id[d] = s % nn; s /= nn; }
-            double v = 1.0;
-            for (int d = 0; d < dim; d++) { v *= B[(size_t)qd[d] * nn + id[d]]; }
-            if (phi) { phi[(size_t)q * ncols + toff + i] = v; }
-            for (int k = 0; k < dim; k++)
+            triangle_shapes(f.space->basis, f.space->order, pts[2 * q], pts[2 * q + 1], ph.data(), dp.data());
+            for (int i = 0; i < nd; i++)
             {
-               double g = 1.0;
-               for (int d = 0; d < dim; d++) { g *= (d == k) ? G[(size_t)qd[d] * nn + id[d]] : B[(size_t)qd[d] * nn + id[d]]; }
-               dphi[((size_t)q * ncols + toff + i) * dim + k] = g;
+               I.phi[(size_t)q * ntab + toff + i] = ph[i];
+               I.dphi[((size_t)q * ntab + toff + i) * 2] = dp[2 * i];
+               I.dphi[((size_t)q * ntab + toff + i) * 2 + 1] = dp[2 * i + 1];
             }
          }
+         toff += nd;
       }
-   };
-   int toff = 0;
-   I.b1d.clear(); I.g1d.clear();
-   I.xq1d = xq; I.w1d = wq;
-   for (const FieldDesc &f : I.fields)
-   {
-      std::vector<double> nodes, wtmp;
-      if (f.space->basis == BASIS_H1) { gauss_lobatto_01(f.space->order + 1, nodes); }
-      else { gauss_legendre_01(f.space->order + 1, nodes, wtmp); }
-      fill_tables(nodes, toff, ntab, I.phi.data(), I.dphi.data());
-      toff += f.space->nd_el();
-      std::vector<double> B, Gd;
-      lagrange_tables(nodes, xq, B, Gd);
-      I.b1d.push_back(B);
-      I.g1d.push_back(Gd);
+      for (int q = 0; q < I.nq; q++)
+      {
+         double ph[3], dp[6];
+         triangle_shapes(BASIS_H1, 1, pts[2 * q], pts[2 * q + 1], ph, dp);
+         for (int k = 0; k < 6; k++) { I.gdphi[(size_t)q * 6 + k] = dp[k]; }
+      }
    }
-   fill_tables(std::vector<double> {0.0, 1.0}, 0, ngn, nullptr, I.gdphi.data());
-   for (int q = 0; q < I.nq; q++)
+   else
    {
-      int r = q;
-      double ww = 1.0;
-      for (int d = 0; d < dim; d++) { ww *= wq[r % I.nq1d]; r /= I.nq1d; }
-      I.w[q] = ww;
+      // basis tables at the quadrature points: [q][toff_f + i], x fastest in q and i
+      std::vector<double> xq, wq;
+      gauss_legendre_01(I.nq1d, xq, wq);
+      I.nq = 1;
+      for (int d = 0; d < dim; d++) { I.nq *= I.nq1d; }
+      int ntab = 0;
+      for (const FieldDesc &f : I.fields) { ntab += f.space->nd_el(); }
+      I.phi.assign((size_t)I.nq * ntab, 0.0);
+      I.dphi.assign((size_t)I.nq * ntab * dim, 0.0);
+      I.gdphi.assign((size_t)I.nq * ngn * dim, 0.0);
+      I.w.assign(I.nq, 0.0);
+      auto fill_tables = [&](const std::vector<double> &nodes, int toff, int ncols, double *phi, double *dphi)
+      {
+         const int nn = (int)nodes.size();
+         std::vector<double> B, G;
+         lagrange_tables(nodes, xq, B, G);
+         int nd = 1;
+         for (int d = 0; d < dim; d++) { nd *= nn; }
+         for (int q = 0; q < I.nq; q++)
+         {
+            int qd[3], r = q;
+            for (int d = 0; d < dim; d++) { qd[d] = r % I.nq1d; r /= I.nq1d; }
+            for (int i = 0; i < nd; i++)
+            {
+               int id[3], s = i;
+               for (int d = 0; d < dim; d++) { id[d] = s % nn; s /= nn; }
+               double v = 1.0;
+               for (int d = 0; d < dim; d++) { v *= B[(size_t)qd[d] * nn + id[d]]; }
+               if (phi) { phi[(size_t)q * ncols + toff + i] = v; }
+               for (int k = 0; k < dim; k++)
+               {
+                  double g = 1.0;
+                  for (int d = 0; d < dim; d++) { g *= (d == k) ? G[(size_t)qd[d] * nn + id[d]] : B[(size_t)qd[d] * nn + id[d]]; }
+                  dphi[((size_t)q * ncols + toff + i) * dim + k] = g;
+               }
+            }
+         }
+      };
+      int toff = 0;
+      I.b1d.clear(); I.g1d.clear();
+      I.xq1d = xq; I.w1d = wq;
+      for (const FieldDesc &f : I.fields)
+      {
+         std::vector<double> nodes, wtmp;
+         if (f.space->basis == BASIS_H1) { gauss_lobatto_01(f.space->order + 1, nodes); }
+         else { gauss_legendre_01(f.space->order + 1, nodes, wtmp); }
+         fill_tables(nodes, toff, ntab, I.phi.data(), I.dphi.data());
+         toff += f.space->nd_el();
+         std::vector<double> B, Gd;
+         lagrange_tables(nodes, xq, B, Gd);
+         I.b1d.push_back(B);
+         I.g1d.push_back(Gd);
+      }
+      fill_tables(std::vector<double> {0.0, 1.0}, 0, ngn, nullptr, I.gdphi.data());
+      for (int q = 0; q < I.nq; q++)
+      {
+         int r = q;
+         double ww = 1.0;
+         for (int d = 0; d < dim; d++) { ww *= wq[r % I.nq1d]; r /= I.nq1d; }
+         I.w[q] = ww;
+      }
    }
    I.pdata.assign(I.fields.size(), nullptr);
    I.d_pstage.assign(I.fields.size(), nullptr);
@@ -436,6 +480,8 @@ static int setup_integrator(Integrator &I, bool allow_patches = true)
       const int rc = ensure_pattern_device(I);
       if (rc) { return rc; }
       const long ld = I.pe + 1;
+      int ntab = 0;
+      for (const FieldDesc &f : I.fields) { ntab += f.space->nd_el(); }
       const long tables = ((long)I.nq * ntab * (1 + dim) + (long)I.nq * ngn * dim + I.nq) * 8;
       const long need = patch_al16((int)(I.nvd * ld * 8)) + patch_al16((int)((long)I.nvd * (I.nvd + 1) / 2 * ld * 8)) +
                         I.max_yblob + I.max_vblob + tables + 64;
@@ -722,6 +768,20 @@ extern "C"
       *out = m;
       return 0;
    }
+   int madb_mesh_create_simplex(madb_ctx *ctx, int dim, int ne, const int32_t *e2n, int nnodes, const double *coords,
+                                madb_mesh **out)
+   {
+      if (dim != 2 || ne <= 0 || !e2n || !coords) { set_error("madb_mesh_create_simplex: triangles (dim = 2) only"); return 1; }
+      CUDA_OK(cudaSetDevice(ctx->device));
+      madb_mesh *m = new madb_mesh;
+      m->ctx = ctx; m->dim = dim; m->ne = ne; m->geom_order = 1; m->nnodes = nnodes; m->simplex = true;
+      m->e2n.assign(e2n, e2n + (size_t)ne * (dim + 1));
+      m->coords.assign(coords, coords + (size_t)nnodes * dim);
+      for (int v : m->e2n) { if (v < 0 || v >= nnodes) { delete m; set_error("madb_mesh_create_simplex: vertex id out of range"); return 1; } }
+      if (upload(m->coords, &m->d_coords)) { delete m; return 2; }
+      *out = m;
+      return 0;
+   }
    int madb_mesh_destroy(madb_mesh *m)
    {
       if (m) { cudaFree(m->d_coords); delete m; }
@@ -734,6 +794,11 @@ extern "C"
       if (!mesh || order < 0 || vdim < 1 || ndofs <= 0 || !e2l || (basis != BASIS_H1 && basis != BASIS_L2) || (basis == BASIS_H1 && order < 1))
       {
          set_error("madb_space_create: bad arguments");
+         return 1;
+      }
+      if (mesh->simplex && triangle_ndof(basis, order) == 0)
+      {
+         set_error("madb_space_create: on triangles H1 orders 1, 2 and L2 order 0 are available");
          return 1;
       }
       madb_space *s = new madb_space;
@@ -989,6 +1054,7 @@ extern "C"
                set_error("madb_integrator_create: Invalid ADEval mode: QVALUE can only be combined with VECTOR (src/_ad_intg.hpp:55-66)");
                return 1;
             }
+            if (spaces[i]->mesh->simplex) { delete I; set_error("madb_integrator_create: QVALUE is available on tensor-product elements only"); return 1; }
             qvalue = true;
             m = (m & ~(unsigned)EV_QVALUE) | EV_VALUE;
          }
@@ -1022,9 +1088,15 @@ extern "C"
          }
       }
       std::string key = f->key() + "|d" + std::to_string(I->mesh->dim) + "q" + std::to_string(I->nq1d);
+      if (I->mesh->simplex)
+      {
+         std::vector<double> tp, tw;
+         if (!triangle_rule(I->quad_order, tp, tw)) { const int o = I->quad_order; delete I; set_error("madb_integrator_create: triangle rules of order 0 - 6 are available, not " + std::to_string(o)); return 1; }
+         key = f->key() + "|s2q" + std::to_string(tw.size());
+      }
       for (const FieldDesc &fd : I->fields)
       {
-         key += "|" + std::to_string(fd.space->order + 1) + "." + std::to_string(fd.space->vdim) + "." +
+         key += "|" + std::to_string(I->mesh->simplex ? fd.space->nd_el() : fd.space->order + 1) + "." + std::to_string(fd.space->vdim) + "." +
                 std::to_string((int)(fd.mode & (EV_VALUE | EV_GRAD))) + "." + std::to_string(fd.role);
       }
       // One vector space with ADEval::VECTOR = ADNonlinearFormIntegrator<...|VECTOR>: the reference's single-space
@@ -1297,9 +1369,27 @@ extern "C"
       // (src/ad_native.hpp:56-61, src/ad_native.cpp:132-165) are sampled before they are handed over as a
       // QuadratureFunction (madb_integrator_set_param_qf)
       const Mesh &M = *I->mesh;
-      const int dim = M.dim, ngn = 1 << dim, nq = I->nq, nq1 = I->nq1d;
+      const int dim = M.dim, ngn = M.ngn(), nq = I->nq, nq1 = I->nq1d;
       std::vector<double> out((size_t)I->ne * nq * dim);
-      for (int e = 0; e < I->ne; e++)
+      if (M.simplex)
+      {
+         for (int e = 0; e < I->ne; e++)
+         {
+            for (int q = 0; q < nq; q++)
+            {
+               const double xi = I->tri_pts[2 * q], eta = I->tri_pts[2 * q + 1], N[3] = {1.0 - xi - eta, xi, eta};
+               double *o = &out[((size_t)e * nq + q) * 2];
+               o[0] = o[1] = 0.0;
+               for (int k = 0; k < 3; k++)
+               {
+                  const double *X = &M.coords[(size_t)M.e2n[(size_t)e * 3 + k] * 2];
+                  o[0] += N[k] * X[0];
+                  o[1] += N[k] * X[1];
+               }
+            }
+         }
+      }
+      for (int e = 0; e < (M.simplex ? 0 : I->ne); e++)
       {
          for (int q = 0; q < nq; q++)
          {

@@ -43,7 +43,7 @@ struct Sf2dNone
 /// configurations the sum-factorised 2-D path covers
 template <class Cfg> constexpr bool sf2d_cfg()
 {
-   if constexpr (Cfg::DIM == 2 && Cfg::NF == 1)
+   if constexpr (Cfg::TENSOR && Cfg::DIM == 2 && Cfg::NF == 1)
    {
       using F = typename Cfg::template field<0>;
       return F::VDIM == 1 && F::HAS_GRAD && !F::HAS_VALUE && F::ROLE == ROLE_INPUT;

@@ -63,9 +63,41 @@ def cartesian_mesh(n, lengths=None, perturb=0.0):
     return dict(dim=dim, n=n, lengths=lengths, e2n=e2n, coords=coords, geom_order=1)
 
 
+def triangle_mesh(n, lengths=None, perturb=0.0):
+    """Mesh::MakeCartesian2D(nx, ny, Element::TRIANGLE) (ex5.cpp:72-73): every cell of the nx x ny grid is cut by its
+    (v0, v2) diagonal into the triangles (v0, v1, v2) and (v0, v2, v3).  Returns dict(dim, e2n[ne, 3], coords,
+    geom_order=-1 (the oracle's code for linear simplices), simplex=True, edges[ned, 2], e2e[ne, 3])."""
+    q = cartesian_mesh(n, lengths, perturb)
+    v = q["e2n"]  # [nq, 4] lexicographic: (0,0), (1,0), (0,1), (1,1)
+    tri = np.concatenate([v[:, [0, 1, 3]], v[:, [0, 3, 2]]], axis=1).reshape(-1, 3).astype(np.int32)
+    # edges in MFEM's local order (0,1), (1,2), (2,0), numbered in order of first appearance
+    loc = np.stack([tri[:, [0, 1]], tri[:, [1, 2]], tri[:, [2, 0]]], axis=1)  # [ne, 3, 2]
+    key = np.sort(loc, axis=2).reshape(-1, 2)
+    uniq, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    order = np.argsort(first)
+    rank = np.empty_like(order)
+    rank[order] = np.arange(order.size)
+    e2e = rank[inv.reshape(-1)].reshape(-1, 3).astype(np.int32)
+    edges = uniq[order]
+    return dict(dim=2, n=q["n"], lengths=q["lengths"], e2n=tri, coords=q["coords"], geom_order=-1, simplex=True,
+                edges=edges.astype(np.int32), e2e=e2e)
+
+
+def _tri_h1_space(mesh, p, vdim, ordering, mode):
+    nv = mesh["coords"].shape[0]
+    if p == 1:
+        return dict(basis=0, order=1, vdim=vdim, ordering=ordering, ndofs=nv, e2l=mesh["e2n"].astype(np.int32), mode=mode)
+    if p == 2:
+        e2l = np.concatenate([mesh["e2n"], nv + mesh["e2e"]], axis=1).astype(np.int32)
+        return dict(basis=0, order=2, vdim=vdim, ordering=ordering, ndofs=nv + mesh["edges"].shape[0], e2l=e2l, mode=mode)
+    raise ValueError("triangles: H1 orders 1 and 2")
+
+
 def h1_space(mesh, p, vdim=1, ordering=0, mode=0):
     """Continuous tensor space of order p on a cartesian_mesh; dofs numbered
-    lexicographically on the global (n*p+1)^dim node grid."""
+    lexicographically on the global (n*p+1)^dim node grid.  On a triangle_mesh: P1 (vertices) / P2 (vertices, then edges)."""
+    if mesh.get("simplex"):
+        return _tri_h1_space(mesh, p, vdim, ordering, mode)
     n, dim = mesh["n"], mesh["dim"]
     ng = [k * p + 1 for k in n]
     eg = np.meshgrid(*[np.arange(k) for k in n[::-1]], indexing="ij")
@@ -85,6 +117,8 @@ def h1_space(mesh, p, vdim=1, ordering=0, mode=0):
 
 def l2_space(mesh, p, vdim=1, ordering=0, mode=0):
     ne = mesh["e2n"].shape[0]
+    if mesh.get("simplex") and p != 0:
+        raise ValueError("triangles: L2 order 0")
     nd = (p + 1) ** mesh["dim"]
     e2l = (np.arange(ne, dtype=np.int64)[:, None] * nd + np.arange(nd)[None, :]).astype(np.int32)
     return dict(basis=1, order=p, vdim=vdim, ordering=ordering, ndofs=ne * nd, e2l=e2l, mode=mode)
@@ -125,6 +159,13 @@ def _lagrange(nodes, t):
 
 def dof_coords(mesh, space):
     """Physical coordinates of the scalar dofs (nodes mapped through the vertex map)."""
+    if mesh.get("simplex"):
+        X = mesh["coords"]
+        if space["basis"] == 1:
+            return X[mesh["e2n"]].mean(axis=1)
+        if space["order"] == 1:
+            return X.copy()
+        return np.concatenate([X, 0.5 * (X[mesh["edges"][:, 0]] + X[mesh["edges"][:, 1]])], axis=0)
     dim, p = mesh["dim"], space["order"]
     nodes = gauss_lobatto_01(p + 1) if space["basis"] == 0 else gauss_legendre_01(p + 1)[0]
     N = _lagrange(np.array([0.0, 1.0]), nodes)  # [p+1, 2]
@@ -144,7 +185,7 @@ def dof_coords(mesh, space):
 
 def boundary_dofs(mesh, space, tol=1e-12):
     """Scalar dofs on the boundary of the Cartesian box (by coordinates of the unperturbed grid)."""
-    xc = dof_coords(dict(mesh, coords=cartesian_mesh(mesh["n"], mesh["lengths"])["coords"]), space)
+    xc = dof_coords(dict(mesh, coords=cartesian_mesh(mesh["n"], mesh["lengths"])["coords"]), space)  # same vertices on triangles
     on = np.zeros(space["ndofs"], dtype=bool)
     for d in range(mesh["dim"]):
         on |= (np.abs(xc[:, d]) < tol) | (np.abs(xc[:, d] - mesh["lengths"][d]) < tol)

@@ -581,12 +581,54 @@ static void lagrange_1d(int nn, const double *nodes, double t, double *b, double
 
 enum { BASIS_H1 = 0, BASIS_L2 = 1 };
 
-struct TensorElement // H1_{Segment,Quadrilateral,Hex}Element / L2_* with lexicographic dofs
+// Triangle elements (H1_TriangleElement orders 1, 2; L2_TriangleElement order 0): nodal bases on the reference triangle
+// (0,0), (1,0), (0,1); dofs: vertices, then edge midpoints in MFEM's edge order (0,1), (1,2), (2,0).
+static int tri_dofs(int basis, int p) { return basis == BASIS_H1 ? (p == 1 ? 3 : (p == 2 ? 6 : -1)) : (p == 0 ? 1 : -1); }
+static void tri_shape(int basis, int p, const double *ip, double *shape, double *dshape, int dof)
+{
+   // barycentric coordinates and their gradients
+   const double L[3] = {1.0 - ip[0] - ip[1], ip[0], ip[1]};
+   const double gx[3] = {-1.0, 1.0, 0.0}, gy[3] = {-1.0, 0.0, 1.0};
+   if (basis != BASIS_H1)
+   {
+      if (shape) { shape[0] = 1.0; }
+      if (dshape) { dshape[0] = 0.0; dshape[dof] = 0.0; }
+      return;
+   }
+   for (int v = 0; v < 3; v++)
+   {
+      const double s = (p == 1) ? L[v] : L[v] * (2.0 * L[v] - 1.0);
+      const double d = (p == 1) ? 1.0 : 4.0 * L[v] - 1.0; // ds/dL_v
+      if (shape) { shape[v] = s; }
+      if (dshape) { dshape[v] = d * gx[v]; dshape[v + dof] = d * gy[v]; }
+   }
+   if (p == 2)
+   {
+      for (int e = 0; e < 3; e++)
+      {
+         const int a = e, b = (e + 1) % 3; // edges (0,1), (1,2), (2,0)
+         if (shape) { shape[3 + e] = 4.0 * L[a] * L[b]; }
+         if (dshape)
+         {
+            dshape[3 + e] = 4.0 * (gx[a] * L[b] + L[a] * gx[b]);
+            dshape[3 + e + dof] = 4.0 * (gy[a] * L[b] + L[a] * gy[b]);
+         }
+      }
+   }
+}
+
+struct TensorElement // H1_{Segment,Quadrilateral,Hex}Element / L2_* with lexicographic dofs; or a triangle element
 {
    int dim, p, nn, dof;
+   int simplex = 0, basis_ = 0;
    std::vector<double> nodes;
-   TensorElement(int dim_, int p_, int basis) : dim(dim_), p(p_), nn(p_ + 1)
+   TensorElement(int dim_, int p_, int basis, int simplex_ = 0) : dim(dim_), p(p_), nn(p_ + 1), simplex(simplex_), basis_(basis)
    {
+      if (simplex)
+      {
+         dof = tri_dofs(basis, p_);
+         return;
+      }
       nodes.resize(nn);
       if (basis == BASIS_H1)
       {
@@ -604,6 +646,7 @@ struct TensorElement // H1_{Segment,Quadrilateral,Hex}Element / L2_* with lexico
    // CalcShape: shape[dof]
    void CalcShape(const double *ip, double *shape) const
    {
+      if (simplex) { tri_shape(basis_, p, ip, shape, nullptr, dof); return; }
       std::vector<double> b(3 * nn), db(3 * nn);
       for (int d = 0; d < dim; d++) { lagrange_1d(nn, nodes.data(), ip[d], &b[d * nn], &db[d * nn]); }
       for (int i = 0; i < dof; i++)
@@ -617,6 +660,7 @@ struct TensorElement // H1_{Segment,Quadrilateral,Hex}Element / L2_* with lexico
    // CalcDShape: dshape[dof x dim] column-major
    void CalcDShape(const double *ip, double *dshape) const
    {
+      if (simplex) { tri_shape(basis_, p, ip, nullptr, dshape, dof); return; }
       std::vector<double> b(3 * nn), db(3 * nn);
       for (int d = 0; d < dim; d++) { lagrange_1d(nn, nodes.data(), ip[d], &b[d * nn], &db[d * nn]); }
       for (int i = 0; i < dof; i++)
@@ -634,12 +678,52 @@ struct TensorElement // H1_{Segment,Quadrilateral,Hex}Element / L2_* with lexico
    }
 };
 
-struct IntRule // IntRules.Get(SEGMENT/SQUARE/CUBE, order): tensor Gauss-Legendre
+// IntRules.Get(Geometry::TRIANGLE, order) for orders 0 - 6, restated from the published symmetric rules MFEM's
+// intrules.cpp lists (centroid / 3-point orbits (a, a, 1-2a) / 6-point orbits (a, b, 1-a-b)); weights sum to 1/2.
+// Orbit tables: {kind (1, 3, 6), a, b, weight}
+static const double TRI_RULES[7][4][4] = {
+   {{1, 0, 0, 0.5}},
+   {{1, 0, 0, 0.5}},
+   {{3, 1.0 / 6.0, 0, 1.0 / 6.0}},
+   {{1, 0, 0, -0.28125}, {3, 0.2, 0, 25.0 / 96.0}},
+   {{3, 0.091576213509770743460, 0, 0.054975871827660933819}, {3, 0.44594849091596488632, 0, 0.11169079483900573285}},
+   {{1, 0, 0, 0.1125}, {3, 0.10128650732345633880, 0, 0.062969590272413576298}, {3, 0.47014206410511508977, 0, 0.066197076394253090369}},
+   {{3, 0.063089014491502228340, 0, 0.025422453185103408460}, {3, 0.24928674517091042129, 0, 0.058393137863189683013},
+    {6, 0.053145049844816947353, 0.31035245103378440542, 0.041425537809186787597}}};
+
+struct IntRule // IntRules.Get(SEGMENT/SQUARE/CUBE, order): tensor Gauss-Legendre; TRIANGLE: the tables above
 {
    int dim, n1, np;
    std::vector<double> pts, w; // pts[np*dim]
-   IntRule(int dim_, int order) : dim(dim_)
+   IntRule(int dim_, int order, int simplex = 0) : dim(dim_)
    {
+      if (simplex)
+      {
+         n1 = 0;
+         const int o = std::min(std::max(order, 0), 6);
+         for (int k = 0; k < 4; k++)
+         {
+            const double *r = TRI_RULES[o][k];
+            const int kind = (int)r[0];
+            if (kind == 0) { break; }
+            const double a = r[1], b = r[2], wt = r[3];
+            if (kind == 1) { pts.insert(pts.end(), {1.0 / 3.0, 1.0 / 3.0}); w.push_back(wt); }
+            else if (kind == 3)
+            {
+               const double c = 1.0 - 2.0 * a;
+               pts.insert(pts.end(), {a, a, a, c, c, a});
+               w.insert(w.end(), {wt, wt, wt});
+            }
+            else
+            {
+               const double c = 1.0 - a - b;
+               pts.insert(pts.end(), {a, b, b, a, a, c, c, a, b, c, c, b});
+               w.insert(w.end(), {wt, wt, wt, wt, wt, wt});
+            }
+         }
+         np = (int)w.size();
+         return;
+      }
       const int real_order = order | 1; // GetSegmentRealOrder
       n1 = real_order / 2 + 1;
       std::vector<double> x1(n1), w1(n1);
@@ -771,16 +855,17 @@ struct ElemCtx // per-form scratch: elements, rule, offsets
       return 2 * order + 2;
    }
    ElemCtx(const orc_form_t &F_)
-      : F(F_), dim(F_.mesh.dim), geom(F_.mesh.dim, F_.mesh.geom_order, BASIS_H1),
-        ir(F_.mesh.dim, qorder(F_))
+      : F(F_), dim(F_.mesh.dim), geom(F_.mesh.dim, F_.mesh.geom_order < 0 ? 1 : F_.mesh.geom_order, BASIS_H1, F_.mesh.geom_order < 0),
+        ir(F_.mesh.dim, qorder(F_), F_.mesh.geom_order < 0)
    {
+      const int simplex = F.mesh.geom_order < 0 ? 1 : 0; // mesh.geom_order = -1: triangles (3 vertices, affine map)
       n_input = 0;
       nvd_total = 0;
       goff.push_back(0);
       for (int s = 0; s < F.nspaces; s++)
       {
          const orc_space_t &S = F.spaces[s];
-         els.emplace_back(dim, S.order, S.basis);
+         els.emplace_back(dim, S.order, S.basis, simplex);
          dof.push_back(els.back().dof);
          vdim.push_back(S.vdim);
          sd.push_back(shapedim_of(S.mode, dim));
@@ -796,8 +881,8 @@ struct ElemCtx // per-form scratch: elements, rule, offsets
          poff.push_back(nprm);
          nprm += F.params[i].size;
          const orc_param_t &P = F.params[i];
-         if (P.type == PRM_GF || P.type == PRM_GF_GRAD) { pels.emplace_back(dim, P.space.order, P.space.basis); }
-         else { pels.emplace_back(dim, 0, BASIS_L2); }
+         if (P.type == PRM_GF || P.type == PRM_GF_GRAD) { pels.emplace_back(dim, P.space.order, P.space.basis, simplex); }
+         else { pels.emplace_back(dim, 0, BASIS_L2, simplex); }
       }
    }
    int vdof(int s, int e, int i, int c) const // global index in the concatenated vector
@@ -1293,6 +1378,14 @@ extern "C"
    void orc_gauss_lobatto(int n, double *x) { gauss_lobatto(n, x); }
    int orc_rule_npts_1d(int order) { return (order | 1) / 2 + 1; }
 
+   /// reference points [nq*dim] and weights [nq] of the form's integration rule
+   int orc_form_rule(const orc_form_t *F, double *pts, double *w)
+   {
+      ElemCtx C(*F);
+      for (size_t i = 0; i < C.ir.pts.size(); i++) { pts[i] = C.ir.pts[i]; }
+      for (size_t i = 0; i < C.ir.w.size(); i++) { w[i] = C.ir.w[i]; }
+      return 0;
+   }
    int orc_form_sizes(const orc_form_t *F, int *n_input, int *nvd_el, int *nq, int *ndof_total)
    {
       ElemCtx C(*F);

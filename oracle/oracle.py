@@ -245,6 +245,13 @@ class OracleForm:
         S.mode, S.ordering, S.ndofs = s.get("mode", 0), s.get("ordering", BYNODES), s["ndofs"]
         S.e2l = _ip(e2l)
 
+    def rule(self):
+        """Reference points [nq, dim] and weights [nq] of the form's integration rule."""
+        dim = self.F.mesh.dim
+        pts, w = np.zeros((self.nq, dim)), np.zeros(self.nq)
+        lib().orc_form_rule(C.byref(self.F), _dp(pts), _dp(w))
+        return pts, w
+
     def energy(self, x):
         x = _f64(x)
         return lib().orc_form_energy(C.byref(self.F), _dp(x))
