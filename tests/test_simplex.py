@@ -122,3 +122,72 @@ def test_load_vector_on_triangles(ctx):
         ref = O.OracleForm(mesh, [s], S.load().oracle(), quad_order=2 * p, params=[dict(type=O.PRM_QF, size=1, data=qf)]).mult(np.zeros(s["ndofs"]))
         assert S.csr_rel_err(b, ref) <= 1e-13
     assert abs(b.sum() - 7.5) <= 1e-3  # int 15 sin^2(pi x) = 7.5 (order-4 rule on P2: not exact, close)
+
+
+@pytest.mark.gpu
+def test_ex5_lvpp_on_triangles_iteration_counts(ctx):
+    """The ex5 driver on its own mesh type (ex5.cpp:72-212): gradient-constrained problem, Hellinger entropy with the
+    spatial bound 0.1 + 0.2 x + 0.4 y, load 15 sin^2(pi x), Newton (abs tol 1e-9, 20 iterations) inside the proximal loop;
+    the CUDA assembly and the CPU oracle drive the same loop and must take the same Newton / PG iterations."""
+    import mfem_ad_b200 as M
+    from mfem_ad_b200 import lvpp
+    mesh = G.triangle_mesh((6, 6))
+    u = G.h1_space(mesh, 2, mode=O.GRAD)
+    lat = G.h1_space(mesh, 1, vdim=2, mode=O.VALUE | O.VECTOR)
+    nu, nl = u["ndofs"], 2 * lat["ndofs"]
+    ess = G.boundary_dofs(mesh, u)
+    fs_factory = lambda a: S.pg(S.gradobstacle(2), S.hellinger(2, 0.0, qoff=2), a)
+    gm = M.Mesh(ctx, mesh)
+    gu, gl = M.Space(ctx, gm, u), M.Space(ctx, gm, lat)
+    gfn = fs_factory(1.0).madb(ctx)
+    gi = M.Integrator(ctx, [(gu, O.GRAD), (gl, O.VALUE | O.VECTOR), (gl, O.VALUE | O.VECTOR, M.ROLE_PARAM)], gfn)
+    gi.set_essential(ess)
+    bound = gi.set_param_coefficient(lambda X: 0.1 + 0.2 * X[:, 0] + 0.4 * X[:, 1])
+    b = np.zeros(nu + nl)
+    b[:nu] = M.load_vector(ctx, M.Space(ctx, gm, dict(u, mode=O.VALUE)), lambda p: 15.0 * np.sin(np.pi * p[:, 0]) ** 2)
+    b[ess] = 0.0
+    # lumped P1 weights: a third of the area of every triangle at the vertex
+    X = mesh["coords"][mesh["e2n"]]
+    area = 0.5 * np.abs((X[:, 1, 0] - X[:, 0, 0]) * (X[:, 2, 1] - X[:, 0, 1]) - (X[:, 2, 0] - X[:, 0, 0]) * (X[:, 1, 1] - X[:, 0, 1]))
+    wv = np.zeros(lat["ndofs"])
+    np.add.at(wv, mesh["e2n"].reshape(-1), np.repeat(area / 3.0, 3))
+    l1 = lambda v: float(np.sum(np.tile(wv, 2) * np.abs(v)))
+    rule = M.PGStepSizeRule(M.PGStepSizeRule.EXP, 1.0, 1e4, 2.0)
+    sl = slice(nu, nu + nl)
+    nk = dict(abs_tol=1e-9, rel_tol=0.0, max_iter=20)
+
+    class OracleOp:
+        def __init__(self):
+            self.alpha, self.psik, self._f = 1.0, np.zeros(nl), None
+
+        def form(self):
+            if self._f is None:
+                self._f = O.OracleForm(mesh, [u, lat], fs_factory(self.alpha).oracle(), ess=ess,
+                                       params=[dict(type=O.PRM_GF, size=2, data=self.psik, space=lat), dict(type=O.PRM_QF, size=1, data=bound)])
+            return self._f
+
+        def set_alpha(self, a):
+            self.alpha, self._f = a, None
+
+        def set_latent_k(self, p):
+            self.psik, self._f = p.copy(), None
+
+        def mult(self, x):
+            return self.form().mult(x)
+
+        def grad(self, x):
+            return self.form().grad(x)[2]
+
+        def pattern(self):
+            return self.form().pattern()
+
+    oop = OracleOp()
+    xo = np.zeros(nu + nl)
+    ho = lvpp.lvpp_solve(oop, oop.set_alpha, oop.set_latent_k, rule, b, xo, sl, l1, max_pg=25, tol=1e-8, newton_kw=nk)
+    xg = np.zeros(nu + nl)
+    hg = lvpp.lvpp_solve(gi, lambda a: gfn.set_params([a]), lambda p: gi.set_param_field(2, p), rule, b, xg, sl, l1, max_pg=25, tol=1e-8,
+                         newton_kw=nk)
+    assert not ho["newton_failed"] and not hg["newton_failed"], (ho, hg)
+    assert ho["newton_iterations"] == hg["newton_iterations"] and ho["pg_iterations"] == hg["pg_iterations"]
+    assert np.max(np.abs(xo - xg)) <= 1e-8 * max(1.0, np.max(np.abs(xo)))
+    assert sum(hg["newton_iterations"]) > 5
