@@ -2,9 +2,12 @@
 //   ex0: AD known answers (ex0.cpp:100-163) on the device AD type
 //   ex2: minimal-surface residual/Jacobian on a Cartesian mesh, eps halved between calls (ex2.cpp:94-99)
 //   ex4: one PG block system H1(p+1) x L2(p-1) with FermiDirac entropy (ex4.cpp:99-142)
+//   ex1: LinearForm + DomainLFIntegrator load vector (ex4.cpp:145-148) and one linear solve on the device
+//        (diffusion Jacobian, Jacobi-PCG through madb_solver_pcg instead of UMFPackSolver, ex1.cpp:64-66)
 // Prints checksums that tests/test_gpu_host_cpp.py compares with the Python path.
 //   g++ -std=c++17 examples/ex_assemble.cpp -Lmfem-ad_b200 -lmadb -Wl,-rpath,$PWD/mfem-ad_b200 -o examples/ex_assemble
 #include "../mfem-ad_b200/host/madb.hpp"
+#include <cmath>
 #include <cstdio>
 using namespace madb_host;
 
@@ -61,6 +64,37 @@ int main()
       double s = 0;
       for (double v : K.A) { s += v * v; }
       std::printf("ex4 alpha=%.4f y2=%.17g K2=%.17g nnz=%zu\n", pg.GetAlpha(), dot(y, y), s, K.A.size());
+   }
+   {
+      Mesh mesh = Mesh::MakeCartesian2D(12, 12);
+      FiniteElementSpace fes(mesh, MADB_BASIS_H1, 2);
+      LinearForm b(&fes);
+      b.AddDomainIntegrator([](const double *x) { return 2.0 * M_PI * M_PI * std::sin(M_PI * x[0]) * std::sin(M_PI * x[1]); });
+      b.Assemble();
+      double bs = 0;
+      for (double v : b) { bs += v; }
+      DiffusionEnergy energy(2);
+      NonlinearForm nlf({&fes});
+      nlf.AddDomainIntegrator(new ADNonlinearFormIntegrator<ADEval::GRAD>(energy));
+      std::vector<int> ess;
+      const int ng = 2 * 12 + 1;
+      for (int j = 0; j < ng; j++) { for (int i = 0; i < ng; i++) { if (i == 0 || j == 0 || i == ng - 1 || j == ng - 1) { ess.push_back(j * ng + i); } } }
+      nlf.SetEssentialTrueDofs(ess);
+      for (int d : ess) { b[d] = 0.0; }
+      Vector x(fes.GetVSize(), 0.0);
+      int iters = 0;
+      double relres = 0.0;
+      nlf.SolveGradientPCG(x, b, x, 1e-12, 5000, &iters, &relres); // K(0) u = b on the device
+      double err = 0.0;
+      for (int j = 0; j < ng; j++)
+      {
+         for (int i = 0; i < ng; i++)
+         {
+            const double ex = std::sin(M_PI * i / (ng - 1.0)) * std::sin(M_PI * j / (ng - 1.0));
+            err = std::max(err, std::fabs(x[j * ng + i] - ex));
+         }
+      }
+      std::printf("ex1 bsum=%.17g iters=%d relres=%.3e maxerr=%.3e\n", bs, iters, relres, err);
    }
    return 0;
 }

@@ -31,6 +31,7 @@
 #ifndef MFEMAD_B200_H
 #define MFEMAD_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -73,6 +74,10 @@ int madb_registry_has(const char *key);
 int madb_ctx_create(int device, madb_ctx **out);
 int madb_ctx_destroy(madb_ctx *ctx);
 int madb_ctx_sync(madb_ctx *ctx);
+/* Device memory for hosts that do not link the CUDA runtime themselves (MFEM's own device memory works as well: every
+ * array argument of this API may be a device pointer). */
+int madb_device_alloc(madb_ctx *ctx, size_t bytes, void **ptr);
+int madb_device_free(madb_ctx *ctx, void *ptr);
 /* cudaStream_t of the context, so callers can bracket calls with CUDA events. */
 void *madb_ctx_stream(madb_ctx *ctx);
 

@@ -44,6 +44,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
                 : "memory");
 }
+#ifndef MADB_MBAR_HINT_NS
+#define MADB_MBAR_HINT_NS 0 // suspend-time hint of mbarrier.try_wait (ns): a waiting warp leaves the issue slots to the others
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
 {
    unsigned done = 0;
@@ -51,11 +54,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
    {
       asm volatile("{\n"
                    ".reg .pred p;\n"
+#if MADB_MBAR_HINT_NS > 0
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+#else
                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
                    "selp.u32 %0, 1, 0, p;\n"
                    "}"
                    : "=r"(done)
                    : "r"(smem_u32(bar)), "r"(parity)
+#if MADB_MBAR_HINT_NS > 0
+                     , "r"((unsigned)MADB_MBAR_HINT_NS)
+#endif
                    : "memory");
    }
 }

@@ -753,6 +753,18 @@ extern "C"
       return 0;
    }
    void *madb_ctx_stream(madb_ctx *c) { return (void *)c->stream; }
+   int madb_device_alloc(madb_ctx *c, size_t bytes, void **ptr)
+   {
+      CUDA_OK(cudaSetDevice(c->device));
+      CUDA_OK(cudaMalloc(ptr, bytes > 0 ? bytes : 1));
+      return 0;
+   }
+   int madb_device_free(madb_ctx *c, void *ptr)
+   {
+      CUDA_OK(cudaSetDevice(c->device));
+      CUDA_OK(cudaFree(ptr));
+      return 0;
+   }
 
    int madb_mesh_create(madb_ctx *ctx, int dim, int ne, const int32_t *e2n, int nnodes, const double *coords,
                         madb_mesh **out)

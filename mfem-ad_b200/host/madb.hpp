@@ -281,7 +281,12 @@ class BlockNonlinearForm
    SparseMatrix grad;
 public:
    explicit BlockNonlinearForm(std::vector<FiniteElementSpace *> spaces) : fes(std::move(spaces)) {}
-   ~BlockNonlinearForm() { madb_integrator_destroy(intg); }
+   ~BlockNonlinearForm()
+   {
+      if (solver) { madb_solver_destroy(solver); }
+      if (d_vals) { madb_device_free(Device::Get().ctx, d_vals); }
+      madb_integrator_destroy(intg);
+   }
    /// GridFunction parameters of the functional's Evaluator (e.g. psi_k of ADPGFunctional, src/pg.hpp:106-111)
    void AddParameterSpace(FiniteElementSpace *s) { pfes.push_back(s); }
    template <ADEval... modes> void AddDomainIntegrator(ADBlockNonlinearFormIntegrator<modes...> *bfi)
@@ -313,6 +318,25 @@ public:
       MADB_CALL(madb_integrator_grad_assemble(intg, x.data(), grad.A.data()));
       return grad;
    }
+   /// Newton correction on the device: assembles the Jacobian at x into device memory and solves J(x) c = rhs with
+   /// Jacobi-PCG (madb_solver_pcg; stands where the drivers hand the matrix to UMFPackSolver, ex1.cpp:64-66, ex2.cpp:80);
+   /// the CSR values never reach the host.
+   void SolveGradientPCG(const Vector &x, const Vector &rhs, Vector &c, real_t rtol = 1e-12, int maxit = 10000,
+                         int *iters = nullptr, real_t *relres = nullptr)
+   {
+      fn->Sync();
+      if (!solver) { MADB_CALL(madb_solver_create(intg, &solver)); }
+      int64_t n = 0, nnz = 0;
+      MADB_CALL(madb_integrator_pattern(intg, &n, &nnz, nullptr, nullptr));
+      if (!d_vals) { MADB_VERIFY(madb_device_alloc(Device::Get().ctx, (size_t)nnz * sizeof(double), (void **)&d_vals) == 0, madb_last_error()); }
+      MADB_CALL(madb_integrator_grad_assemble(intg, x.data(), d_vals));
+      Vector sol(c.size() == (size_t)n ? c : Vector((size_t)n, 0.0));
+      MADB_CALL(madb_solver_pcg(solver, d_vals, rhs.data(), sol.data(), rtol, 0.0, maxit, iters, relres));
+      c = sol;
+   }
+private:
+   madb_solver *solver = nullptr;
+   double *d_vals = nullptr;
 };
 typedef BlockNonlinearForm NonlinearForm;
 
