@@ -53,6 +53,15 @@ def _worker(rank, world, port, n, p, out):
         dist.all_reduce(cnt)
         ex.broadcast_from_owner(y)
         err2 = np.max(np.abs(y.numpy() - y_glob[blk["l2g"]])) / np.max(np.abs(y_glob))
+        # the halo route bench.py takes (lowest_rank_owner + halo_lists + HaloExchange, CPU tensors through gloo): same owners,
+        # same values after P^T and P
+        owner = P.lowest_rank_owner(blk["l2g"], blk["candidates"], lspace["ndofs"], rank, world)
+        assert np.array_equal(owner == rank, owned)
+        hx = P.HaloExchange(*P.halo_lists(blk["l2g"], owner, rank, world))
+        y2 = torch.from_numpy(y_loc.copy())
+        hx.reverse(y2)
+        hx.forward(y2)
+        assert torch.equal(y2, y)
         out[rank] = (float(err), float(err2), bool(torch.all(cnt == 1.0)), len(ex.peers))
     finally:
         dist.destroy_process_group()
