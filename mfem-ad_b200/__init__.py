@@ -498,14 +498,14 @@ def load_vector(ctx, space, f, quad_order=None):
     ex4.cpp:145-148).  f: host callback xyz[npts, dim] -> [npts] sampled at the rule's points
     (Coefficient-type source), or an array [ne, nq] already sampled there.  quad_order None: MFEM's linear-form rule
     (order 2p).  Implemented as the residual of the energy f(x) u (functional "load"): same kernels as every other form."""
-    order = int(space.desc["order"])
-    fn = Functional(ctx, "load")
-    gi = Integrator(ctx, [(space, VALUE)], fn, quad_order=2 * order if quad_order is None else quad_order)
+    order, vdim = int(space.desc["order"]), int(space.desc.get("vdim", 1))
+    fn = Functional(ctx, "load") if vdim == 1 else Functional(ctx, "vload", iparams=[vdim])  # VectorDomainLFIntegrator (ex3.cpp:64-67)
+    gi = Integrator(ctx, [(space, VALUE | (VECTOR if vdim > 1 else 0))], fn, quad_order=2 * order if quad_order is None else quad_order)
     if callable(f):
         gi.set_param_coefficient(f)
     else:
         gi.set_param_qf(np.ascontiguousarray(f, dtype=np.float64))
-    return gi.mult(np.zeros(space.desc["ndofs"]))
+    return gi.mult(np.zeros(space.desc["ndofs"] * vdim))
 
 
 def lvpp_update(ctx, alpha, psi, psik, lambda_prev, w=None):

@@ -74,6 +74,20 @@ struct LoadFunctional
    template <class T> MADB_HD T operator()(const T *x, const double *qp) const { return x[0] * qp[0]; }
 };
 
+// Vector load (f, v) = sum_c f_c(x) u_c on a vector space with ADEval::VALUE | VECTOR: VectorDomainLFIntegrator (ex3.cpp:64-67)
+template <int N> struct VectorLoadFunctional
+{
+   static constexpr int N_INPUT = N, N_PARAM = 0, N_QPRM = N;
+   MADB_HD void load(const double *) {}
+   template <class T> MADB_HD T operator()(const T *x, const double *qp) const
+   {
+      T s = x[0] * qp[0];
+#pragma unroll
+      for (int c = 1; c < N; c++) { s += x[c] * qp[c]; }
+      return s;
+   }
+};
+
 // src/ad_native.hpp:421-481.  KDIM selects the K kind at compile time
 // (0 none, 1 scalar, DIM diagonal, DIM*DIM full, column-major) instead of the
 // per-point size dispatch of the reference.  K is a constant here;

@@ -736,18 +736,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
 // One launch covers the residual rows and the CSR entries: blocks [0,nb0) list A packed, [nb0,nb1) A general,
 // [nb1,nb2) B packed, [nb2,nb3) B general.
 using IfcList = IfcListDev;
-__device__ __forceinline__ void ifc_reduce_packed(const IfcList &L, const int i)
+constexpr int IFC_U = 4; // packed entries per thread: all loads of the batch are independent (the kernel is latency bound)
+__device__ __forceinline__ void ifc_reduce_packed(const IfcList &L, const int i0)
 {
-   if (i >= L.n4) { return; }
-   const int4 s = L.src4[i];
-   const int d = L.dst4[i];
-   const double a0 = L.stage[s.x], a1 = (s.y >= 0) ? L.stage[s.y] : 0.0, a2 = (s.z >= 0) ? L.stage[s.z] : 0.0,
-                a3 = (s.w >= 0) ? L.stage[s.w] : 0.0;
-   double v = a0;
-   if (s.y >= 0) { v += a1; }
-   if (s.z >= 0) { v += a2; }
-   if (s.w >= 0) { v += a3; }
-   L.out[d] = v;
+   int4 s[IFC_U];
+   int d[IFC_U];
+   double a[IFC_U][4];
+#pragma unroll
+   for (int u = 0; u < IFC_U; u++)
+   {
+      const int i = i0 + u * 256;
+      const bool live = i < L.n4;
+      s[u] = live ? __ldg(L.src4 + i) : make_int4(-1, -1, -1, -1);
+      d[u] = live ? __ldg(L.dst4 + i) : -1;
+   }
+#pragma unroll
+   for (int u = 0; u < IFC_U; u++)
+   {
+      a[u][0] = (s[u].x >= 0) ? L.stage[s[u].x] : 0.0;
+      a[u][1] = (s[u].y >= 0) ? L.stage[s[u].y] : 0.0;
+      a[u][2] = (s[u].z >= 0) ? L.stage[s[u].z] : 0.0;
+      a[u][3] = (s[u].w >= 0) ? L.stage[s[u].w] : 0.0;
+   }
+#pragma unroll
+   for (int u = 0; u < IFC_U; u++)
+   {
+      if (d[u] < 0) { continue; }
+      double v = a[u][0]; // ascending patch order, exactly the sources that exist (x + 0.0 is not always x: -0.0)
+      if (s[u].y >= 0) { v += a[u][1]; }
+      if (s[u].z >= 0) { v += a[u][2]; }
+      if (s[u].w >= 0) { v += a[u][3]; }
+      L.out[d[u]] = v;
+   }
 }
 __device__ __forceinline__ void ifc_reduce_general(const IfcList &L, const int i)
 {
@@ -761,9 +781,9 @@ static __global__ void __launch_bounds__(256) k_ifc_reduce(const IfcList A, cons
                                                            const int nb2)
 {
    const int blk = blockIdx.x, t = threadIdx.x;
-   if (blk < nb0) { ifc_reduce_packed(A, blk * 256 + t); }
+   if (blk < nb0) { ifc_reduce_packed(A, blk * 256 * IFC_U + t); }
    else if (blk < nb1) { ifc_reduce_general(A, (blk - nb0) * 256 + t); }
-   else if (blk < nb2) { ifc_reduce_packed(B, (blk - nb1) * 256 + t); }
+   else if (blk < nb2) { ifc_reduce_packed(B, (blk - nb1) * 256 * IFC_U + t); }
    else { ifc_reduce_general(B, (blk - nb2) * 256 + t); }
 }
 
@@ -851,8 +871,8 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       lv.stage = P.vstage; lv.out = L.vals;
       if (!wy) { ly.n4 = ly.ng = 0; }
       if (!wv || L.defer_v_ifc) { lv.n4 = lv.ng = 0; }
-      const int nb0 = (ly.n4 + 255) / 256, nb1 = nb0 + (ly.ng + 255) / 256, nb2 = nb1 + (lv.n4 + 255) / 256,
-                nb3 = nb2 + (lv.ng + 255) / 256;
+      const int nb0 = (ly.n4 + 256 * IFC_U - 1) / (256 * IFC_U), nb1 = nb0 + (ly.ng + 255) / 256,
+                nb2 = nb1 + (lv.n4 + 256 * IFC_U - 1) / (256 * IFC_U), nb3 = nb2 + (lv.ng + 255) / 256;
       if (nb3 > 0) { k_ifc_reduce<<<nb3, 256, 0, L.stream>>>(ly, lv, nb0, nb1, nb2); }
    }
    return (int)cudaGetLastError();

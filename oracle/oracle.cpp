@@ -273,9 +273,10 @@ template <class T> T fn_eval(const Ctx &c, int id, const Vec<T> &x)
          return x * x * 0.5;
       case K_EMPTY: // src/_dof_pg.hpp:14
          return zero<T>();
-      case K_LOAD: // linear form (f, v): the gradient of f(x) u is MFEM's DomainLFIntegrator(f) (ex4.cpp:145-148)
+      case K_LOAD: // linear form (f, v): the gradient of sum_c f_c(x) u_c is MFEM's (Vector)DomainLFIntegrator(f) (ex4.cpp:145-148, ex3.cpp:64-67)
       {
          T result = x[0] * (qp ? qp[0] : f.param[0]);
+         for (int c = 1; c < f.n_input; c++) { result += x[c] * (qp ? qp[c] : f.param[c]); }
          return result;
       }
       case K_LAGRANGIAN: // src/ad_native.hpp:607-618

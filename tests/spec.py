@@ -44,6 +44,8 @@ class FSpec:
             kind = "hellingerq"  # the bound is a per-point parameter (ex5.cpp:114-117)
         if kind == "diffusion" and self.qoff >= 0:
             kind = "diffusionq"
+        if kind == "load" and self.n_input > 1:
+            kind = "vload"
         return M.Functional(ctx, kind, params=self.params, iparams=ip, children=ch)
 
 
@@ -68,9 +70,10 @@ def mass(n):
     return FSpec("mass", n)
 
 
-def load():
-    """f(x) u with f the first per-point parameter: its gradient is the load vector (DomainLFIntegrator, ex4.cpp:145-148)."""
-    return FSpec("load", 1, qoff=0)
+def load(n=1):
+    """sum_c f_c(x) u_c with f the first per-point parameters: its gradient is the load vector ((Vector)DomainLFIntegrator,
+    ex4.cpp:145-148, ex3.cpp:64-67)."""
+    return FSpec("load", n, [], [n] if n > 1 else [], qoff=0)
 
 
 def elasticity(dim, lam, mu):

@@ -130,3 +130,30 @@ def test_newton_and_lvpp_iteration_counts_with_device_solves(ctx):
     assert ha["newton_iterations"] == hb["newton_iterations"] and ha["pg_iterations"] == hb["pg_iterations"]
     assert ha["converged"] and hb["converged"] and sum(ha["newton_iterations"]) >= 10
     assert np.max(np.abs(xa - xb)) <= 1e-8 * max(1.0, np.max(np.abs(xa)))
+
+
+def test_ex3_linear_elasticity_with_vector_load_solved_on_device(ctx):
+    """ex3.cpp:37-78: (H1 order 2)^2, LinearElasticityEnergy(lambda = mu = 1), VectorDomainLFIntegrator load (1, 1), one
+    essential boundary side, K(0) x = load: the load vector and the solve on the device against the oracle + SuperLU."""
+    import mfem_ad_b200 as M
+    mesh = G.cartesian_mesh((10, 10))
+    s = G.h1_space(mesh, 2, vdim=2, mode=O.GRAD | O.VECTOR)
+    nd = s["ndofs"]
+    xc = G.dof_coords(mesh, s)
+    side = np.nonzero(np.abs(xc[:, 0]) < 1e-12)[0]  # bdr attribute 4 of MakeCartesian2D (x = 0)
+    ess = np.concatenate([side, side + nd]).astype(np.int32)
+    of, gi = S.make_pair(ctx, mesh, [s], S.elasticity(2, 1.0, 1.0), ess=ess)
+    gm = M.Mesh(ctx, mesh)
+    gs = M.Space(ctx, gm, dict(s, mode=O.VALUE | O.VECTOR))
+    load = M.load_vector(ctx, gs, lambda p: np.ones((p.shape[0], 2)))
+    lref = O.OracleForm(mesh, [dict(s, mode=O.VALUE | O.VECTOR)], S.load(2).oracle(), quad_order=4,
+                        params=[dict(type=O.PRM_QF, size=2, data=np.ones((100, 9, 2)))]).mult(np.zeros(2 * nd))
+    assert S.csr_rel_err(load, lref) <= 1e-13 and abs(load.sum() - 2.0) <= 1e-13
+    load[ess] = 0.0
+    x0 = np.zeros(2 * nd)
+    lin = lvpp.DeviceLinear(gi, "pcg", rtol=1e-13)
+    x = lin.step(x0, -load)  # J(0) c = F(0) - b with F(0) = 0, b = -load  ->  c = K^-1 load
+    rp, ci, vals = of.grad(x0)
+    ref = spla.splu(sp.csr_matrix((vals, ci, rp), shape=(2 * nd,) * 2).tocsc()).solve(load)
+    assert np.max(np.abs(x - ref)) <= 1e-9 * np.max(np.abs(ref))
+    assert 0 < lin.linear_iterations[0] < 3000
