@@ -737,7 +737,7 @@ __device__ __forceinline__ void element_compute_sf2d_core(const AsmArgs<Func, Cf
             }
          }
       }
-
+      mid_matrix(100 + q2); // end of a row of points (hook codes: 0.. block of the matrix phase, 100 + q2, 200 + block: between its two stages)
    }
 
    pre_matrix();
@@ -825,6 +825,7 @@ __device__ __forceinline__ void element_compute_sf2d_core(const AsmArgs<Func, Cf
                   }
                }
             }
+            mid_matrix(200 + j1 * (j1 + 1) / 2 + i1);
 #pragma unroll
             for (int i2 = 0; i2 < ND; i2++)
             {

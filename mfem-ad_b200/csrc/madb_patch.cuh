@@ -410,6 +410,11 @@ __device__ __forceinline__ void bb_break(const int never_negative)
                            // gain 10 % (0.223 -> 0.200 ms), the full kernel loses (0.269 -> 0.321 ms): ptxas spills the
                            // prefetched values right after the loads, which stalls the warp until they land
 #endif
+#ifndef MADB_WS_BLOCK_BB
+#define MADB_WS_BLOCK_BB 1 // bit 0: basic-block boundary between the (i1, j1) blocks of the matrix phase (spills 120 -> 16 B, element
+                           // kernel 0.270 -> 0.248 ms); bit 1: after every row of points (more spills: 0.283 ms); bit 2: between the
+                           // two stages of a block (8 B of spills, no further gain)
+#endif
 #ifndef MADB_WS_STAGE_U
 #define MADB_WS_STAGE_U 0 // 1: the writer warpgroup gathers the dof values of its compute warpgroup's next patch into shared
                           // memory while it waits for `full`.  Measured (config 2): 0.298 ms against 0.266 ms without: the
@@ -527,7 +532,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
             };
             auto load_values = [&](int blk)
             {
-               if (blk != MADB_WS_PREFETCH_AT) { return; }
+               if (blk > 0 && blk < 100 && blk != MADB_WS_PREFETCH_AT && (MADB_WS_BLOCK_BB & 1)) { bb_break(a.stride); }
+               if (blk != MADB_WS_PREFETCH_AT) { return; } // (codes >= 100 are the other hook points)
                bb_break(a.stride);
 #pragma unroll
                for (int k = 0; k < 4; k++) { ldg_nc_f64x2(a.coords + (size_t)nidx[k] * 2, sf_in.X[k][0], sf_in.X[k][1]); }
@@ -580,7 +586,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
                      mbar_wait(&bar_empty[w], par);
 #pragma unroll
                      for (int i = 0; i < NVD; i++) { *(double *)(base + 8 * (i * LD + tid)) = r[i]; }
-                  });
+                  }
+#if MADB_WS_BLOCK_BB
+                  ,
+                  // basic-block boundary between the (i1, j1) blocks of the matrix phase: ptxas then schedules every block
+                  // on its own and does not hoist the constant loads of later blocks (uniform-register pressure)
+                  [&](int code)
+                  {
+                     if (code < 100) { if (code > 0 && (MADB_WS_BLOCK_BB & 1)) { bb_break(a.stride); } }
+                     else if (code < 200) { if (MADB_WS_BLOCK_BB & 2) { bb_break(a.stride); } }
+                     else { if (MADB_WS_BLOCK_BB & 4) { bb_break(a.stride); } }
+                  }
+#endif
+               );
             }
             // threads past the end of the last patch take part in the hand-off like the others: without this wait their
             // arrival on `full` would be counted in the previous, still open phase and the writers could start early
