@@ -57,6 +57,18 @@ template <class Func, class Cfg> struct AsmArgs
    typename Sf2dTabFor<Cfg>::type sf; // 1-D tables of the sum-factorised 2-D path (empty otherwise)
 };
 
+/// Basic-block boundary ptxas cannot remove (the stride is never negative, which it cannot know).  ptxas schedules
+/// inside basic blocks and sinks loads whose results are needed late to the end of theirs: without the boundaries the
+/// map loads and the value loads of the prefetch end up next to each other at the end of the matrix phase.
+__device__ __forceinline__ void bb_break(const int never_negative)
+{
+   for (int k = never_negative; k < 0; k++) { __nanosleep(1); }
+}
+#ifndef MADB_QPOINT_BB
+#define MADB_QPOINT_BB 1 // generic qpoint(): bit 0: boundary between the per-point phase (inputs, AD, pull-back) and the contraction for
+                         // element matrices of more than 12 dofs (config 5: 4.51 -> 4.18 ms; config 4's 8-dof block loses 3 %, so
+                         // small matrices are left alone), bit 1: between the test-function dofs' fields (no further gain)
+#endif
 /// functionals that implement ParamGradient::Eval as written provide param_gradient_as_written(x, qp, J)
 template <class F, class = void> struct has_param_gradient : std::false_type
 {
@@ -420,12 +432,14 @@ __device__ __forceinline__ void qpoint(const AsmArgs<Func, Cfg> &a, const Tables
       }
 
       // ---- test-function contraction: elvect += B g^ ; elmat += B H^ B^T ----------
+      if constexpr ((MADB_QPOINT_BB & 1) != 0 && (MODE & MODE_JAC) != 0 && Cfg::NVD > 12) { bb_break(a.stride); }
       static_for<NF>([&](auto FB)
       {
          constexpr int fb = decltype(FB)::value;
          using Fb = typename Cfg::template field<fb>;
          if constexpr (Cfg::template is_input<fb>())
          {
+            if constexpr ((MADB_QPOINT_BB & 2) != 0 && (MODE & MODE_JAC) != 0 && fb > 0) { bb_break(a.stride); }
             constexpr int ndb = Cfg::template nd<fb>(), sdb = Cfg::template sd<fb>();
             constexpr int tob = Cfg::template toff<fb>(), vob = Cfg::template voff<fb>(), xob = Cfg::template xoff<fb>();
 #pragma unroll

@@ -394,13 +394,6 @@ __device__ __forceinline__ void ldg_nc_f64x2(const double *p, double &v0, double
 {
    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "l"(p));
 }
-/// Basic-block boundary ptxas cannot remove (the stride is never negative, which it cannot know).  ptxas schedules
-/// inside basic blocks and sinks loads whose results are needed late to the end of theirs: without the boundaries the
-/// map loads and the value loads of the prefetch end up next to each other at the end of the matrix phase.
-__device__ __forceinline__ void bb_break(const int never_negative)
-{
-   for (int k = never_negative; k < 0; k++) { __nanosleep(1); }
-}
 #ifndef MADB_WS_JOINT
 #define MADB_WS_JOINT 0 // 1: both writer warpgroups drain one buffer at a time; 0: writer warpgroup w serves compute warpgroup w
                         // (measured on config 2, profiles/r02_k_patch_ws.md: 0.309 ms joint, 0.269 ms separate)
