@@ -403,6 +403,9 @@ __device__ __forceinline__ void ldg_nc_f64x2(const double *p, double &v0, double
                            // gain 10 % (0.223 -> 0.200 ms), the full kernel loses (0.269 -> 0.321 ms): ptxas spills the
                            // prefetched values right after the loads, which stalls the warp until they land
 #endif
+#ifndef MADB_WS_DRAIN_U
+#define MADB_WS_DRAIN_U 4 // independent entries per thread and batch in the drain loops of the writer warpgroups
+#endif
 #ifndef MADB_WS_BLOCK_BB
 #define MADB_WS_BLOCK_BB 1 // bit 0: basic-block boundary between the (i1, j1) blocks of the matrix phase (spills 120 -> 16 B, element
                            // kernel 0.270 -> 0.248 ms); bit 1: after every row of points (more spills: 0.283 ms); bit 2: between the
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          };
          if (!(P.diag & 1))
          {
-            patch_drain<1, WNT, 4>(base, o_sa, o_yb, o_yf, o_vb, o_vf, D, wy, true, wtid, a.y, a.vals, P.ystage, P.vstage, bar_id, after_fold);
+            patch_drain<1, WNT, MADB_WS_DRAIN_U>(base, o_sa, o_yb, o_yf, o_vb, o_vf, D, wy, true, wtid, a.y, a.vals, P.ystage, P.vstage, bar_id, after_fold);
          }
          else { after_fold(); }
          mbar_arrive(&bar_empty[w]);
@@ -747,7 +750,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
 // One launch covers the residual rows and the CSR entries: blocks [0,nb0) list A packed, [nb0,nb1) A general,
 // [nb1,nb2) B packed, [nb2,nb3) B general.
 using IfcList = IfcListDev;
-constexpr int IFC_U = 4; // packed entries per thread: all loads of the batch are independent (the kernel is latency bound)
+#ifndef MADB_IFC_U
+#define MADB_IFC_U 4
+#endif
+constexpr int IFC_U = MADB_IFC_U; // packed entries per thread: all loads of the batch are independent (the kernel is latency bound)
 __device__ __forceinline__ void ifc_reduce_packed(const IfcList &L, const int i0)
 {
    int4 s[IFC_U];
