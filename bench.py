@@ -173,6 +173,30 @@ def workload_config(nx, px, py):
             "l2": "working set per step (CSR values + maps) is > 6x the 126 MB L2; no explicit flush"}
 
 
+def bind_to_gpu_numa(local):
+    """Run this rank (and allocate its pinned host buffers: first touch) on the NUMA node its GPU hangs off; under torchrun
+    all ranks otherwise start on node 0 and the host<->device copies of the end-to-end leg share one memory controller
+    (round-1 record: 51 GB/s at N = 1, 11 GB/s per rank at N = 8).  Best effort: silently does nothing without sysfs."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------
@@ -191,6 +215,7 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa(local) if world > 1 else None
 
     def note(msg):
         if os.environ.get("MADB_BENCH_VERBOSE"):
@@ -355,6 +380,8 @@ def run_gpu(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }
+        if numa_node is not None:
+            out["e2e"]["host_numa_node_rank0"] = numa_node
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             forms = cpu_forms(nx, nx, cores)

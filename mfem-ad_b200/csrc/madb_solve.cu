@@ -406,6 +406,23 @@ __global__ void k_apply_precond(const int nel, const int nh, const double *dinvA
    }
 }
 
+/// The block solvers assume an element-local latent space: row nh + e * nb + i has exactly nb latent columns, nh + e * nb ..
+/// (sorted).  flag[0] is set when a row violates that (an H1 latent space, a different numbering).
+__global__ void k_check_latent_blocks(const int nel, const int nh, const int nb, const int *rowptr, const int *colidx, int *flag)
+{
+   const int r = blockIdx.x * blockDim.x + threadIdx.x;
+   if (r >= nel * nb) { return; }
+   const int row = nh + r, c0 = nh + (r / nb) * nb;
+   int lo = rowptr[row], hi = rowptr[row + 1];
+   const int end = hi;
+   while (lo < hi)
+   {
+      const int m = (lo + hi) >> 1;
+      if (colidx[m] < nh) { lo = m + 1; } else { hi = m; }
+   }
+   if (end - lo != nb || colidx[lo] != c0 || colidx[end - 1] != c0 + nb - 1) { flag[0] = 1; }
+}
+
 bool is_dev(const void *p)
 {
    if (!p) { return false; }
@@ -454,6 +471,24 @@ static void spmv(const Solver &S, cudaStream_t st, int r0, int r1, const double 
       case 32: k_spmv<32><<<RED_BLOCKS, RED_THREADS, 0, st>>>(r0, r1, S.rowptr, S.colidx, vals, w, y, dotw, partial); break;
       default: k_spmv<8><<<RED_BLOCKS, RED_THREADS, 0, st>>>(r0, r1, S.rowptr, S.colidx, vals, w, y, dotw, partial); break;
    }
+}
+
+/// refuses systems whose latent block is not block diagonal with nb x nb element blocks
+static int check_latent_blocks(Solver &S, cudaStream_t st, int nel, int nh, int nb, const char *who)
+{
+   int *flag = reinterpret_cast<int *>(S.work + 9 * (size_t)S.n + 2 * RED_BLOCKS + 8); // behind the CG scalars
+   SOLVE_OK(cudaMemsetAsync(flag, 0, sizeof(int), st));
+   k_check_latent_blocks<<<(nel * nb + 255) / 256, 256, 0, st>>>(nel, nh, nb, S.rowptr, S.colidx, flag);
+   int h = 0;
+   SOLVE_OK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+   SOLVE_OK(cudaStreamSynchronize(st));
+   if (h)
+   {
+      set_error(std::string(who) + ": the unknowns [nh, n) are not an element-local (L2) latent space with nb dofs per element: "
+                                   "the latent block of the Jacobian is not block diagonal");
+      return 1;
+   }
+   return 0;
 }
 
 static int block_solve(const Solver &S, cudaStream_t st, int nel, int nh, int nb, const double *vals, const double *in, double *out, double sign)
@@ -647,6 +682,7 @@ extern "C"
       const int n = S.n, nl = n - nh;
       if (nh <= 0 || nl <= 0 || nb <= 0 || nl % nb != 0) { set_error("madb_solver_condensed_pcg: bad block sizes"); return 1; }
       const int nel = nl / nb;
+      if (check_latent_blocks(S, st, nel, nh, nb, "madb_solver_condensed_pcg")) { return 1; }
       const double *dv, *db, *dx0;
       if (stage_in(S, vals, (size_t)S.nnz, &S.vals_buf, &dv) || stage_in(S, b, (size_t)n, &S.b_buf, &db) || stage_in(S, x, (size_t)n, &S.x_buf, &dx0))
       {
@@ -702,6 +738,7 @@ extern "C"
       const int n = S.n, nl = n - nh;
       if (nh <= 0 || nl <= 0 || nb <= 0 || nl % nb != 0) { set_error("madb_solver_pg_minres: bad block sizes"); return 1; }
       const int nel = nl / nb;
+      if (check_latent_blocks(S, st, nel, nh, nb, "madb_solver_pg_minres")) { return 1; }
       const double *dv, *db, *dx0;
       if (stage_in(S, vals, (size_t)S.nnz, &S.vals_buf, &dv) || stage_in(S, b, (size_t)n, &S.b_buf, &db) || stage_in(S, x, (size_t)n, &S.x_buf, &dx0))
       {

@@ -157,3 +157,14 @@ def test_ex3_linear_elasticity_with_vector_load_solved_on_device(ctx):
     ref = spla.splu(sp.csr_matrix((vals, ci, rp), shape=(2 * nd,) * 2).tocsc()).solve(load)
     assert np.max(np.abs(x - ref)) <= 1e-9 * np.max(np.abs(ref))
     assert 0 < lin.linear_iterations[0] < 3000
+
+
+def test_block_solvers_refuse_a_latent_space_that_is_not_element_local(ctx):
+    import mfem_ad_b200 as M
+    mesh, h1, l2, ess, b, gi = _ex4_problem(ctx, 4)
+    gi.set_param_field(2, np.zeros(l2["ndofs"]))
+    r, vals = gi.assemble(np.zeros(b.size))
+    sol = M.Solver(gi)
+    for fn in (sol.condensed_pcg, sol.pg_minres):
+        with pytest.raises(M.MadbError, match="not block diagonal"):
+            fn(h1["ndofs"], 2, vals, r)  # the latent space has 4 dofs per element, not 2
