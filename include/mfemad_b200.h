@@ -297,7 +297,9 @@ int madb_solver_condensed_pcg(madb_solver *s, int nh, int nb, const double *vals
 /* The same block systems without condensation: preconditioned MINRES on the symmetric indefinite matrix with the block
  * diagonal preconditioner diag(|diag A|, S_e), S_e = D_e + C_e^T diag(A)^-1 C_e per element (the PGPreconditioner idea,
  * src/pg.hpp:378-504, with Jacobi instead of AMG on the primal block).  Robust when the entropy Hessian degenerates
- * (active sets: D -> 0), where the condensed operator becomes a penalty matrix.  Stopping on the preconditioned residual. */
+ * (active sets: D -> 0), where the condensed operator becomes a penalty matrix.  Stopping on the preconditioned residual.
+ * nb = 0 (nh ignored): no block structure, Jacobi preconditioner |diag J|^-1 on all unknowns: any symmetric indefinite
+ * Jacobian, e.g. ex5's system with its H1 latent space. */
 int madb_solver_pg_minres(madb_solver *s, int nh, int nb, const double *vals, const double *b, double *x, double rtol,
                           double atol, int maxit, int *iters, double *relres);
 /* y = A x with the solver's pattern (hand-written CSR kernel, deterministic) */

@@ -735,17 +735,22 @@ extern "C"
       Solver &S = *reinterpret_cast<Solver *>(s);
       SOLVE_OK(cudaSetDevice(S.ctx->device));
       cudaStream_t st = S.ctx->stream;
-      const int n = S.n, nl = n - nh;
-      if (nh <= 0 || nl <= 0 || nb <= 0 || nl % nb != 0) { set_error("madb_solver_pg_minres: bad block sizes"); return 1; }
-      const int nel = nl / nb;
-      if (check_latent_blocks(S, st, nel, nh, nb, "madb_solver_pg_minres")) { return 1; }
+      const int n = S.n;
+      // nb == 0: no block structure is used: Jacobi preconditioner |diag J|^-1 on all unknowns (symmetric indefinite systems
+      // in general, e.g. ex5's H1 latent space)
+      const bool plain = (nb == 0);
+      if (plain) { nh = n; }
+      const int nl = n - nh;
+      if (!plain && (nh <= 0 || nl <= 0 || nb < 0 || nl % nb != 0)) { set_error("madb_solver_pg_minres: bad block sizes"); return 1; }
+      const int nel = plain ? 0 : nl / nb;
+      if (!plain && check_latent_blocks(S, st, nel, nh, nb, "madb_solver_pg_minres")) { return 1; }
       const double *dv, *db, *dx0;
       if (stage_in(S, vals, (size_t)S.nnz, &S.vals_buf, &dv) || stage_in(S, b, (size_t)n, &S.b_buf, &db) || stage_in(S, x, (size_t)n, &S.x_buf, &dx0))
       {
          return 2;
       }
       double *dx = const_cast<double *>(dx0);
-      const size_t need = 8 * (size_t)n + (size_t)nl * nb + 16;
+      const size_t need = 8 * (size_t)n + (size_t)nl * (plain ? 0 : nb) + 16;
       if (S.work2_words < need)
       {
          cudaFree(S.work2);
@@ -761,6 +766,7 @@ extern "C"
          const int grid = RED_BLOCKS;
          switch (nb)
          {
+            case 0:
             case 1: k_apply_precond<1><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
             case 3: k_apply_precond<3><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
             case 4: k_apply_precond<4><<<grid, RED_THREADS, 0, st>>>(nel, nh, dinvA, blocks, v, z); break;
@@ -774,6 +780,7 @@ extern "C"
          const int grid = (nel + 127) / 128;
          switch (nb)
          {
+            case 0: break;
             case 1: k_schur_blocks<1><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
             case 3: k_schur_blocks<3><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;
             case 4: k_schur_blocks<4><<<grid, 128, 0, st>>>(nel, nh, S.rowptr, S.colidx, dv, dinvA, blocks); break;

@@ -38,8 +38,8 @@ class DeviceLinear:
             c, it, rr = self.solver.pcg(self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
         elif self.kind == "condensed":
             c, it, rr = self.solver.condensed_pcg(self.nh, self.nb, self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
-        else:  # "minres": the block system as it is, block-diagonal preconditioner
-            c, it, rr = self.solver.pg_minres(self.nh, self.nb, self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
+        else:  # "minres": the block system as it is, block-diagonal preconditioner (nb = 0: plain Jacobi, any symmetric system)
+            c, it, rr = self.solver.pg_minres(self.nh or 0, self.nb or 0, self.vals, r, c, rtol=self.rtol, maxit=self.maxit)
         self.linear_iterations.append(it)
         self.relres = getattr(self, "relres", []) + [rr]
         if not rr <= max(1e3 * self.rtol, 1e-8):

@@ -191,3 +191,12 @@ def test_ex5_lvpp_on_triangles_iteration_counts(ctx):
     assert ho["newton_iterations"] == hg["newton_iterations"] and ho["pg_iterations"] == hg["pg_iterations"]
     assert np.max(np.abs(xo - xg)) <= 1e-8 * max(1.0, np.max(np.abs(xo)))
     assert sum(hg["newton_iterations"]) > 5
+    # the same loop with the linear solves on the device: ex5's latent space is H1 (no element blocks), so the symmetric
+    # indefinite system goes through MINRES with the plain Jacobi preconditioner (madb_solver_pg_minres, nb = 0)
+    lin = lvpp.DeviceLinear(gi, "minres", rtol=1e-13, maxit=20000)
+    xd = np.zeros(nu + nl)
+    hd = lvpp.lvpp_solve(gi, lambda a: gfn.set_params([a]), lambda p: gi.set_param_field(2, p), rule, b, xd, sl, l1, max_pg=25, tol=1e-8,
+                         newton_kw=dict(nk, linear=lin))
+    print("ex5 device MINRES iterations per solve: min %d max %d" % (min(lin.linear_iterations), max(lin.linear_iterations)))
+    assert not hd["newton_failed"] and hd["newton_iterations"] == hg["newton_iterations"] and hd["pg_iterations"] == hg["pg_iterations"]
+    assert np.max(np.abs(xd - xg)) <= 1e-7 * max(1.0, np.max(np.abs(xg)))
