@@ -33,8 +33,18 @@ template <class Func, int ND, int NQ> struct Sf3Args
    double B[NQ][ND], G[NQ][ND], xq[NQ], wq[NQ];
 };
 
+// Minimum CTAs per SM asked of ptxas (a register cap).  Measured on config 3 (104^3 Q3, 125-thread CTAs): residual 6.86 / 4.94 /
+// 4.15 / 3.86 ms and action 7.82 / 5.79 / 5.03 / 5.24 ms for 1 / 3 / 4 / 5 CTAs (178 / 168 / 126 / 96 registers for the residual):
+// occupancy wins over spills up to 5 CTAs for the residual and 4 for the action (the default heuristic gave 126 / 142 registers).
+#ifndef MADB_SF3D_MINB_RES
+#define MADB_SF3D_MINB_RES 5
+#endif
+#ifndef MADB_SF3D_MINB_ACT
+#define MADB_SF3D_MINB_ACT 4
+#endif
+template <int MODE> constexpr int sf3_minb() { return (MODE & MODE_ACT) ? MADB_SF3D_MINB_ACT : MADB_SF3D_MINB_RES; }
 template <class Func, int ND, int NQ, int NEB, int MODE>
-__global__ void __launch_bounds__(NQ *NQ *NEB) k_sumfac3d(const __grid_constant__ Sf3Args<Func, ND, NQ> a)
+__global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(const __grid_constant__ Sf3Args<Func, ND, NQ> a)
 {
    constexpr int ND3 = ND * ND * ND;
    const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;

@@ -309,8 +309,20 @@ __device__ __forceinline__ void patch_compute_stage(const AsmArgs<Func, Cfg> &a,
 }
 
 /// One CTA per patch: PE = patch_pe(NVD) elements, NPART = element_parts threads per element.
+// Register cap of k_patch through the minimum CTAs per SM: kernels without the Jacobian (residual, action) are short of warps,
+// not of registers (MADB_PATCH_MINB_REGS: registers per thread the cap corresponds to; 0: ptxas' default)
+#ifndef MADB_PATCH_MINB_REGS
+#define MADB_PATCH_MINB_REGS 0
+#endif
+template <int THREADS, int MODE> constexpr int patch_minb()
+{
+   if ((MODE & MODE_JAC) != 0 || MADB_PATCH_MINB_REGS == 0) { return 1; }
+   const int b = 65536 / (MADB_PATCH_MINB_REGS * THREADS);
+   return b < 1 ? 1 : (b > 16 ? 16 : b);
+}
 template <class Func, class Cfg, int MODE, bool UNROLLQ>
-__global__ void __launch_bounds__(patch_pe_of<Func, Cfg>() * element_parts<Cfg, MODE>())
+__global__ void __launch_bounds__(patch_pe_of<Func, Cfg>() * element_parts<Cfg, MODE>(),
+                                  patch_minb<patch_pe_of<Func, Cfg>() * element_parts<Cfg, MODE>(), MODE>())
    k_patch(const __grid_constant__ AsmArgs<Func, Cfg> a, const __grid_constant__ PatchDev P)
 {
    constexpr int NVD = Cfg::NVD, NSYM = Cfg::NSYM, PE = patch_pe_of<Func, Cfg>(), LD = PE + 1, NPART = element_parts<Cfg, MODE>();
