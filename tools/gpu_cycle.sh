@@ -1,7 +1,7 @@
 #!/bin/bash
 # one GPU cycle for kernel work: parity subset, bench line, one full ncu capture of the dominant kernel
 # usage: tools/gpu_cycle.sh TAG [kernel-regex]
-TAG=$1; KRE=${2:-k_patch_img}
+TAG=$1; KRE=${2:-k_patch_ws}
 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -m gpu -q -x 2>&1 | tail -15 > gpurun_out/${TAG}_t.log
 tail -n 3 gpurun_out/${TAG}_t.log
 timeout 300 python bench.py --no-cpu > gpurun_out/${TAG}_b.json 2> gpurun_out/${TAG}_b.err
