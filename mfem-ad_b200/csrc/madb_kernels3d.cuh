@@ -55,9 +55,12 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
    __shared__ double sU[NEB][ND3];          // dofs, [iz][iy][ix]
    __shared__ double sV[(MODE & MODE_ACT) ? NEB : 1][(MODE & MODE_ACT) ? ND3 : 1];
    __shared__ double sX[NEB][8][3];
-   __shared__ double s0[NEB][NQ * NQ * ND]; // scratch: [iy|qy][qx][iz]
-   __shared__ double s1[NEB][NQ * NQ * ND];
-   __shared__ double s2[NEB][NQ * NQ * ND];
+   // scratch [iy|qy][qx][iz] with an ODD leading dimension in iz: consecutive threads (qx) are then LDZ doubles apart and hit
+   // different banks (with LDZ = ND = 4 the 8-byte accesses of a half-warp fell on 4 banks: 38 M conflicts per colour launch)
+   constexpr int LDZ = ND | 1;
+   __shared__ double s0[NEB][NQ * NQ * LDZ];
+   __shared__ double s1[NEB][NQ * NQ * LDZ];
+   __shared__ double s2[NEB][NQ * NQ * LDZ];
 
    if (active)
    {
@@ -93,8 +96,8 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
                sa = fma(a.B[tx][ix], uu, sa);
                sc = fma(a.G[tx][ix], uu, sc);
             }
-            s0[tz][(ty * NQ + tx) * ND + iz] = sa;
-            s1[tz][(ty * NQ + tx) * ND + iz] = sc;
+            s0[tz][(ty * NQ + tx) * LDZ + iz] = sa;
+            s1[tz][(ty * NQ + tx) * LDZ + iz] = sc;
          }
       }
       __syncthreads();
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
 #pragma unroll
          for (int iy = 0; iy < ND; iy++)
          {
-            const double av = s0[tz][(iy * NQ + tx) * ND + iz], cv = s1[tz][(iy * NQ + tx) * ND + iz];
+            const double av = s0[tz][(iy * NQ + tx) * LDZ + iz], cv = s1[tz][(iy * NQ + tx) * LDZ + iz];
             bb = fma(a.B[ty][iy], av, bb);
             gb = fma(a.B[ty][iy], cv, gb);
             bg = fma(a.G[ty][iy], av, bg);
@@ -237,9 +240,9 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
 #pragma unroll
       for (int iz = 0; iz < ND; iz++)
       {
-         s0[tz][(ty * NQ + tx) * ND + iz] = Z0[iz];
-         s1[tz][(ty * NQ + tx) * ND + iz] = Z1[iz];
-         s2[tz][(ty * NQ + tx) * ND + iz] = Z2[iz];
+         s0[tz][(ty * NQ + tx) * LDZ + iz] = Z0[iz];
+         s1[tz][(ty * NQ + tx) * LDZ + iz] = Z1[iz];
+         s2[tz][(ty * NQ + tx) * LDZ + iz] = Z2[iz];
       }
       __syncthreads();
       double Y0[ND], Y1[ND];
@@ -252,9 +255,9 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
 #pragma unroll
             for (int qy = 0; qy < NQ; qy++)
             {
-               y0 = fma(a.B[qy][ty], s0[tz][(qy * NQ + tx) * ND + iz], y0);
-               y1 = fma(a.G[qy][ty], s1[tz][(qy * NQ + tx) * ND + iz], y1);
-               y1 = fma(a.B[qy][ty], s2[tz][(qy * NQ + tx) * ND + iz], y1);
+               y0 = fma(a.B[qy][ty], s0[tz][(qy * NQ + tx) * LDZ + iz], y0);
+               y1 = fma(a.G[qy][ty], s1[tz][(qy * NQ + tx) * LDZ + iz], y1);
+               y1 = fma(a.B[qy][ty], s2[tz][(qy * NQ + tx) * LDZ + iz], y1);
             }
             Y0[iz] = y0; Y1[iz] = y1;
          }
@@ -265,8 +268,8 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
 #pragma unroll
          for (int iz = 0; iz < ND; iz++)
          {
-            s0[tz][(ty * NQ + tx) * ND + iz] = Y0[iz];
-            s1[tz][(ty * NQ + tx) * ND + iz] = Y1[iz];
+            s0[tz][(ty * NQ + tx) * LDZ + iz] = Y0[iz];
+            s1[tz][(ty * NQ + tx) * LDZ + iz] = Y1[iz];
          }
       }
       __syncthreads();
@@ -280,8 +283,8 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
 #pragma unroll
             for (int qx = 0; qx < NQ; qx++)
             {
-               out = fma(a.G[qx][tx], s0[tz][(ty * NQ + qx) * ND + iz], out);
-               out = fma(a.B[qx][tx], s1[tz][(ty * NQ + qx) * ND + iz], out);
+               out = fma(a.G[qx][tx], s0[tz][(ty * NQ + qx) * LDZ + iz], out);
+               out = fma(a.B[qx][tx], s1[tz][(ty * NQ + qx) * LDZ + iz], out);
             }
             const int m = a.vmap[(size_t)t * ND3 + (iz * ND + ty) * ND + tx];
             const int idx = m & 0x7fffffff;
