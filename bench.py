@@ -271,10 +271,6 @@ def run_gpu(args):
         ex = PAR.HaloExchange(*PAR.halo_lists(blk["l2g"], owner, rank, world), ctx=ctx, comm=comm)
     note("exchange lists ready")
 
-    def exchange():
-        if ex is not None:
-            ex.reverse(y)
-
     def step_device():
         if ex is None:
             gi.assemble(x, y, vals)
