@@ -296,7 +296,10 @@ __global__ void __launch_bounds__(NQ *NQ *NEB, sf3_minb<MODE>()) k_sumfac3d(cons
 
 template <class Func, int ND, int NQ> int launch_sumfac3d(const LaunchCtx &L, int mode)
 {
-   constexpr int NEB = (128 / (NQ * NQ) > 0) ? 128 / (NQ * NQ) : 1;
+#ifndef MADB_SF3D_CTA_THREADS
+#define MADB_SF3D_CTA_THREADS 128 // target threads per CTA: NEB = that / NQ^2 elements per CTA
+#endif
+   constexpr int NEB = (MADB_SF3D_CTA_THREADS / (NQ * NQ) > 0) ? MADB_SF3D_CTA_THREADS / (NQ * NQ) : 1;
    static thread_local Sf3Args<Func, ND, NQ> a;
    if (mode & MODE_JAC) { return -2; }
    a.e2n = L.e2n; a.coords = L.coords; a.vmap = L.vmap;
