@@ -64,6 +64,11 @@ __device__ __forceinline__ void bb_break(const int never_negative)
 {
    for (int k = never_negative; k < 0; k++) { __nanosleep(1); }
 }
+#ifndef MADB_QLOOP_UNROLL
+#define MADB_QLOOP_UNROLL 1 // unroll factor of the quadrature loop of configurations registered with UNROLLQ = false
+#endif
+#define MADB_PRAGMA_(x) _Pragma(#x)
+#define MADB_UNROLL(n) MADB_PRAGMA_(unroll n)
 #ifndef MADB_QPOINT_BB
 #define MADB_QPOINT_BB 1 // generic qpoint(): bit 0: boundary between the per-point phase (inputs, AD, pull-back) and the contraction for
                          // element matrices of more than 12 dofs (config 5: 4.51 -> 4.18 ms; config 4's 8-dof block loses 3 %, so
@@ -983,7 +988,7 @@ __device__ __forceinline__ void element_compute(const AsmArgs<Func, Cfg> &a, con
    }
    else
    {
-#pragma unroll 1
+      MADB_UNROLL(MADB_QLOOP_UNROLL)
       for (int q = 0; q < Cfg::NQ; q++) { qpoint<Func, Cfg, MODE, B0, B1>(a, tab, q, t, X, u, vdir, f, r, A, energy); }
    }
 }
