@@ -12,7 +12,7 @@ int launch_ifc_v(const PatchDev &P, double *vals, cudaStream_t stream)
    lv.stage = P.vstage;
    lv.out = vals;
    const int nb2 = (lv.n4 + 256 * IFC_U - 1) / (256 * IFC_U), nb3 = nb2 + (lv.ng + 255) / 256;
-   if (nb3 > 0) { k_ifc_reduce<<<nb3, 256, 0, stream>>>(ly, lv, 0, 0, nb2); }
+   if (nb3 > 0) { launch_pdl(k_ifc_reduce, nb3, 256, 0, stream, ly, lv, 0, 0, nb2); }
    return (int)cudaGetLastError();
 }
 } // namespace madb

@@ -77,6 +77,34 @@ template <int BAR, int NT> __device__ __forceinline__ void patch_bar(const int i
    else { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 }
 
+/// Programmatic dependent launch (MADB_PDL, default on): the element kernel and the interface reduction follow each
+/// other on one stream, step after step.  Launched with the programmatic-serialisation attribute, the CTAs of the next
+/// kernel are placed on SMs as the CTAs of the previous one exit (its tail and the launch latency overlap); every kernel
+/// of the chain waits (`griddepcontrol.wait`: completion and visibility of the whole previous grid) before it touches
+/// global memory, so the ordering of the data is that of a plain stream.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled()
+{
+   static const bool on = getenv("MADB_PDL") ? atoi(getenv("MADB_PDL")) != 0 : true;
+   return on;
+}
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), const int grid, const int block, const size_t smem, cudaStream_t stream, Args &&...args)
+{
+   cudaLaunchConfig_t cfg = {};
+   cfg.gridDim = dim3(grid);
+   cfg.blockDim = dim3(block);
+   cfg.dynamicSmemBytes = smem;
+   cfg.stream = stream;
+   cudaLaunchAttribute at[1];
+   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+   at[0].val.programmaticStreamSerializationAllowed = 1;
+   cfg.attrs = at;
+   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 /// Fold + gather + write-out of one staged patch by NT threads (tid = 0..NT-1).
 /// base: shared memory of the patch: element vectors at 0, element matrices at o_sa, y maps at o_yb, matrix maps at o_vb.
 /// Every loop is written in batches of U independent iterations (all index loads, then all value loads, then
@@ -338,6 +366,8 @@ __global__ void __launch_bounds__(patch_pe_of<Func, Cfg>() * element_parts<Cfg, 
    if (tid < (int)(sizeof(PatchDesc) / sizeof(int))) { ((int *)&D)[tid] = ((const int *)(P.desc + p))[tid]; }
    if (tid == 0) { mbar_init(&mbar, 1); }
    __syncthreads();
+   pdl_wait(); // (the patch descriptor above is set-up data: no dependence on the previous kernel)
+   pdl_trigger();
    const bool wy = HAS_Y && a.write_y, wv = HAS_V && a.write_vals;
 
    // shared-memory carve-up (byte offsets into smraw): staged element vectors | matrices | y maps | matrix maps
@@ -500,6 +530,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
       }
    }
    __syncthreads();
+   pdl_wait(); // the previous kernel of the stream (the interface reduction of the previous step) is complete
+   pdl_trigger();
 
    if (wg >= WG_C0)
    {
@@ -809,6 +841,8 @@ __device__ __forceinline__ void ifc_reduce_general(const IfcList &L, const int i
 static __global__ void __launch_bounds__(256) k_ifc_reduce(const IfcList A, const IfcList B, const int nb0, const int nb1,
                                                            const int nb2)
 {
+   pdl_wait();
+   pdl_trigger();
    const int blk = blockIdx.x, t = threadIdx.x;
    if (blk < nb0) { ifc_reduce_packed(A, blk * 256 * IFC_U + t); }
    else if (blk < nb1) { ifc_reduce_general(A, (blk - nb0) * 256 + t); }
@@ -881,7 +915,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
             static const int diag = getenv("MADB_DIAG") ? atoi(getenv("MADB_DIAG")) : 0;
             PatchDev Pd = P;
             Pd.diag = diag;
-            kws<<<grid, WS_THREADS, ws_bytes, L.stream>>>(a, Pd);
+            launch_pdl(kws, grid, WS_THREADS, (size_t)ws_bytes, L.stream, a, Pd);
             done = true;
          }
       }
@@ -889,7 +923,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
    if (!done)
    {
       if (wv && !P.vblob) { return (int)cudaErrorInvalidValue; } // the gather maps of this path were not built
-      kern<<<P.npatch, PE * NPART, smem_bytes, L.stream>>>(a, P);
+      launch_pdl(kern, P.npatch, PE * NPART, (size_t)smem_bytes, L.stream, a, P);
    }
    (void)ws_smem_set;
    (void)nsm;
@@ -902,7 +936,7 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
       if (!wv || L.defer_v_ifc) { lv.n4 = lv.ng = 0; }
       const int nb0 = (ly.n4 + 256 * IFC_U - 1) / (256 * IFC_U), nb1 = nb0 + (ly.ng + 255) / 256,
                 nb2 = nb1 + (lv.n4 + 256 * IFC_U - 1) / (256 * IFC_U), nb3 = nb2 + (lv.ng + 255) / 256;
-      if (nb3 > 0) { k_ifc_reduce<<<nb3, 256, 0, L.stream>>>(ly, lv, nb0, nb1, nb2); }
+      if (nb3 > 0) { launch_pdl(k_ifc_reduce, nb3, 256, 0, L.stream, ly, lv, nb0, nb1, nb2); }
    }
    return (int)cudaGetLastError();
 }
