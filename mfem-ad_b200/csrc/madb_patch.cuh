@@ -38,8 +38,38 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 {
    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef MADB_BLOB_EVICT_FIRST
+#define MADB_BLOB_EVICT_FIRST 0 // 1: the bulk copies of the per-patch maps (read once per launch) carry an L2 evict-first policy
+#endif
+#ifndef MADB_ST_CS
+#define MADB_ST_CS 0 // 1: the final CSR values are written with streaming stores (st.global.cs)
+#endif
+__device__ __forceinline__ void st_out(double *p, const double v)
+{
+#if MADB_ST_CS
+   __stcs(p, v);
+#else
+   *p = v;
+#endif
+}
+__device__ __forceinline__ void st_out2(double *p, const double a, const double b)
+{
+#if MADB_ST_CS
+   __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+#else
+   *reinterpret_cast<double2 *>(p) = make_double2(a, b);
+#endif
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
 {
+#if MADB_BLOB_EVICT_FIRST
+   unsigned long long pol;
+   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+                "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+                : "memory");
+   return;
+#endif
    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
                 : "memory");
@@ -221,11 +251,11 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
                if (g[u] >= 0)
                {
                   double *dst = vals + g[u] + 2 * lane;
-                  if (al16) { *reinterpret_cast<double2 *>(dst) = make_double2(vA[u], vB[u]); }
+                  if (al16) { st_out2(dst, vA[u], vB[u]); }
                   else
                   {
-                     dst[0] = vA[u];
-                     dst[1] = vB[u];
+                     st_out(dst, vA[u]);
+                     st_out(dst + 1, vB[u]);
                   }
                }
             }
@@ -251,7 +281,7 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
 #pragma unroll
             for (int u = 0; u < U; u++) { v[u] = MADB_SA(ix[u]); }
 #pragma unroll
-            for (int u = 0; u < U; u++) { if (gp[u] >= 0) { vals[gp[u]] = v[u]; } }
+            for (int u = 0; u < U; u++) { if (gp[u] >= 0) { st_out(vals + gp[u], v[u]); } }
          }
       }
          // irregular chunks: explicit positions (-1: none)
@@ -270,7 +300,7 @@ __device__ __forceinline__ void patch_drain(unsigned char *base, const int o_sa,
                v[u] = MADB_SA(ip[u * NW * 32]);
             }
 #pragma unroll
-            for (int u = 0; u < UI; u++) { if (g[u] >= 0) { vals[g[u]] = v[u]; } }
+            for (int u = 0; u < UI; u++) { if (g[u] >= 0) { st_out(vals + g[u], v[u]); } }
             ip += NW * UI * 32;
             op += NW * UI * 32;
          }
