@@ -38,6 +38,13 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 {
    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef MADB_WS_L2PF
+#define MADB_WS_L2PF 1 // 1: k_patch_ws compute warps prefetch the index lines of their next patch into L2 (config 2: -1.6 %); 2: the indices are
+                       // staged in shared memory by cp.async one patch ahead (measured: ptxas spills 136 B in the compute warps, +19 %)
+#endif
+#ifndef MADB_WS_L2PF_GEN
+#define MADB_WS_L2PF_GEN 1 // the same prefetch in the generic (not sum-factorised) branch of k_patch_ws (config 4 state block: 0.611 -> 0.597 ms)
+#endif
 #ifndef MADB_BLOB_EVICT_FIRST
 #define MADB_BLOB_EVICT_FIRST 0 // 1: the bulk copies of the per-patch maps (read once per launch) carry an L2 evict-first policy
 #endif
@@ -546,7 +553,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
    constexpr bool STAGE_U = (MADB_WS_STAGE_U != 0) && use_sf2d<Func, Cfg, MODE>() && !(MADB_WS_PREFETCH) && !(MADB_WS_JOINT);
    constexpr int U_BYTES = STAGE_U ? patch_al16(NVD * PE * 8) : 0; // staged dof values [NVD][PE]
    const int o_u = SR_BYTES + SA_BYTES + P.max_yg + P.max_yf + P.max_vg + P.max_vf;
-   const int wg_bytes = o_u + U_BYTES;
+   // MADB_WS_L2PF == 2: the 4 vertex + NVD dof indices of every element of the NEXT patch, staged by cp.async ([k][element])
+   constexpr int IDX_BYTES = (MADB_WS_L2PF == 2 && use_sf2d<Func, Cfg, MODE>()) ? patch_al16((4 + NVD) * PE * 4) : 0;
+   const int o_idx = o_u + U_BYTES;
+   const int wg_bytes = o_idx + IDX_BYTES;
    if (threadIdx.x == 0)
    {
       for (int k = 0; k < 2; k++)
@@ -643,7 +653,70 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
             }
             else
             {
+#if MADB_WS_L2PF == 2
+               // The indices of this thread's element were copied to shared memory during the previous patch (cp.async: no
+               // registers held, nobody waits): the gather is ONE round trip (values) instead of two dependent ones.  Every
+               // thread reads only the slots it copied itself (cp.async.wait_group): no barrier.
+               {
+                  int *ix = (int *)(base + o_idx);
+                  auto stage_idx = [&](const int pn)
+                  {
+                     const int tn = pn * PE + tid;
+                     if (pn < P.npatch && tn < a.end)
+                     {
+#pragma unroll
+                        for (int k = 0; k < 4; k++)
+                        {
+                           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(ix + k * PE + tid)), "l"(a.e2n + (size_t)k * a.stride + tn) : "memory");
+                        }
+#pragma unroll
+                        for (int i = 0; i < NVD; i++)
+                        {
+                           asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(ix + (4 + i) * PE + tid)), "l"(a.vmap + (size_t)i * a.stride + tn) : "memory");
+                        }
+                     }
+                     asm volatile("cp.async.commit_group;" ::: "memory");
+                  };
+                  if (it == 0) { stage_idx(p); }
+                  asm volatile("cp.async.wait_group 0;" ::: "memory");
+                  if (valid)
+                  {
+                     constexpr int ND1 = Cfg::template field<0>::ND1D;
+                     int nn[4], nd[NVD];
+#pragma unroll
+                     for (int k = 0; k < 4; k++) { nn[k] = ix[k * PE + tid]; }
+#pragma unroll
+                     for (int i = 0; i < NVD; i++) { nd[i] = ix[(4 + i) * PE + tid] & 0x7fffffff; }
+#pragma unroll
+                     for (int k = 0; k < 4; k++)
+                     {
+                        sf_in.X[k][0] = a.coords[(size_t)nn[k] * 2];
+                        sf_in.X[k][1] = a.coords[(size_t)nn[k] * 2 + 1];
+                     }
+#pragma unroll
+                     for (int i = 0; i < NVD; i++) { sf_in.u[i / ND1][i % ND1] = a.x[nd[i]]; }
+                  }
+                  stage_idx(((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w);
+               }
+#elif MADB_WS_L2PF
+               // the element -> vertex / dof index lines of this warp's elements in the NEXT patch: into L2 now, so that the
+               // first of the two dependent loads of the next gather does not go to DRAM (no registers held)
+               {
+                  const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+                  const int tn = pn * PE + tid;
+                  const int ln = tid & 31;
+                  if (pn < P.npatch && tn < a.end && (ln == 0 || ln == 31))
+                  {
+#pragma unroll
+                     for (int k = 0; k < 4; k++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.e2n + (size_t)k * a.stride + tn)); }
+#pragma unroll
+                     for (int i = 0; i < NVD; i++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vmap + (size_t)i * a.stride + tn)); }
+                  }
+               }
+#endif
+#if MADB_WS_L2PF != 2
                if (valid) { sf2d_gather<Func, Cfg, false>(a, t, sf_in); }
+#endif
             }
             if (valid && !(P.diag & 2))
             {
@@ -678,6 +751,26 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
          else
          {
             double A[NSYM], energy;
+#if MADB_WS_L2PF_GEN
+            // index lines of this warp's elements in the next patch into L2 (as in the sum-factorised branch)
+            {
+               const int pn = ((it + 1) * (int)gridDim.x + (int)blockIdx.x) * 2 + w;
+               const int tn = pn * PE + tid;
+               const int ln = tid & 31;
+               if (pn < P.npatch && tn < a.end && (ln == 0 || ln == 31))
+               {
+#pragma unroll
+                  for (int k = 0; k < Cfg::NGN; k++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.e2n + (size_t)k * a.stride + tn)); }
+#pragma unroll
+                  for (int i = 0; i < NVD; i++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vmap + (size_t)i * a.stride + tn)); }
+                  if constexpr (Cfg::NDOF_ALL > NVD)
+                  {
+#pragma unroll
+                     for (int i = 0; i < Cfg::NDOF_ALL - NVD; i++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pmap + (size_t)i * a.stride + tn)); }
+                  }
+               }
+            }
+#endif
             if (valid) { element_compute<Func, Cfg, MODE, UNROLLQ>(a, a.tab, t, r, A, energy); }
             mbar_wait(&bar_empty[w], par);
             if (valid)
@@ -931,7 +1024,8 @@ int launch_patch_mode(const AsmArgs<Func, Cfg> &a, const LaunchCtx &L)
          auto kws = k_patch_ws<Func, Cfg, UNROLLQ>;
          constexpr bool STAGE_U = (MADB_WS_STAGE_U != 0) && use_sf2d<Func, Cfg, MODE>() && !(MADB_WS_PREFETCH) && !(MADB_WS_JOINT);
          const int ws_bytes = 2 * (patch_al16(Cfg::NVD * PATCH_LD * 8) + patch_al16(Cfg::NSYM * PATCH_LD * 8) + P.max_yg + P.max_yf + P.max_vg + P.max_vf +
-                                   (STAGE_U ? patch_al16(Cfg::NVD * PATCH_PE * 8) : 0)) + 16;
+                                   (STAGE_U ? patch_al16(Cfg::NVD * PATCH_PE * 8) : 0) +
+                                   ((MADB_WS_L2PF == 2 && use_sf2d<Func, Cfg, MODE>()) ? patch_al16((4 + Cfg::NVD) * PATCH_PE * 4) : 0)) + 16;
          if (nsm == 0) { cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev); }
          if (ws_bytes <= 226 * 1024)
          {
