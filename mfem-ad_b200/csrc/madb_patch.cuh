@@ -42,6 +42,18 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 #define MADB_WS_L2PF 1 // 1: k_patch_ws compute warps prefetch the index lines of their next patch into L2 (config 2: -1.6 %); 2: the indices are
                        // staged in shared memory by cp.async one patch ahead (measured: ptxas spills 136 B in the compute warps, +19 %)
 #endif
+#ifndef MADB_WS_L1PF
+#define MADB_WS_L1PF 0 // writers warm the L1 with the values of the compute warpgroup's next gather: 1 prefetch.global.L1, 2 discarded loads
+#endif
+__device__ __forceinline__ void l1_touch(const double *p)
+{
+#if MADB_WS_L1PF == 2
+   double d;
+   asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(d) : "l"(p));
+#else
+   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 #ifndef MADB_WS_L2PF_GEN
 #define MADB_WS_L2PF_GEN 1 // the same prefetch in the generic (not sum-factorised) branch of k_patch_ws (config 4 state block: 0.611 -> 0.597 ms)
 #endif
@@ -886,6 +898,31 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_patch_ws(const __grid_constan
                stage_u(w, pn);
             }
          }
+#if MADB_WS_L1PF
+         // While the compute warpgroup finishes patch `it`, warm this SM's L1 with the vertex coordinates and dof values its
+         // next gather (patch pn) will load: the index lines are in L2 already (MADB_WS_L2PF), the writers wait here anyway.
+         if constexpr (use_sf2d<Func, Cfg, MODE>() && !JOINT)
+         {
+            const int tn = pn * PE + wtid;
+            if (more && tn < a.end)
+            {
+               int n4[4];
+#pragma unroll
+               for (int k = 0; k < 4; k++) { n4[k] = __ldg(a.e2n + (size_t)k * a.stride + tn); }
+#pragma unroll
+               for (int k = 0; k < 4; k++) { l1_touch(a.coords + (size_t)n4[k] * 2); }
+#pragma unroll
+               for (int i0 = 0; i0 < NVD; i0 += 5)
+               {
+                  int d5[5];
+#pragma unroll
+                  for (int i = 0; i < 5; i++) { if (i0 + i < NVD) { d5[i] = __ldg(a.vmap + (size_t)(i0 + i) * a.stride + tn) & 0x7fffffff; } }
+#pragma unroll
+                  for (int i = 0; i < 5; i++) { if (i0 + i < NVD) { l1_touch(a.x + d5[i]); } }
+               }
+            }
+         }
+#endif
          mbar_wait(&bar_blobF[w], it & 1); // fold lists of this patch
          mbar_wait(&bar_full[w], it & 1);  // the compute warpgroup has staged the patch
          auto after_fold = [&]()
