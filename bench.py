@@ -40,8 +40,8 @@ EPS = 0.5
 P = 2
 FP64_INSTR = 2278  # DFMA+DMUL+DADD executed per element by k_patch_ws<minsurf,Q2> (ncu smsp__sass_thread_inst_executed_op_d*, r02 v1)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_patch_ws launch of this workload (1000x1000),
-# ncu --set full capture summarised in profiles/r02_k_patch_ws.md (final build: 409.0 MB read + 521.3 MB written)
-NCU_TRAFFIC_BYTES = {1000: 930328320}
+# ncu --set full capture of the final build, profiles/r02_v7_k_patch_ws_full.txt (409.5 MB read + 521.8 MB written)
+NCU_TRAFFIC_BYTES = {1000: 931366912}
 
 
 def peaks():
