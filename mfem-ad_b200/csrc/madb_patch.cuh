@@ -42,6 +42,9 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned
 #define MADB_WS_L2PF 1 // 1: k_patch_ws compute warps prefetch the index lines of their next patch into L2 (config 2: -1.6 %); 2: the indices are
                        // staged in shared memory by cp.async one patch ahead (measured: ptxas spills 136 B in the compute warps, +19 %)
 #endif
+#ifndef MADB_PATCH_L2PF
+#define MADB_PATCH_L2PF 0 // k_patch: prefetch distance (in waves of one CTA per SM) of the index lines of a later patch; 0: off
+#endif
 #ifndef MADB_WS_L1PF
 #define MADB_WS_L1PF 0 // writers warm the L1 with the values of the compute warpgroup's next gather: 1 prefetch.global.L1, 2 discarded loads
 #endif
@@ -417,6 +420,30 @@ __global__ void __launch_bounds__(patch_pe_of<Func, Cfg>() * element_parts<Cfg, 
    __syncthreads();
    pdl_wait(); // (the patch descriptor above is set-up data: no dependence on the previous kernel)
    pdl_trigger();
+#if MADB_PATCH_L2PF
+   // index lines (vertices, dofs, parameter dofs) of the patch that starts MADB_PATCH_L2PF waves of CTAs later: into L2 now,
+   // so that the first of the two dependent loads of ITS gather is not a DRAM access (all warps of a CTA gather at the same time:
+   // with one CTA per SM nothing covers that latency)
+   {
+      unsigned nsm;
+      asm("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+      const int pn = p + (int)nsm * MADB_PATCH_L2PF;
+      const int tn = pn * PE + l, ln = tid & 31;
+      if (part == 0 && pn < (int)gridDim.x && tn < a.end && (ln == 0 || ln == 31))
+      {
+#pragma unroll
+         for (int k = 0; k < Cfg::NGN; k++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.e2n + (size_t)k * a.stride + tn)); }
+#pragma unroll
+         for (int i = 0; i < NVD; i++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.vmap + (size_t)i * a.stride + tn)); }
+         if constexpr (Cfg::NDOF_ALL > NVD)
+         {
+#pragma unroll
+            for (int i = 0; i < Cfg::NDOF_ALL - NVD; i++) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pmap + (size_t)i * a.stride + tn)); }
+         }
+      }
+      if (tid == 32 && pn < (int)gridDim.x) { asm volatile("prefetch.global.L2 [%0];" ::"l"(P.desc + pn)); }
+   }
+#endif
    const bool wy = HAS_Y && a.write_y, wv = HAS_V && a.write_vals;
 
    // shared-memory carve-up (byte offsets into smraw): staged element vectors | matrices | y maps | matrix maps
